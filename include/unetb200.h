@@ -1,0 +1,139 @@
+/*
+ * unetb200 -- C ABI of the B200 (sm_100a) U-Net forward library.
+ *
+ * This is the drop-in boundary for the one hot path of
+ * tingyu-c/TW-invoice-unet-ocr-llm: `UNet.forward` (reference unet_model.py:55-86)
+ * as called by `inference.run_unet` (reference inference.py:58-79).  The reference
+ * has no FFI of its own (it calls torch.nn); the host-side mirror in
+ * tw_invoice_unet_ocr_llm_b200/{unet_model,inference}.py binds these entry points
+ * with ctypes.  Signatures use plain pointers and sizes only; the caller owns all
+ * device memory (weights blob, workspace, inputs, outputs) and passes raw device
+ * pointers plus the CUDA stream to enqueue on.
+ *
+ * Every function returns 0 on success or a non-zero UNETB200_E* code;
+ * unetb200_last_error() then returns a thread-local message.  Nothing aborts.
+ */
+#ifndef UNETB200_H
+#define UNETB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UNETB200_ABI_VERSION 1
+
+enum {
+    UNETB200_OK = 0,
+    UNETB200_EINVAL = 1,   /* bad argument (shape not divisible by 16, null pointer, ...) */
+    UNETB200_ECUDA = 2,    /* a CUDA runtime/driver call failed */
+    UNETB200_EARCH = 3,    /* device is not compute capability 10.x (no fallback exists) */
+    UNETB200_ENOMEM = 4    /* workspace too small */
+};
+
+/* layer kinds in the packed-weights table */
+enum { UNETB200_STEM = 0, UNETB200_CONV3X3 = 1, UNETB200_CONVT2X2 = 2, UNETB200_HEAD = 3 };
+
+/* input formats accepted by unetb200_forward */
+enum {
+    UNETB200_X_F32_NCHW = 0, /* float32 [N,C,H,W] in [0,1] -- what inference.preprocess returns (inference.py:36-42) */
+    UNETB200_X_U8_NHWC = 1   /* uint8 [N,H,W,C], scaled by /255 in the first kernel (inference.py:36) */
+};
+
+/* A-operand staging strategy of the tensor-core conv kernel (see csrc/conv_tc.cuh) */
+enum { UNETB200_A_TAP = 0, UNETB200_A_COL3 = 1, UNETB200_A_HALO = 2 };
+
+/* UNet(n_channels, n_classes) of reference unet_model.py:24; base_width is the 64 of :29. */
+typedef struct {
+    int32_t n_channels; /* 1, 3 or 4 */
+    int32_t n_classes;  /* 1..8 */
+    int32_t base_width; /* must be 64 */
+} unetb200_arch_t;
+
+/* One row of the packed-weights table.  Order == execution order of UNet.forward. */
+typedef struct {
+    char name[32];      /* state_dict prefix of the conv, e.g. "down1.net.0", "up4", "out_conv" */
+    char bn_name[32];   /* state_dict prefix of the BatchNorm folded into it, or "" */
+    int32_t kind;       /* UNETB200_STEM / CONV3X3 / CONVT2X2 / HEAD */
+    int32_t cin, cout;
+    int32_t level;      /* spatial level of the layer INPUT: 0 = H x W, k = H/2^k */
+    uint64_t w_off, w_bytes; /* byte range of the packed weights in the blob */
+    uint64_t b_off, b_bytes; /* byte range of the fp32 (folded) bias in the blob */
+} unetb200_layer_t;
+
+typedef struct unetb200_handle_s* unetb200_handle_t;
+
+int unetb200_abi_version(void);
+const char* unetb200_last_error(void);
+
+/* ---- packed weights: layout + device-side fold/pack (replaces nothing in the
+ *      reference; it is the "BN fold + repack" step after inference.py:21) ---- */
+int unetb200_num_layers(const unetb200_arch_t* arch);
+int unetb200_layer_info(const unetb200_arch_t* arch, int index, unetb200_layer_t* out);
+uint64_t unetb200_packed_bytes(const unetb200_arch_t* arch);
+
+/* Fold BatchNorm (pass NULL gamma/beta/mean/var for "no BN") and write layer `index`
+ * of the blob at `blob_dev`.  All pointers are device pointers to fp32 tensors laid
+ * out as PyTorch stores them (Conv2d: [Cout,Cin,kh,kw]; ConvTranspose2d: [Cin,Cout,2,2]). */
+int unetb200_pack_layer(const unetb200_arch_t* arch, int index, const float* weight,
+                        const float* bias, const float* bn_gamma, const float* bn_beta,
+                        const float* bn_mean, const float* bn_var, float bn_eps, void* blob_dev,
+                        void* stream);
+
+/* ---- model handle ---- */
+/* Replaces the model the reference builds in inference.py:17-24.  `blob_dev` (borrowed)
+ * must outlive the handle.  Fails with UNETB200_EARCH on anything but sm_100. */
+int unetb200_create(const unetb200_arch_t* arch, const void* blob_dev, uint64_t blob_bytes,
+                    int device, unetb200_handle_t* out);
+int unetb200_destroy(unetb200_handle_t h);
+
+/* options: "amode" (UNETB200_A_*), "bn_max" (64/128/256), "profile" (0/1) */
+int unetb200_set_option(unetb200_handle_t h, const char* key, int value);
+int unetb200_get_option(unetb200_handle_t h, const char* key, int* value);
+
+uint64_t unetb200_workspace_bytes(unetb200_handle_t h, int n, int height, int width);
+
+/* UNet.forward (unet_model.py:55-86) + the sigmoid/threshold of inference.py:72-79.
+ *   x            device pointer, format `x_fmt`, N x C x H x W with H, W divisible by 16
+ *   workspace    device scratch of >= unetb200_workspace_bytes(h, N, H, W) bytes
+ *   logits       nullable; float32 [N, n_classes, H, W] raw logits (what UNet.forward returns)
+ *   mask         nullable; uint8   [N, n_classes, H, W], 1 where logit > logit_thr[c]
+ *                (logit_thr[c] = ln(t/(1-t)) reproduces sigmoid(logit) > t)
+ *   logit_thr    host pointer to n_classes floats (may be NULL if mask is NULL)
+ *   stream       cudaStream_t to enqueue on (NULL = legacy default stream)
+ * Asynchronous: returns after enqueueing. */
+int unetb200_forward(unetb200_handle_t h, const void* x, int x_fmt, int n, int height, int width,
+                     void* workspace, uint64_t workspace_bytes, float* logits, uint8_t* mask,
+                     const float* logit_thr, void* stream);
+
+/* Per-layer device times (ms) of the last forward run with option "profile" = 1.
+ * Synchronises the stream's events.  `ms` has room for `count` floats. */
+int unetb200_layer_times(unetb200_handle_t h, float* ms, int count);
+/* Number of kernels the last forward enqueued. */
+int unetb200_last_launch_count(unetb200_handle_t h);
+
+/* ---- single-kernel entry points (unit parity tests; same code paths as forward) ---- */
+/* 3x3 conv + bias + optional ReLU over NHWC bf16.  src1/c1 = second (skip) source or NULL/0.
+ * w_packed: [9][cout][c0+c1] bf16, bias fp32[cout].  pool_out nullable (2x2 max-pool 2nd output).
+ * bn in {64,128,256}, amode in UNETB200_A_*, desc_mode in {0,1} (A_HALO descriptor variant). */
+int unetb200_conv3x3(const void* src0, int c0, const void* src1, int c1, const void* w_packed,
+                     const float* bias, int n, int height, int width, int cout, int relu, void* out,
+                     void* pool_out, int bn, int amode, int desc_mode, void* stream);
+/* 3x3 conv (cout = 64) + ReLU with the 1x1 head and threshold fused into the epilogue. */
+int unetb200_conv3x3_head(const void* src0, int c0, const void* w_packed, const float* bias,
+                          const float* head_w, const float* head_b, int n_classes, int n, int height,
+                          int width, float* logits, uint8_t* mask, const float* logit_thr, int amode,
+                          int desc_mode, void* stream);
+/* ConvTranspose2d(k=2,s=2): src [N,H,W,cin] bf16 -> out [N,2H,2W,cout] bf16. w_packed [4*cout][cin]. */
+int unetb200_convt2x2(const void* src, int cin, const void* w_packed, const float* bias, int n,
+                      int height, int width, int cout, void* out, int bn, void* stream);
+/* First conv (n_channels -> 64) + ReLU: x (format x_fmt) -> out [N,H,W,64] bf16. w fp32 [9*cin][64]. */
+int unetb200_stem(const void* x, int x_fmt, int cin, const float* w, const float* bias, int n,
+                  int height, int width, void* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UNETB200_H */

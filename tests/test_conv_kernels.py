@@ -1,0 +1,158 @@
+"""Unit parity of each CUDA kernel, called through the C ABI, against torch fp32 ops on the
+same bf16-rounded operands ("unit" level of the test pyramid).
+
+Tolerance: the kernels accumulate in fp32 and round once to bf16 on store, so the result
+must equal the fp32 reference rounded to bf16 up to accumulation-order noise:
+|err| <= 2^-7 * |ref| + 2e-3 (bf16 has 8 significand bits; half-ulp = 2^-9 relative).
+"""
+import ctypes as C
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _nat():
+    from tw_invoice_unet_ocr_llm_b200 import _native as nat
+    return nat
+
+
+def _nhwc_bf16(t):          # [N,C,H,W] fp32 -> [N,H,W,C] bf16 contiguous
+    return t.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+
+
+def _to_nchw_f32(t):        # [N,H,W,C] bf16 -> [N,C,H,W] fp32
+    return t.float().permute(0, 3, 1, 2).contiguous()
+
+
+def _close(got, ref, what):
+    err = (got - ref).abs()
+    tol = ref.abs() * 2.0 ** -7 + 2e-3
+    bad = err > tol
+    assert not bad.any(), (f"{what}: {int(bad.sum())} / {bad.numel()} elements out of tolerance, "
+                           f"max err {float(err.max()):.4g}, first bad idx {bad.nonzero()[0].tolist()}")
+
+
+def _pack3x3(w):            # [Cout,Cin,3,3] -> [9][Cout][Cin] bf16
+    return w.permute(2, 3, 0, 1).reshape(9, w.shape[0], w.shape[1]).contiguous().to(torch.bfloat16)
+
+
+import os
+
+AMODES = [int(v) for v in os.environ.get("UNETB200_TEST_AMODES", "0,1,2").split(",")]
+
+
+@pytest.mark.parametrize("amode", AMODES)
+@pytest.mark.parametrize("cin,cout,bn,n,h,w", [
+    (64, 64, 64, 2, 32, 24),
+    (128, 128, 128, 1, 48, 40),
+    (64, 256, 256, 1, 16, 16),
+    (192, 128, 64, 1, 20, 12),      # partial tiles in both directions
+    (64, 64, 64, 3, 2, 2),          # smaller than one tile (deepest level of a 32x32 input)
+])
+def test_conv3x3(cuda_dev, amode, cin, cout, bn, n, h, w):
+    nat = _nat()
+    g = torch.Generator(device="cpu").manual_seed(cin * 7 + cout + h)
+    x = torch.randn((n, cin, h, w), generator=g).to(cuda_dev)
+    wt = (torch.randn((cout, cin, 3, 3), generator=g) / (3.0 * cin ** 0.5)).to(cuda_dev)
+    b = torch.randn((cout,), generator=g).to(cuda_dev)
+    xb, wb = _nhwc_bf16(x), _pack3x3(wt)
+    out = torch.full((n, h, w, cout), float("nan"), dtype=torch.bfloat16, device=cuda_dev)
+    nat.check(nat.lib().unetb200_conv3x3(xb.data_ptr(), cin, None, 0, wb.data_ptr(), b.data_ptr(),
+                                         n, h, w, cout, 1, out.data_ptr(), None, bn, amode, 0, None))
+    torch.cuda.synchronize()
+    ref = F.relu(F.conv2d(_to_nchw_f32(xb), wb.float().reshape(3, 3, cout, cin).permute(2, 3, 0, 1),
+                          b, padding=1))
+    _close(_to_nchw_f32(out), ref, f"conv3x3 amode={amode}")
+
+
+@pytest.mark.parametrize("amode", AMODES)
+def test_conv3x3_two_sources_and_pool(cuda_dev, amode):
+    """cat([up, skip]) as two K ranges + fused 2x2 max-pool second output (unet_model.py:57,71)."""
+    nat = _nat()
+    n, c0, c1, cout, h, w = 2, 64, 128, 128, 32, 16
+    g = torch.Generator(device="cpu").manual_seed(5)
+    x0 = torch.randn((n, c0, h, w), generator=g).to(cuda_dev)
+    x1 = torch.randn((n, c1, h, w), generator=g).to(cuda_dev)
+    wt = (torch.randn((cout, c0 + c1, 3, 3), generator=g) / (3.0 * (c0 + c1) ** 0.5)).to(cuda_dev)
+    b = torch.randn((cout,), generator=g).to(cuda_dev)
+    x0b, x1b, wb = _nhwc_bf16(x0), _nhwc_bf16(x1), _pack3x3(wt)
+    out = torch.full((n, h, w, cout), float("nan"), dtype=torch.bfloat16, device=cuda_dev)
+    pool = torch.full((n, h // 2, w // 2, cout), float("nan"), dtype=torch.bfloat16, device=cuda_dev)
+    nat.check(nat.lib().unetb200_conv3x3(x0b.data_ptr(), c0, x1b.data_ptr(), c1, wb.data_ptr(),
+                                         b.data_ptr(), n, h, w, cout, 1, out.data_ptr(),
+                                         pool.data_ptr(), 128, amode, 0, None))
+    torch.cuda.synchronize()
+    xin = torch.cat([_to_nchw_f32(x0b), _to_nchw_f32(x1b)], dim=1)
+    ref = F.relu(F.conv2d(xin, wb.float().reshape(3, 3, cout, c0 + c1).permute(2, 3, 0, 1), b, padding=1))
+    _close(_to_nchw_f32(out), ref, f"dual-source conv amode={amode}")
+    # pooled output must be exactly the max-pool of the stored (bf16) full-resolution output
+    assert torch.equal(_to_nchw_f32(pool), F.max_pool2d(_to_nchw_f32(out), 2))
+
+
+@pytest.mark.parametrize("cin,cout,bn", [(128, 64, 128), (256, 128, 64), (128, 64, 256)])
+def test_convt2x2(cuda_dev, cin, cout, bn):
+    nat = _nat()
+    n, h, w = 2, 16, 24
+    g = torch.Generator(device="cpu").manual_seed(cin + cout)
+    x = torch.randn((n, cin, h, w), generator=g).to(cuda_dev)
+    wt = (torch.randn((cin, cout, 2, 2), generator=g) / cin ** 0.5).to(cuda_dev)
+    b = torch.randn((cout,), generator=g).to(cuda_dev)
+    xb = _nhwc_bf16(x)
+    wb = wt.permute(2, 3, 1, 0).reshape(4 * cout, cin).contiguous().to(torch.bfloat16)   # [(a,b,co)][ci]
+    out = torch.full((n, 2 * h, 2 * w, cout), float("nan"), dtype=torch.bfloat16, device=cuda_dev)
+    nat.check(nat.lib().unetb200_convt2x2(xb.data_ptr(), cin, wb.data_ptr(), b.data_ptr(), n, h, w,
+                                          cout, out.data_ptr(), bn, None))
+    torch.cuda.synchronize()
+    wref = wb.float().reshape(2, 2, cout, cin).permute(3, 2, 0, 1).contiguous()
+    ref = F.conv_transpose2d(_to_nchw_f32(xb), wref, b, stride=2)
+    _close(_to_nchw_f32(out), ref, "convT2x2")
+
+
+@pytest.mark.parametrize("fmt", ["f32", "u8"])
+def test_stem(cuda_dev, fmt):
+    nat = _nat()
+    n, h, w = 2, 40, 48
+    g = torch.Generator(device="cpu").manual_seed(11)
+    u8 = torch.randint(0, 256, (n, h, w, 3), generator=g, dtype=torch.uint8)
+    xf = (u8.float() / 255.0).permute(0, 3, 1, 2).contiguous().to(cuda_dev)
+    wt = (torch.randn((64, 3, 3, 3), generator=g) / 5.0).to(cuda_dev)
+    b = torch.randn((64,), generator=g).to(cuda_dev)
+    wp = wt.permute(2, 3, 1, 0).reshape(27, 64).contiguous()       # [(ky,kx,ci)][co] fp32
+    out = torch.full((n, h, w, 64), float("nan"), dtype=torch.bfloat16, device=cuda_dev)
+    src = xf if fmt == "f32" else u8.to(cuda_dev)
+    nat.check(nat.lib().unetb200_stem(src.data_ptr(), 0 if fmt == "f32" else 1, 3, wp.data_ptr(),
+                                      b.data_ptr(), n, h, w, out.data_ptr(), None))
+    torch.cuda.synchronize()
+    ref = F.relu(F.conv2d(xf, wt, b, padding=1))
+    _close(_to_nchw_f32(out), ref, f"stem {fmt}")
+
+
+@pytest.mark.parametrize("amode", AMODES)
+def test_conv3x3_head(cuda_dev, amode):
+    """conv1.net.3 + out_conv 1x1 + logit-space threshold in one kernel (unet_model.py:86,
+    inference.py:72-79)."""
+    nat = _nat()
+    n, h, w, ncls = 2, 32, 32, 3
+    g = torch.Generator(device="cpu").manual_seed(3)
+    x = torch.randn((n, 64, h, w), generator=g).to(cuda_dev)
+    wt = (torch.randn((64, 64, 3, 3), generator=g) / 24.0).to(cuda_dev)
+    b = torch.randn((64,), generator=g).to(cuda_dev)
+    hw = torch.randn((ncls, 64), generator=g).to(cuda_dev) / 4.0
+    hb = torch.randn((ncls,), generator=g).to(cuda_dev)
+    xb, wb = _nhwc_bf16(x), _pack3x3(wt)
+    logits = torch.full((n, ncls, h, w), float("nan"), dtype=torch.float32, device=cuda_dev)
+    mask = torch.full((n, ncls, h, w), 7, dtype=torch.uint8, device=cuda_dev)
+    thr = (C.c_float * ncls)(-0.5, 0.0, 0.7)
+    nat.check(nat.lib().unetb200_conv3x3_head(xb.data_ptr(), 64, wb.data_ptr(), b.data_ptr(),
+                                              hw.data_ptr(), hb.data_ptr(), ncls, n, h, w,
+                                              logits.data_ptr(), mask.data_ptr(), thr, amode, 0, None))
+    torch.cuda.synchronize()
+    feat = F.relu(F.conv2d(_to_nchw_f32(xb), wb.float().reshape(3, 3, 64, 64).permute(2, 3, 0, 1), b, padding=1))
+    ref = F.conv2d(feat, hw.reshape(ncls, 64, 1, 1), hb)
+    err = (logits - ref).abs().max().item()
+    assert err < 2e-3, f"fused head logits max err {err}"
+    thr_t = torch.tensor(list(thr), device=cuda_dev).view(1, ncls, 1, 1)
+    assert torch.equal(mask, (logits > thr_t).to(torch.uint8)), "mask != (logits > thr)"

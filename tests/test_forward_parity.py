@@ -1,0 +1,125 @@
+"""Integration parity: the CUDA forward, called through the drop-in ``UNet`` module and the
+C ABI, against the CPU fp32 oracle on the same seeded inputs.
+
+Stated tolerance (north_star: "logit max-abs/rel error, >= 99.9 % pixel agreement plus mask
+IoU"), for bf16 storage / fp32 accumulation through 23 layers:
+  * logit max-abs error  <= 0.35   and  max-abs / std(logits) <= 0.25
+  * logit mean-abs error <= 0.04
+  * binarised-mask pixel agreement >= 99.9 % at 512x512 (>= 99.7 % on tiny inputs, where a
+    handful of near-threshold pixels is already 0.1 %)
+  * every pixel with |logit - threshold| > 0.25 agrees
+  * per-class IoU >= 0.95
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _model(fixture_state, dev):
+    from tw_invoice_unet_ocr_llm_b200.unet_model import UNet
+    m = UNet(n_channels=3, n_classes=3)
+    m.load_state_dict(fixture_state)          # strict, 136 keys
+    return m.to(dev).eval()
+
+
+@pytest.fixture(scope="module")
+def model(fixture_state, cuda_dev):
+    return _model(fixture_state, cuda_dev)
+
+
+def _check(rep, min_agree):
+    assert rep["max_abs"] <= 0.35, rep
+    assert rep["max_abs_over_std"] <= 0.25, rep
+    assert rep["mean_abs"] <= 0.04, rep
+    assert rep["agreement"] >= min_agree, rep
+    assert rep["agreement_outside_0.25"] == 1.0, rep
+    assert min(rep["iou"]) >= 0.95, rep
+
+
+@pytest.mark.parametrize("n,h,w,seed", [(2, 64, 64, 42), (1, 32, 48, 43), (3, 16, 16, 44), (1, 96, 80, 45)])
+def test_logits_small(model, fixture_state, cuda_dev, n, h, w, seed):
+    from oracle.unet_oracle import oracle_forward, parity_report
+    from tw_invoice_unet_ocr_llm_b200.synthetic import synthetic_invoices
+    x = synthetic_invoices(n, h, w, seed=seed)
+    with torch.no_grad():
+        z = model(x.to(cuda_dev))
+    assert z.shape == (n, 3, h, w) and z.dtype == torch.float32 and z.is_cuda
+    rep = parity_report(oracle_forward(fixture_state, x), z)
+    print(f"parity {n}x{h}x{w}: {rep}")
+    _check(rep, 0.997)
+
+
+def test_logits_512(model, fixture_state, cuda_dev):
+    """BASELINE.json configs[0] shape: one invoice at inference.py's native 512x512."""
+    from oracle.unet_oracle import oracle_forward, parity_report
+    from tw_invoice_unet_ocr_llm_b200.synthetic import synthetic_invoices
+    x = synthetic_invoices(1, 512, 512, seed=42)
+    with torch.no_grad():
+        z = model(x.to(cuda_dev))
+    rep = parity_report(oracle_forward(fixture_state, x), z)
+    print(f"parity 1x512x512: {rep}")
+    _check(rep, 0.999)
+
+
+import os
+
+
+@pytest.mark.parametrize("amode", [int(v) for v in os.environ.get("UNETB200_TEST_AMODES", "0,1,2").split(",")])
+def test_amodes_agree(model, cuda_dev, amode):
+    """The three activation-staging strategies feed the same tiles to the same MMAs.  A_TAP
+    and A_HALO also accumulate the nine taps in the same order -> bit-identical logits;
+    A_COL3 walks the taps column-major, so it differs by fp32 accumulation order only."""
+    from tw_invoice_unet_ocr_llm_b200.synthetic import synthetic_invoices
+    x = synthetic_invoices(2, 64, 96, seed=46).to(cuda_dev)
+    eng = model.engine(cuda_dev)
+    keep = eng.get_option("amode")
+    try:
+        eng.set_option("amode", 0)
+        z0, _ = eng.run(x)
+        eng.set_option("amode", amode)
+        z1, _ = eng.run(x)
+        torch.cuda.synchronize()
+    finally:
+        eng.set_option("amode", keep)
+    if amode == 1:
+        assert (z0 - z1).abs().max().item() < 0.05
+    else:
+        assert torch.equal(z0, z1)
+
+
+def test_u8_input_and_masks(model, fixture_state, cuda_dev):
+    """uint8 NHWC ingest (/255 in-kernel, inference.py:36) == float path, bit for bit; fused
+    logit-space threshold == sigmoid(z) > t on the returned logits (inference.py:72-79)."""
+    from oracle.unet_oracle import oracle_masks
+    from tw_invoice_unet_ocr_llm_b200.synthetic import synthetic_invoices_u8
+    u8 = synthetic_invoices_u8(2, 64, 64, seed=47)
+    xf = torch.from_numpy(u8.astype(np.float32) / 255.0).permute(0, 3, 1, 2).contiguous().to(cuda_dev)
+    eng = model.engine(cuda_dev)
+    thr = [0.25, 0.40, 0.30]
+    zf, mf = eng.run(xf, thresholds=thr)
+    zu, mu = eng.run(torch.from_numpy(u8).to(cuda_dev), thresholds=thr)
+    torch.cuda.synchronize()
+    assert torch.equal(zf, zu) and torch.equal(mf, mu)
+    assert np.array_equal(mf.cpu().numpy().astype(bool), oracle_masks(zf.cpu()))
+
+
+def test_batch_independence(model, cuda_dev):
+    """Images are independent units: a batched forward equals per-image forwards bit for bit
+    (what makes multi-GPU sharding exact)."""
+    from tw_invoice_unet_ocr_llm_b200.synthetic import synthetic_invoices
+    x = synthetic_invoices(5, 48, 64, seed=48).to(cuda_dev)
+    with torch.no_grad():
+        zb = model(x)
+        zs = torch.cat([model(x[i:i + 1]) for i in range(5)])
+    assert torch.equal(zb, zs)
+
+
+def test_errors(model, cuda_dev):
+    with pytest.raises(RuntimeError):
+        model(torch.zeros(1, 3, 500, 500, device=cuda_dev))     # not divisible by 16 (reference raises too)
+    with pytest.raises(RuntimeError):
+        model(torch.zeros(1, 3, 64, 64))                        # CPU tensor: no CPU path
+    with pytest.raises(RuntimeError):
+        model(torch.zeros(1, 4, 64, 64, device=cuda_dev))       # wrong channel count

@@ -1,0 +1,391 @@
+// Implicit-GEMM convolution on the sm_100a tensor cores (tcgen05 + TMEM + TMA).
+//
+// One kernel template covers every dense contraction of the U-Net forward
+// (reference: unet_model.py:9-17 DoubleConv convs, :38-47 ConvTranspose2d):
+//
+//   TAPS == 9 : 3x3 / pad 1 / stride 1 convolution, NHWC bf16 activations,
+//               weights packed [tap][Cout][Cin] bf16 with BatchNorm folded in.
+//               Up to two activation sources are read back to back along K,
+//               which is torch.cat([up, skip], dim=1) without the copy
+//               (unet_model.py:71,75,79,83).
+//   TAPS == 1 : ConvTranspose2d(k=2, s=2) as one GEMM with N = 4*Cout
+//               (rows of B ordered [tap = 2a+b][Cout]); the epilogue scatters
+//               column block `tap` to output pixel (2y+a, 2x+b).
+//
+// GEMM view: D[M=128 pixels (16 rows x 8 cols of one image), N=BN channels]
+//            += A[128, 64] * B[BN, 64]^T  per (channel slice of 64, tap).
+//
+// How the A operand (activations) reaches shared memory -- `AMODE`:
+//   A_TAP   : one 16x8 TMA box per (slice, tap), shifted by the tap offset.
+//             Fully standard SWIZZLE_128B K-major tile; 9x the smem fill traffic.
+//   A_COL3  : one 18x8 box per (slice, kx): the three ky taps of that column
+//             shift are the same patch read 0/1/2 rows (= 1024 B, a whole
+//             swizzle atom) further down, so the layout stays canonical.
+//             3.4x the fill traffic of one tile.
+//   A_HALO  : one 18x10 box per slice; the nine taps are nine descriptors into
+//             it, start address shifted by (ky*10+kx) rows of 128 B and the
+//             8-row group stride set to one patch row (1280 B).  1.4x traffic,
+//             but relies on the swizzle being a function of the absolute smem
+//             address (validated on hardware by tests/test_conv_kernels.py).
+// TMA zero-fills out-of-bounds box elements, which is the conv zero padding.
+//
+// Warp roles (256 threads, 1 CTA / SM, persistent over tiles):
+//   warp 0 : TMA producer          warp 1 : MMA issuer (one lane)
+//   warp 2 : TMEM allocator        warps 4-7 : epilogue (TMEM -> regs -> smem -> TMA store)
+// Two TMEM accumulators so the epilogue of tile i overlaps the MMAs of tile i+1.
+#pragma once
+#include "ptx.cuh"
+
+namespace ub {
+
+enum : int { EPI_STORE = 0, EPI_STORE_POOL = 1, EPI_HEAD = 2, EPI_UPSAMPLE = 3 };
+enum : int { A_TAP = 0, A_COL3 = 1, A_HALO = 2 };
+
+constexpr int kMaxClasses = 8;
+
+struct ConvParams {
+    CUtensorMap tmA0;        // source 0 activations, dims (C, W, H, N)
+    CUtensorMap tmA1;        // source 1 activations (skip tensor), or == tmA0
+    CUtensorMap tmB;         // weights, dims (Cin_total, rows, taps)
+    CUtensorMap tmOut[4];    // output store maps ([0] for convs, [tap] for convT)
+    CUtensorMap tmPool;      // pooled output store map
+    const float* bias;       // [Cout] fp32 (BatchNorm-folded)
+    const float* head_w;     // [ncls][64] fp32      (EPI_HEAD)
+    const float* head_b;     // [ncls]               (EPI_HEAD)
+    float* logits;           // [N][ncls][H][W] fp32 (EPI_HEAD, nullable)
+    uint8_t* mask;           // [N][ncls][H][W] u8   (EPI_HEAD, nullable)
+    float thr[kMaxClasses];  // logit-space thresholds
+    int* dbg;                // watchdog record (nullable)
+    int C0, C1;              // channels of source 0 / 1 (multiples of 64; C1 may be 0)
+    int H, W, NIMG;          // spatial size of the INPUT (== output for 3x3)
+    int Cout;                // output channels (per tap for convT)
+    int tiles_x, tiles_y;    // ceil(W/8), ceil(H/16)
+    int n_blocks;            // column blocks per pixel tile
+    int total_tiles;
+    int relu;
+    int ncls;
+    int desc_mode;           // A_HALO: 0 = base_offset 0, 1 = base_offset from address bits
+};
+
+template <int BN, int TAPS, int AMODE>
+struct ConvCfg {
+    static constexpr int TPA = TAPS == 1 ? 1 : (AMODE == A_TAP ? 1 : (AMODE == A_COL3 ? 3 : 9));
+    static constexpr int A_ROWS = TAPS == 1 ? 128 : (AMODE == A_TAP ? 128 : (AMODE == A_COL3 ? 144 : 180));
+    static constexpr int A_TX = A_ROWS * 128;
+    static constexpr int A_STAGE = (A_TX + 1023) / 1024 * 1024;
+    static constexpr int B_STAGE = BN * 128;
+    static constexpr int OUT_STAGE = 16384;
+    static constexpr int POOL_STAGE = 4096;
+    static constexpr int FIXED = 2 * OUT_STAGE + 2 * POOL_STAGE + 1024 /*barriers*/ + 1024 /*align*/ +
+                                 2304 /*static smem*/;
+    static constexpr int BUDGET = 232448 - FIXED;
+    // weights: enough stages to cover one A item's worth of taps plus slack
+    static constexpr int NB = BN == 256 ? 3 : (BN == 128 ? 5 : 8);
+    static constexpr int NA_RAW = (BUDGET - NB * B_STAGE) / A_STAGE;
+    static constexpr int NA = NA_RAW > 6 ? 6 : NA_RAW;
+    static_assert(NA >= 2, "need at least two activation stages");
+    static constexpr int OFF_A = 0;
+    static constexpr int OFF_B = OFF_A + NA * A_STAGE;
+    static constexpr int OFF_OUT = OFF_B + NB * B_STAGE;
+    static constexpr int OFF_POOL = OFF_OUT + 2 * OUT_STAGE;
+    static constexpr int OFF_BAR = OFF_POOL + 2 * POOL_STAGE;
+    static constexpr int NBAR = 2 * NA + 2 * NB + 4;
+    static constexpr int SMEM_BYTES = OFF_BAR + 1024 + 1024;   // barriers + alignment slack
+    static constexpr int TMEM_COLS = 2 * BN;                   // 128 / 256 / 512
+};
+
+template <int BN, int TAPS, int AMODE, int EPI>
+__global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
+    static_assert(TAPS == 9 || TAPS == 1, "3x3 conv or per-tap GEMM");
+    static_assert(EPI != EPI_HEAD || BN == 64, "fused head needs all 64 channels in one tile");
+    using Cfg = ConvCfg<BN, TAPS, AMODE>;
+    constexpr int TPA = Cfg::TPA;
+    constexpr int ITEMS = TAPS / TPA;
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t sA = smem_base + Cfg::OFF_A;
+    const uint32_t sB = smem_base + Cfg::OFF_B;
+    const uint32_t sOut = smem_base + Cfg::OFF_OUT;
+    const uint32_t sPool = smem_base + Cfg::OFF_POOL;
+    const uint32_t sBar = smem_base + Cfg::OFF_BAR;
+    const uint32_t bar_a_full = sBar;
+    const uint32_t bar_a_empty = bar_a_full + 8 * Cfg::NA;
+    const uint32_t bar_b_full = bar_a_empty + 8 * Cfg::NA;
+    const uint32_t bar_b_empty = bar_b_full + 8 * Cfg::NB;
+    const uint32_t bar_t_full = bar_b_empty + 8 * Cfg::NB;
+    const uint32_t bar_t_empty = bar_t_full + 16;
+    const uint32_t s_tmem_ptr = bar_t_empty + 16;
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));   // generic view of smem_base
+
+    __shared__ float s_head_w[kMaxClasses * 64];
+    __shared__ float s_head_b[kMaxClasses];
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.tmA0);
+        tma_prefetch_desc(&p.tmA1);
+        tma_prefetch_desc(&p.tmB);
+        if (EPI != EPI_HEAD) tma_prefetch_desc(&p.tmOut[0]);
+        if (EPI == EPI_STORE_POOL) tma_prefetch_desc(&p.tmPool);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < Cfg::NA; ++i) {
+            mbar_init(bar_a_full + 8 * i, 1);
+            mbar_init(bar_a_empty + 8 * i, 1);
+        }
+        for (int i = 0; i < Cfg::NB; ++i) {
+            mbar_init(bar_b_full + 8 * i, 1);
+            mbar_init(bar_b_empty + 8 * i, 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(bar_t_full + 8 * i, 1);
+            mbar_init(bar_t_empty + 8 * i, 4);   // one arrive per epilogue warp
+        }
+        mbar_fence_init();
+    }
+    if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(s_tmem_ptr);
+    if (EPI == EPI_HEAD) {
+        for (int i = threadIdx.x; i < p.ncls * 64; i += blockDim.x) s_head_w[i] = p.head_w[i];
+        if (threadIdx.x < p.ncls) s_head_b[threadIdx.x] = p.head_b[threadIdx.x];
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(
+        smem_gen + (s_tmem_ptr - smem_base));
+
+    const int n_cs = (p.C0 + p.C1) >> 6;            // 64-channel slices along K
+    const int tiles_per_img = p.tiles_x * p.tiles_y;
+
+    if (warp == 0) {
+        // ============================ TMA producer ============================
+        if (lane == 0) {
+            uint32_t a_it = 0, b_it = 0;
+            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+                const int nb = t % p.n_blocks;
+                const int mt = t / p.n_blocks;
+                const int n = mt / tiles_per_img;
+                const int r = mt - n * tiles_per_img;
+                const int y0 = (r / p.tiles_x) * 16;
+                const int x0 = (r % p.tiles_x) * 8;
+                for (int cs = 0; cs < n_cs; ++cs) {
+                    const bool src0 = (cs << 6) < p.C0;
+                    const CUtensorMap* tmA = src0 ? &p.tmA0 : &p.tmA1;
+                    const int ca = src0 ? (cs << 6) : (cs << 6) - p.C0;
+#pragma unroll 1
+                    for (int item = 0; item < ITEMS; ++item) {
+                        {
+                            // box origin of this activation item
+                            int bx = x0, by = y0;
+                            if (TAPS == 9) {
+                                if (AMODE == A_TAP) { bx += item % 3 - 1; by += item / 3 - 1; }
+                                if (AMODE == A_COL3) { bx += item - 1; by -= 1; }
+                                if (AMODE == A_HALO) { bx -= 1; by -= 1; }
+                            }
+                            const uint32_t s = a_it % Cfg::NA, ph = (a_it / Cfg::NA) & 1;
+                            mbar_wait(bar_a_empty + 8 * s, ph ^ 1, 1, p.dbg);
+                            mbar_expect_tx(bar_a_full + 8 * s, Cfg::A_TX);
+                            tma_load_4d(sA + s * Cfg::A_STAGE, tmA, bar_a_full + 8 * s, ca, bx, by, n);
+                            ++a_it;
+                        }
+#pragma unroll 1
+                        for (int tt = 0; tt < TPA; ++tt) {
+                            // weight tap index in the packed tensor (ky*3+kx)
+                            const int tap = TAPS == 1 ? 0 : (AMODE == A_COL3 ? tt * 3 + item
+                                                                             : item * TPA + tt);
+                            const uint32_t s = b_it % Cfg::NB, ph = (b_it / Cfg::NB) & 1;
+                            mbar_wait(bar_b_empty + 8 * s, ph ^ 1, 3, p.dbg);
+                            mbar_expect_tx(bar_b_full + 8 * s, Cfg::B_STAGE);
+                            tma_load_3d(sB + s * Cfg::B_STAGE, &p.tmB, bar_b_full + 8 * s, cs << 6,
+                                        nb * BN, tap);
+                            ++b_it;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ============================ MMA issuer ==============================
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(BN);
+            constexpr uint32_t a_sbo = (TAPS == 9 && AMODE == A_HALO) ? 10 * 128 : 1024;
+            uint32_t a_it = 0, b_it = 0, tile_it = 0;
+            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tile_it) {
+                const uint32_t acc = tile_it & 1, acc_ph = (tile_it >> 1) & 1;
+                mbar_wait(bar_t_empty + 8 * acc, acc_ph ^ 1, 4, p.dbg);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                uint32_t accumulate = 0;
+                for (int cs = 0; cs < n_cs; ++cs) {
+#pragma unroll 1
+                    for (int item = 0; item < ITEMS; ++item) {
+                        const uint32_t sa = a_it % Cfg::NA, pa = (a_it / Cfg::NA) & 1;
+                        mbar_wait(bar_a_full + 8 * sa, pa, 5, p.dbg);
+#pragma unroll 1
+                        for (int tt = 0; tt < TPA; ++tt) {
+                            const uint32_t sb = b_it % Cfg::NB, pb = (b_it / Cfg::NB) & 1;
+                            mbar_wait(bar_b_full + 8 * sb, pb, 6, p.dbg);
+                            tc_fence_after();
+                            uint32_t a_addr = sA + sa * Cfg::A_STAGE;
+                            if (TAPS == 9 && AMODE == A_COL3) a_addr += tt * 1024;
+                            if (TAPS == 9 && AMODE == A_HALO) a_addr += ((tt / 3) * 10 + (tt % 3)) * 128;
+                            const uint32_t b_addr = sB + sb * Cfg::B_STAGE;
+                            const uint32_t a_bo =
+                                (TAPS == 9 && AMODE == A_HALO && p.desc_mode == 1) ? ((a_addr >> 7) & 7) : 0;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const uint64_t ad = umma_desc_sw128(a_addr + k * 32, a_sbo, a_bo);
+                                const uint64_t bd = umma_desc_sw128(b_addr + k * 32, 1024, 0);
+                                umma_bf16(d_tmem, ad, bd, idesc, accumulate);
+                                accumulate = 1;
+                            }
+                            umma_commit(bar_b_empty + 8 * sb);
+                            ++b_it;
+                        }
+                        umma_commit(bar_a_empty + 8 * sa);
+                        ++a_it;
+                    }
+                }
+                umma_commit(bar_t_full + 8 * acc);
+            }
+        }
+    } else if (warp >= 4) {
+        // ============================= epilogue ===============================
+        const int q = warp - 4;                 // TMEM lane quarter
+        const int row = q * 32 + lane;          // pixel row of the tile: h = row/8, w = row%8
+        const int et = threadIdx.x - 128;       // 0..127
+        uint32_t tile_it = 0, chunk_it = 0;
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tile_it) {
+            const int nb = t % p.n_blocks;
+            const int mt = t / p.n_blocks;
+            const int n = mt / tiles_per_img;
+            const int r = mt - n * tiles_per_img;
+            const int y0 = (r / p.tiles_x) * 16;
+            const int x0 = (r % p.tiles_x) * 8;
+            const uint32_t acc = tile_it & 1, acc_ph = (tile_it >> 1) & 1;
+            mbar_wait(bar_t_full + 8 * acc, acc_ph, 7, p.dbg);
+            tc_fence_after();
+            const uint32_t t_addr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
+
+            if (EPI == EPI_HEAD) {
+                float z[kMaxClasses];
+#pragma unroll
+                for (int c = 0; c < kMaxClasses; ++c) z[c] = c < p.ncls ? s_head_b[c] : 0.f;
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t v[32];
+                    tmem_ld32(t_addr + half * 32, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        float f = __uint_as_float(v[i]) + __ldg(p.bias + half * 32 + i);
+                        f = p.relu ? fmaxf(f, 0.f) : f;
+#pragma unroll
+                        for (int c = 0; c < kMaxClasses; ++c)
+                            if (c < p.ncls) z[c] = fmaf(f, s_head_w[c * 64 + half * 32 + i], z[c]);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_t_empty + 8 * acc);
+                const int y = y0 + (row >> 3), x = x0 + (row & 7);
+                if (y < p.H && x < p.W) {
+#pragma unroll
+                    for (int c = 0; c < kMaxClasses; ++c) {
+                        if (c < p.ncls) {
+                            const size_t o = ((static_cast<size_t>(n) * p.ncls + c) * p.H + y) * p.W + x;
+                            if (p.logits) p.logits[o] = z[c];
+                            if (p.mask) p.mask[o] = z[c] > p.thr[c] ? 1 : 0;
+                        }
+                    }
+                }
+                continue;
+            }
+
+#pragma unroll 1
+            for (int j = 0; j < BN / 64; ++j, ++chunk_it) {
+                const int gcol = nb * BN + j * 64;            // global column of this 64-wide chunk
+                const int tapo = EPI == EPI_UPSAMPLE ? gcol / p.Cout : 0;
+                const int ch0 = EPI == EPI_UPSAMPLE ? gcol - tapo * p.Cout : gcol;
+                const uint32_t obuf = sOut + (chunk_it & 1) * Cfg::OUT_STAGE;
+                const uint32_t pbuf = sPool + (chunk_it & 1) * Cfg::POOL_STAGE;
+                // staging buffer (chunk_it & 1) was last read by the store issued two chunks ago
+                if (et == 0) tma_store_wait_read<1>();
+                named_bar_sync(1, 128);
+                uint32_t pk[32];
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t v[32];
+                    tmem_ld32(t_addr + j * 64 + half * 32, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        const float4 b4 =
+                            __ldg(reinterpret_cast<const float4*>(p.bias + ch0 + half * 32 + i));
+                        float f0 = __uint_as_float(v[i + 0]) + b4.x;
+                        float f1 = __uint_as_float(v[i + 1]) + b4.y;
+                        float f2 = __uint_as_float(v[i + 2]) + b4.z;
+                        float f3 = __uint_as_float(v[i + 3]) + b4.w;
+                        if (p.relu) {
+                            f0 = fmaxf(f0, 0.f);
+                            f1 = fmaxf(f1, 0.f);
+                            f2 = fmaxf(f2, 0.f);
+                            f3 = fmaxf(f3, 0.f);
+                        }
+                        pk[half * 16 + i / 2] = pack_bf16x2(f0, f1);
+                        pk[half * 16 + i / 2 + 1] = pack_bf16x2(f2, f3);
+                    }
+                }
+                if (j == BN / 64 - 1) {   // accumulator fully drained -> hand it back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_t_empty + 8 * acc);
+                }
+#pragma unroll
+                for (int c16 = 0; c16 < 8; ++c16)
+                    st_shared_v4(obuf + row * 128 + ((c16 ^ (row & 7)) << 4), pk[c16 * 4],
+                                 pk[c16 * 4 + 1], pk[c16 * 4 + 2], pk[c16 * 4 + 3]);
+                if (EPI == EPI_STORE_POOL) {
+                    // 2x2 max-pool: partners are lane^1 (x) and lane^8 (y); bf16 rounding is
+                    // monotone, so max of rounded == rounded max (unet_model.py:34,57).
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        uint32_t m = max_bf16x2(pk[i], __shfl_xor_sync(0xffffffffu, pk[i], 1));
+                        pk[i] = max_bf16x2(m, __shfl_xor_sync(0xffffffffu, m, 8));
+                    }
+                    if ((lane & 9) == 0) {
+                        const int pr = (q * 2 + (lane >> 4)) * 4 + ((lane & 7) >> 1);
+#pragma unroll
+                        for (int c16 = 0; c16 < 8; ++c16)
+                            st_shared_v4(pbuf + pr * 128 + ((c16 ^ (pr & 7)) << 4), pk[c16 * 4],
+                                         pk[c16 * 4 + 1], pk[c16 * 4 + 2], pk[c16 * 4 + 3]);
+                    }
+                }
+                fence_proxy_async_smem();
+                named_bar_sync(2, 128);
+                if (et == 0) {
+                    if (EPI == EPI_UPSAMPLE)
+                        tma_store_4d(&p.tmOut[tapo], obuf, ch0, x0, y0, n);
+                    else
+                        tma_store_4d(&p.tmOut[0], obuf, ch0, x0, y0, n);
+                    if (EPI == EPI_STORE_POOL)
+                        tma_store_4d(&p.tmPool, pbuf, ch0, x0 >> 1, y0 >> 1, n);
+                    tma_store_commit();
+                }
+            }
+        }
+        if (et == 0) tma_store_wait_all<0>();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    }
+}
+
+}  // namespace ub

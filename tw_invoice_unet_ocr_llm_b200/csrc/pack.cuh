@@ -1,0 +1,81 @@
+// Weight pipeline: fp32 state_dict tensors (exactly what train.py:159 saves and
+// inference.py:20-21 loads) -> BatchNorm folded in fp32 -> the layouts the
+// kernels consume.  Runs once per load_state_dict, on the device.
+//
+// Fold (eval-mode BatchNorm2d, unet_model.py:11,15; eps = nn.BatchNorm2d default):
+//   s[co] = gamma[co] / sqrt(running_var[co] + eps)
+//   w'    = w * s[co]                b' = (b[co] - running_mean[co]) * s[co] + beta[co]
+#pragma once
+#include "ptx.cuh"
+
+namespace ub {
+
+__device__ __forceinline__ float bn_scale(const float* gamma, const float* var, float eps, int co) {
+    return gamma ? __fdiv_rn(gamma[co], __fsqrt_rn(var[co] + eps)) : 1.0f;
+}
+
+__device__ __forceinline__ uint16_t f32_to_bf16_bits(float f) {
+    return static_cast<uint16_t>(pack_bf16x2(f, 0.f) & 0xffffu);
+}
+
+// Conv2d weight [Cout][Cin][3][3] -> [tap = ky*3+kx][Cout][Cin] bf16, bias -> [Cout] fp32.
+__global__ void pack_conv3x3_kernel(const float* __restrict__ w, const float* __restrict__ b,
+                                    const float* __restrict__ gamma, const float* __restrict__ beta,
+                                    const float* __restrict__ mean, const float* __restrict__ var,
+                                    float eps, int cout, int cin, uint16_t* __restrict__ dst_w,
+                                    float* __restrict__ dst_b) {
+    const size_t total = static_cast<size_t>(9) * cout * cin;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int ci = static_cast<int>(i % cin);
+        const int co = static_cast<int>((i / cin) % cout);
+        const int tap = static_cast<int>(i / (static_cast<size_t>(cin) * cout));
+        const float s = bn_scale(gamma, var, eps, co);
+        dst_w[i] = f32_to_bf16_bits(w[(static_cast<size_t>(co) * cin + ci) * 9 + tap] * s);
+    }
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < cout) {
+        const float s = bn_scale(gamma, var, eps, t);
+        const float b0 = b ? b[t] : 0.f;
+        dst_b[t] = gamma ? (b0 - mean[t]) * s + beta[t] : b0;
+    }
+}
+
+// First conv: [64][Cin][3][3] -> fp32 [k = (ky*3+kx)*Cin + ci][64].
+__global__ void pack_stem_kernel(const float* __restrict__ w, const float* __restrict__ b,
+                                 const float* __restrict__ gamma, const float* __restrict__ beta,
+                                 const float* __restrict__ mean, const float* __restrict__ var,
+                                 float eps, int cout, int cin, float* __restrict__ dst_w,
+                                 float* __restrict__ dst_b) {
+    const int total = 9 * cin * cout;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int co = i % cout;
+        const int k = i / cout;
+        const int ci = k % cin, tap = k / cin;
+        const float s = bn_scale(gamma, var, eps, co);
+        dst_w[i] = w[(static_cast<size_t>(co) * cin + ci) * 9 + tap] * s;
+    }
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < cout) {
+        const float s = bn_scale(gamma, var, eps, t);
+        const float b0 = b ? b[t] : 0.f;
+        dst_b[t] = gamma ? (b0 - mean[t]) * s + beta[t] : b0;
+    }
+}
+
+// ConvTranspose2d weight [Cin][Cout][2][2] -> [(a*2+b)*Cout + co][Cin] bf16 (unet_model.py:38-47).
+__global__ void pack_convt_kernel(const float* __restrict__ w, const float* __restrict__ b, int cin,
+                                  int cout, uint16_t* __restrict__ dst_w, float* __restrict__ dst_b) {
+    const size_t total = static_cast<size_t>(4) * cout * cin;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int ci = static_cast<int>(i % cin);
+        const int co = static_cast<int>((i / cin) % cout);
+        const int tap = static_cast<int>(i / (static_cast<size_t>(cin) * cout));
+        dst_w[i] = f32_to_bf16_bits(w[(static_cast<size_t>(ci) * cout + co) * 4 + tap]);
+    }
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < cout) dst_b[t] = b ? b[t] : 0.f;
+}
+
+}  // namespace ub

@@ -1,0 +1,858 @@
+// C ABI (include/unetb200.h) over the sm_100a kernels in this directory.
+// Host side only builds tensor maps / launch plans and enqueues kernels; it owns
+// no device memory on the hot path ("Ownership").
+#include "../../include/unetb200.h"
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "conv_tc.cuh"
+#include "pack.cuh"
+#include "stem.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+#define UB_CUDA(expr)                                                                          \
+    do {                                                                                       \
+        cudaError_t e_ = (expr);                                                               \
+        if (e_ != cudaSuccess)                                                                 \
+            return fail(UNETB200_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));   \
+    } while (0)
+
+// ------------------------------------------------------------------ driver entry point
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) ==
+                cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+// 4-D bf16 activation view: dims (C, W, H, N) with explicit byte strides for W, H, N.
+int make_map4(CUtensorMap* m, const void* base, uint64_t C, uint64_t W, uint64_t H, uint64_t N,
+              uint64_t strideW, uint64_t strideH, uint64_t strideN, uint32_t boxW, uint32_t boxH) {
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) return fail(UNETB200_ECUDA, "cuTensorMapEncodeTiled entry point unavailable");
+    cuuint64_t dims[4] = {C, W, H, N};
+    cuuint64_t strides[3] = {strideW, strideH, strideN};
+    cuuint32_t box[4] = {64, boxW, boxH, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides,
+                     box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        char buf[256];
+        snprintf(buf, sizeof buf,
+                 "cuTensorMapEncodeTiled(4d) failed: %d (C=%llu W=%llu H=%llu N=%llu box=%u,%u base=%p)",
+                 static_cast<int>(r), (unsigned long long)C, (unsigned long long)W,
+                 (unsigned long long)H, (unsigned long long)N, boxW, boxH, base);
+        return fail(UNETB200_ECUDA, buf);
+    }
+    return 0;
+}
+
+int make_act_map(CUtensorMap* m, const void* base, int C, int W, int H, int N, int boxW, int boxH) {
+    return make_map4(m, base, C, W, H, N, uint64_t(C) * 2, uint64_t(W) * C * 2,
+                     uint64_t(H) * W * C * 2, boxW, boxH);
+}
+
+// weights: dims (CinTot, rows, taps)
+int make_w_map(CUtensorMap* m, const void* base, int cin, int rows, int taps, int bn) {
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) return fail(UNETB200_ECUDA, "cuTensorMapEncodeTiled entry point unavailable");
+    cuuint64_t dims[3] = {uint64_t(cin), uint64_t(rows), uint64_t(taps)};
+    cuuint64_t strides[2] = {uint64_t(cin) * 2, uint64_t(rows) * cin * 2};
+    cuuint32_t box[3] = {64, uint32_t(bn), 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides,
+                     box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return fail(UNETB200_ECUDA, "cuTensorMapEncodeTiled(weights) failed: " + std::to_string(int(r)));
+    return 0;
+}
+
+// ------------------------------------------------------------------ layer table
+struct LayerSpec {
+    const char* name;
+    const char* bn;
+    int kind, cin, cout, level;
+};
+
+std::vector<unetb200_layer_t> layer_table(const unetb200_arch_t& a) {
+    const int w = a.base_width;
+    const LayerSpec specs[] = {
+        {"down1.net.0", "down1.net.1", UNETB200_STEM, a.n_channels, w, 0},
+        {"down1.net.3", "down1.net.4", UNETB200_CONV3X3, w, w, 0},
+        {"down2.net.0", "down2.net.1", UNETB200_CONV3X3, w, 2 * w, 1},
+        {"down2.net.3", "down2.net.4", UNETB200_CONV3X3, 2 * w, 2 * w, 1},
+        {"down3.net.0", "down3.net.1", UNETB200_CONV3X3, 2 * w, 4 * w, 2},
+        {"down3.net.3", "down3.net.4", UNETB200_CONV3X3, 4 * w, 4 * w, 2},
+        {"down4.net.0", "down4.net.1", UNETB200_CONV3X3, 4 * w, 8 * w, 3},
+        {"down4.net.3", "down4.net.4", UNETB200_CONV3X3, 8 * w, 8 * w, 3},
+        {"bottleneck.net.0", "bottleneck.net.1", UNETB200_CONV3X3, 8 * w, 16 * w, 4},
+        {"bottleneck.net.3", "bottleneck.net.4", UNETB200_CONV3X3, 16 * w, 16 * w, 4},
+        {"up4", "", UNETB200_CONVT2X2, 16 * w, 8 * w, 4},
+        {"conv4.net.0", "conv4.net.1", UNETB200_CONV3X3, 16 * w, 8 * w, 3},
+        {"conv4.net.3", "conv4.net.4", UNETB200_CONV3X3, 8 * w, 8 * w, 3},
+        {"up3", "", UNETB200_CONVT2X2, 8 * w, 4 * w, 3},
+        {"conv3.net.0", "conv3.net.1", UNETB200_CONV3X3, 8 * w, 4 * w, 2},
+        {"conv3.net.3", "conv3.net.4", UNETB200_CONV3X3, 4 * w, 4 * w, 2},
+        {"up2", "", UNETB200_CONVT2X2, 4 * w, 2 * w, 2},
+        {"conv2.net.0", "conv2.net.1", UNETB200_CONV3X3, 4 * w, 2 * w, 1},
+        {"conv2.net.3", "conv2.net.4", UNETB200_CONV3X3, 2 * w, 2 * w, 1},
+        {"up1", "", UNETB200_CONVT2X2, 2 * w, w, 1},
+        {"conv1.net.0", "conv1.net.1", UNETB200_CONV3X3, 2 * w, w, 0},
+        {"conv1.net.3", "conv1.net.4", UNETB200_CONV3X3, w, w, 0},
+        {"out_conv", "", UNETB200_HEAD, w, a.n_classes, 0},
+    };
+    std::vector<unetb200_layer_t> out;
+    uint64_t off = 0;
+    auto align = [](uint64_t v) { return (v + 255) / 256 * 256; };
+    for (const LayerSpec& s : specs) {
+        unetb200_layer_t l;
+        memset(&l, 0, sizeof l);
+        snprintf(l.name, sizeof l.name, "%s", s.name);
+        snprintf(l.bn_name, sizeof l.bn_name, "%s", s.bn);
+        l.kind = s.kind;
+        l.cin = s.cin;
+        l.cout = s.cout;
+        l.level = s.level;
+        uint64_t wb = 0;
+        switch (s.kind) {
+            case UNETB200_STEM: wb = uint64_t(9) * s.cin * s.cout * 4; break;
+            case UNETB200_CONV3X3: wb = uint64_t(9) * s.cin * s.cout * 2; break;
+            case UNETB200_CONVT2X2: wb = uint64_t(4) * s.cin * s.cout * 2; break;
+            case UNETB200_HEAD: wb = uint64_t(s.cin) * s.cout * 4; break;
+        }
+        l.w_off = off;
+        l.w_bytes = wb;
+        off = align(off + wb);
+        l.b_off = off;
+        l.b_bytes = uint64_t(s.cout) * 4;
+        off = align(off + l.b_bytes);
+        out.push_back(l);
+    }
+    return out;
+}
+
+int check_arch(const unetb200_arch_t* a) {
+    if (!a) return fail(UNETB200_EINVAL, "arch is NULL");
+    if (a->base_width != 64) return fail(UNETB200_EINVAL, "base_width must be 64");
+    if (!(a->n_channels == 1 || a->n_channels == 3 || a->n_channels == 4))
+        return fail(UNETB200_EINVAL, "n_channels must be 1, 3 or 4");
+    if (a->n_classes < 1 || a->n_classes > ub::kMaxClasses)
+        return fail(UNETB200_EINVAL, "n_classes must be in 1..8");
+    return 0;
+}
+
+// ------------------------------------------------------------------ kernel launch plumbing
+typedef void (*ConvKernel)(const ub::ConvParams);
+
+struct ConvLaunch {
+    ConvKernel fn = nullptr;
+    int smem = 0;
+};
+
+template <int BN, int TAPS, int AMODE, int EPI>
+ConvLaunch conv_inst() {
+    ConvLaunch l;
+    l.fn = ub::conv_tc_kernel<BN, TAPS, AMODE, EPI>;
+    l.smem = ub::ConvCfg<BN, TAPS, AMODE>::SMEM_BYTES;
+    return l;
+}
+
+template <int BN, int AMODE>
+ConvLaunch conv3_pick_epi(int epi) {
+    switch (epi) {
+        case ub::EPI_STORE: return conv_inst<BN, 9, AMODE, ub::EPI_STORE>();
+        case ub::EPI_STORE_POOL: return conv_inst<BN, 9, AMODE, ub::EPI_STORE_POOL>();
+        default: return ConvLaunch();
+    }
+}
+
+template <int BN>
+ConvLaunch conv3_pick_amode(int amode, int epi) {
+    switch (amode) {
+        case ub::A_TAP: return conv3_pick_epi<BN, ub::A_TAP>(epi);
+        case ub::A_COL3: return conv3_pick_epi<BN, ub::A_COL3>(epi);
+        case ub::A_HALO: return conv3_pick_epi<BN, ub::A_HALO>(epi);
+        default: return ConvLaunch();
+    }
+}
+
+ConvLaunch pick_conv(int taps, int bn, int amode, int epi) {
+    if (taps == 1) {
+        switch (bn) {
+            case 64: return conv_inst<64, 1, ub::A_TAP, ub::EPI_UPSAMPLE>();
+            case 128: return conv_inst<128, 1, ub::A_TAP, ub::EPI_UPSAMPLE>();
+            case 256: return conv_inst<256, 1, ub::A_TAP, ub::EPI_UPSAMPLE>();
+        }
+        return ConvLaunch();
+    }
+    if (epi == ub::EPI_HEAD) {
+        switch (amode) {
+            case ub::A_TAP: return conv_inst<64, 9, ub::A_TAP, ub::EPI_HEAD>();
+            case ub::A_COL3: return conv_inst<64, 9, ub::A_COL3, ub::EPI_HEAD>();
+            case ub::A_HALO: return conv_inst<64, 9, ub::A_HALO, ub::EPI_HEAD>();
+        }
+        return ConvLaunch();
+    }
+    switch (bn) {
+        case 64: return conv3_pick_amode<64>(amode, epi);
+        case 128: return conv3_pick_amode<128>(amode, epi);
+        case 256: return conv3_pick_amode<256>(amode, epi);
+    }
+    return ConvLaunch();
+}
+
+struct Step {
+    int kind = 0;              // 0 = stem, 1 = conv_tc
+    int layer = -1;            // index into the layer table (profiling)
+    ConvLaunch conv;
+    ub::ConvParams cp;
+    ub::StemParams sp;
+    int stem_cin = 0;
+    dim3 grid, block;
+};
+
+// Describes one tensor-core conv launch; shared by the forward plan and the test hooks.
+struct ConvDesc {
+    const void* src0 = nullptr;
+    int c0 = 0;
+    const void* src1 = nullptr;
+    int c1 = 0;
+    const void* w = nullptr;
+    const float* bias = nullptr;
+    int n = 0, h = 0, wd = 0, cout = 0, relu = 1;
+    int taps = 9;               // 9 = conv3x3, 1 = convT2x2
+    int epi = ub::EPI_STORE;
+    void* out = nullptr;
+    void* pool = nullptr;
+    const float* head_w = nullptr;
+    const float* head_b = nullptr;
+    int ncls = 0;
+    float* logits = nullptr;
+    uint8_t* mask = nullptr;
+    int bn = 128, amode = ub::A_COL3, desc_mode = 0;
+    int* dbg = nullptr;
+};
+
+int build_conv_step(const ConvDesc& d, int num_sms, Step* st) {
+    if (d.c0 <= 0 || d.c0 % 64 || d.c1 % 64 || d.c1 < 0)
+        return fail(UNETB200_EINVAL, "conv: source channels must be multiples of 64");
+    if (d.cout % 64) return fail(UNETB200_EINVAL, "conv: cout must be a multiple of 64");
+    const int cols = d.taps == 1 ? 4 * d.cout : d.cout;
+    int bn = d.bn;
+    if (d.epi == ub::EPI_HEAD) bn = 64;
+    if (bn > cols) bn = cols;
+    while (cols % bn) bn >>= 1;
+    if (!(bn == 64 || bn == 128 || bn == 256)) return fail(UNETB200_EINVAL, "conv: bad column block");
+    if (d.epi == ub::EPI_HEAD && d.cout != 64)
+        return fail(UNETB200_EINVAL, "fused head needs cout == 64");
+    st->kind = 1;
+    st->conv = pick_conv(d.taps, bn, d.amode, d.epi);
+    if (!st->conv.fn) return fail(UNETB200_EINVAL, "conv: no kernel for this configuration");
+    ub::ConvParams& p = st->cp;
+    memset(&p, 0, sizeof p);
+    int boxW = 8, boxH = 16;
+    if (d.taps == 9 && d.amode == ub::A_COL3) boxH = 18;
+    if (d.taps == 9 && d.amode == ub::A_HALO) { boxW = 10; boxH = 18; }
+    int rc;
+    if ((rc = make_act_map(&p.tmA0, d.src0, d.c0, d.wd, d.h, d.n, boxW, boxH))) return rc;
+    if (d.c1 > 0) {
+        if ((rc = make_act_map(&p.tmA1, d.src1, d.c1, d.wd, d.h, d.n, boxW, boxH))) return rc;
+    } else {
+        p.tmA1 = p.tmA0;
+    }
+    const int cin = d.c0 + d.c1;
+    if ((rc = make_w_map(&p.tmB, d.w, cin, cols, d.taps == 9 ? 9 : 1, bn))) return rc;
+    if (d.epi == ub::EPI_UPSAMPLE) {
+        const int ho = 2 * d.h, wo = 2 * d.wd;
+        for (int tap = 0; tap < 4; ++tap) {
+            const int a = tap >> 1, b = tap & 1;
+            const char* base = static_cast<const char*>(d.out) + (uint64_t(a) * wo + b) * d.cout * 2;
+            if ((rc = make_map4(&p.tmOut[tap], base, d.cout, d.wd, d.h, d.n, uint64_t(2) * d.cout * 2,
+                                uint64_t(2) * wo * d.cout * 2, uint64_t(ho) * wo * d.cout * 2, 8, 16)))
+                return rc;
+        }
+    } else if (d.epi != ub::EPI_HEAD) {
+        if ((rc = make_act_map(&p.tmOut[0], d.out, d.cout, d.wd, d.h, d.n, 8, 16))) return rc;
+        for (int i = 1; i < 4; ++i) p.tmOut[i] = p.tmOut[0];
+    }
+    if (d.epi == ub::EPI_STORE_POOL) {
+        if (!d.pool) return fail(UNETB200_EINVAL, "pool output missing");
+        if ((rc = make_act_map(&p.tmPool, d.pool, d.cout, d.wd / 2, d.h / 2, d.n, 4, 8))) return rc;
+    } else {
+        p.tmPool = p.tmA0;
+    }
+    p.bias = d.bias;
+    p.head_w = d.head_w;
+    p.head_b = d.head_b;
+    p.logits = d.logits;
+    p.mask = d.mask;
+    p.dbg = d.dbg;
+    p.C0 = d.c0;
+    p.C1 = d.c1;
+    p.H = d.h;
+    p.W = d.wd;
+    p.NIMG = d.n;
+    p.Cout = d.cout;
+    p.tiles_x = (d.wd + 7) / 8;
+    p.tiles_y = (d.h + 15) / 16;
+    p.n_blocks = cols / bn;
+    const long long total = 1LL * p.tiles_x * p.tiles_y * d.n * p.n_blocks;
+    if (total > 0x7fffffffLL) return fail(UNETB200_EINVAL, "conv: too many tiles");
+    p.total_tiles = static_cast<int>(total);
+    p.relu = d.relu;
+    p.ncls = d.ncls;
+    p.desc_mode = d.desc_mode;
+    st->grid = dim3(static_cast<unsigned>(total < num_sms ? total : num_sms));
+    st->block = dim3(256);
+    return 0;
+}
+
+int launch_step(Step& st, cudaStream_t stream) {
+    if (st.kind == 1) {
+        static std::mutex mu;
+        static std::map<const void*, int> configured;
+        {
+            std::lock_guard<std::mutex> g(mu);
+            int dev = 0;
+            cudaGetDevice(&dev);
+            auto it = configured.find(reinterpret_cast<const void*>(st.conv.fn));
+            if (it == configured.end() || !(it->second & (1 << dev))) {
+                UB_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(st.conv.fn),
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             st.conv.smem));
+                configured[reinterpret_cast<const void*>(st.conv.fn)] |= (1 << dev);
+            }
+        }
+        st.conv.fn<<<st.grid, st.block, st.conv.smem, stream>>>(st.cp);
+    } else {
+        switch (st.stem_cin) {
+            case 1: ub::stem_conv_kernel<1><<<st.grid, st.block, 0, stream>>>(st.sp); break;
+            case 3: ub::stem_conv_kernel<3><<<st.grid, st.block, 0, stream>>>(st.sp); break;
+            case 4: ub::stem_conv_kernel<4><<<st.grid, st.block, 0, stream>>>(st.sp); break;
+            default: return fail(UNETB200_EINVAL, "stem: n_channels must be 1, 3 or 4");
+        }
+    }
+    UB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int build_stem_step(const void* x, int x_fmt, int cin, const float* w, const float* bias, int n,
+                    int h, int wd, void* out, Step* st) {
+    if (x_fmt != UNETB200_X_F32_NCHW && x_fmt != UNETB200_X_U8_NHWC)
+        return fail(UNETB200_EINVAL, "unknown x_fmt");
+    st->kind = 0;
+    st->stem_cin = cin;
+    st->sp.x = x;
+    st->sp.w = w;
+    st->sp.bias = bias;
+    st->sp.out = out;
+    st->sp.N = n;
+    st->sp.H = h;
+    st->sp.W = wd;
+    st->sp.x_fmt = x_fmt;
+    st->grid = dim3((wd + ub::kStemTX - 1) / ub::kStemTX, (h + ub::kStemTY - 1) / ub::kStemTY, n);
+    st->block = dim3(256);
+    if (n > 65535) return fail(UNETB200_EINVAL, "stem: batch too large for one launch");
+    return 0;
+}
+
+int device_num_sms(int* out) {
+    int dev = 0;
+    UB_CUDA(cudaGetDevice(&dev));
+    UB_CUDA(cudaDeviceGetAttribute(out, cudaDevAttrMultiProcessorCount, dev));
+    return 0;
+}
+
+int check_sm100() {
+    int dev = 0, major = 0;
+    UB_CUDA(cudaGetDevice(&dev));
+    UB_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    if (major != 10)
+        return fail(UNETB200_EARCH,
+                    "unetb200 needs an sm_100 (B200) device; found compute capability major " +
+                        std::to_string(major) + " -- there is no fallback path");
+    return 0;
+}
+
+typedef std::tuple<const void*, int, int, int, int, void*, float*, uint8_t*, int, int> PlanKey;
+
+struct Plan {
+    std::vector<Step> steps;
+};
+
+}  // namespace
+
+struct unetb200_handle_s {
+    unetb200_arch_t arch;
+    std::vector<unetb200_layer_t> layers;
+    const char* blob = nullptr;
+    uint64_t blob_bytes = 0;
+    int device = 0;
+    int num_sms = 0;
+    int amode = ub::A_HALO;
+    int bn_max = 128;
+    int desc_mode = 0;
+    int profile = 0;
+    int* dbg = nullptr;         // pinned, device-visible watchdog record
+    std::map<PlanKey, Plan> plans;
+    std::vector<cudaEvent_t> events;
+    int last_launches = 0;
+    bool timed = false;
+    std::mutex mu;
+};
+
+namespace {
+
+struct WsLayout {
+    uint64_t a[5], c[4], p[4], bt, u[4], ca[4], cc[4], total;
+};
+
+// Workspace carve-up (bf16 NHWC).  Level k has (H>>k) x (W>>k) pixels and 64<<k channels.
+WsLayout ws_layout(int n, int h, int w, int bw) {
+    WsLayout L;
+    uint64_t off = 0;
+    auto take = [&](uint64_t elems) {
+        uint64_t o = off;
+        off = (off + elems * 2 + 1023) / 1024 * 1024;
+        return o;
+    };
+    auto px = [&](int k) { return uint64_t(n) * (h >> k) * (w >> k); };
+    for (int k = 0; k < 5; ++k) L.a[k] = take(px(k) * (uint64_t(bw) << k));        // first conv of level k
+    for (int k = 0; k < 4; ++k) L.c[k] = take(px(k) * (uint64_t(bw) << k));        // skip tensors c1..c4
+    for (int k = 0; k < 4; ++k) L.p[k] = take(px(k + 1) * (uint64_t(bw) << k));    // pooled p1..p4
+    L.bt = take(px(4) * (uint64_t(bw) << 4));                                      // bottleneck output
+    for (int k = 0; k < 4; ++k) {
+        L.u[k] = L.a[k];                                   // up_k output reuses the dead a_k buffer
+        L.ca[k] = take(px(k) * (uint64_t(bw) << k));       // first decoder conv of level k
+        L.cc[k] = k == 0 ? 0 : take(px(k) * (uint64_t(bw) << k));   // second decoder conv (level 0: fused head)
+    }
+    L.total = off;
+    return L;
+}
+
+int build_plan(unetb200_handle_t h, const void* x, int x_fmt, int n, int H, int W, void* ws,
+               float* logits, uint8_t* mask, Plan* plan) {
+    const int bw = h->arch.base_width;
+    const WsLayout L = ws_layout(n, H, W, bw);
+    char* base = static_cast<char*>(ws);
+    auto P = [&](uint64_t off) { return static_cast<void*>(base + off); };
+    auto Wp = [&](int li) { return static_cast<const void*>(h->blob + h->layers[li].w_off); };
+    auto Bp = [&](int li) { return reinterpret_cast<const float*>(h->blob + h->layers[li].b_off); };
+    int rc;
+    auto conv = [&](int li, const void* s0, int c0, const void* s1, int c1, int lvl, void* out,
+                    void* pool) -> int {
+        ConvDesc d;
+        d.src0 = s0; d.c0 = c0; d.src1 = s1; d.c1 = c1;
+        d.w = Wp(li); d.bias = Bp(li);
+        d.n = n; d.h = H >> lvl; d.wd = W >> lvl; d.cout = h->layers[li].cout;
+        d.relu = 1; d.taps = 9; d.epi = pool ? ub::EPI_STORE_POOL : ub::EPI_STORE;
+        d.out = out; d.pool = pool;
+        d.bn = h->bn_max; d.amode = h->amode; d.desc_mode = h->desc_mode; d.dbg = h->dbg;
+        Step st;
+        if ((rc = build_conv_step(d, h->num_sms, &st))) return rc;
+        st.layer = li;
+        plan->steps.push_back(st);
+        return 0;
+    };
+    auto convt = [&](int li, const void* s, int lvl, void* out) -> int {
+        ConvDesc d;
+        d.src0 = s; d.c0 = h->layers[li].cin;
+        d.w = Wp(li); d.bias = Bp(li);
+        d.n = n; d.h = H >> lvl; d.wd = W >> lvl; d.cout = h->layers[li].cout;
+        d.relu = 0; d.taps = 1; d.epi = ub::EPI_UPSAMPLE; d.out = out;
+        d.bn = h->bn_max; d.amode = ub::A_TAP; d.dbg = h->dbg;
+        Step st;
+        if ((rc = build_conv_step(d, h->num_sms, &st))) return rc;
+        st.layer = li;
+        plan->steps.push_back(st);
+        return 0;
+    };
+    // ---- encoder (unet_model.py:56-66)
+    {
+        Step st;
+        if ((rc = build_stem_step(x, x_fmt, h->arch.n_channels,
+                                  reinterpret_cast<const float*>(Wp(0)), Bp(0), n, H, W, P(L.a[0]), &st)))
+            return rc;
+        st.layer = 0;
+        plan->steps.push_back(st);
+    }
+    if ((rc = conv(1, P(L.a[0]), bw, nullptr, 0, 0, P(L.c[0]), P(L.p[0])))) return rc;
+    for (int k = 1; k <= 3; ++k) {
+        const int ci = bw << (k - 1), co = bw << k;
+        if ((rc = conv(2 * k, P(L.p[k - 1]), ci, nullptr, 0, k, P(L.a[k]), nullptr))) return rc;
+        if ((rc = conv(2 * k + 1, P(L.a[k]), co, nullptr, 0, k, P(L.c[k]), P(L.p[k])))) return rc;
+    }
+    // ---- bottleneck (:68)
+    if ((rc = conv(8, P(L.p[3]), bw << 3, nullptr, 0, 4, P(L.a[4]), nullptr))) return rc;
+    if ((rc = conv(9, P(L.a[4]), bw << 4, nullptr, 0, 4, P(L.bt), nullptr))) return rc;
+    // ---- decoder (:70-84): up_k -> cat([up, skip]) -> DoubleConv
+    const void* prev = P(L.bt);
+    for (int k = 3; k >= 0; --k) {
+        const int li_up = 10 + 3 * (3 - k);
+        const int co = bw << k;
+        if ((rc = convt(li_up, prev, k + 1, P(L.u[k])))) return rc;
+        if ((rc = conv(li_up + 1, P(L.u[k]), co, P(L.c[k]), co, k, P(L.ca[k]), nullptr))) return rc;
+        if (k > 0) {
+            if ((rc = conv(li_up + 2, P(L.ca[k]), co, nullptr, 0, k, P(L.cc[k]), nullptr))) return rc;
+            prev = P(L.cc[k]);
+        } else {
+            // conv1.net.3 + out_conv (:86) + threshold (inference.py:72-79) in one kernel
+            ConvDesc d;
+            d.src0 = P(L.ca[0]); d.c0 = bw;
+            d.w = Wp(21); d.bias = Bp(21);
+            d.n = n; d.h = H; d.wd = W; d.cout = bw; d.relu = 1; d.taps = 9; d.epi = ub::EPI_HEAD;
+            d.head_w = reinterpret_cast<const float*>(Wp(22)); d.head_b = Bp(22);
+            d.ncls = h->arch.n_classes; d.logits = logits; d.mask = mask;
+            d.bn = 64; d.amode = h->amode; d.desc_mode = h->desc_mode; d.dbg = h->dbg;
+            Step st;
+            if ((rc = build_conv_step(d, h->num_sms, &st))) return rc;
+            st.layer = 21;
+            plan->steps.push_back(st);
+        }
+    }
+    return 0;
+}
+
+}  // namespace
+
+// ====================================================================== C ABI
+extern "C" {
+
+int unetb200_abi_version(void) { return UNETB200_ABI_VERSION; }
+const char* unetb200_last_error(void) { return g_err.c_str(); }
+
+int unetb200_num_layers(const unetb200_arch_t* arch) {
+    if (check_arch(arch)) return -1;
+    return static_cast<int>(layer_table(*arch).size());
+}
+
+int unetb200_layer_info(const unetb200_arch_t* arch, int index, unetb200_layer_t* out) {
+    int rc = check_arch(arch);
+    if (rc) return rc;
+    if (!out) return fail(UNETB200_EINVAL, "out is NULL");
+    auto t = layer_table(*arch);
+    if (index < 0 || index >= static_cast<int>(t.size())) return fail(UNETB200_EINVAL, "layer index out of range");
+    *out = t[index];
+    return 0;
+}
+
+uint64_t unetb200_packed_bytes(const unetb200_arch_t* arch) {
+    if (check_arch(arch)) return 0;
+    auto t = layer_table(*arch);
+    const unetb200_layer_t& l = t.back();
+    return (l.b_off + l.b_bytes + 255) / 256 * 256;
+}
+
+int unetb200_pack_layer(const unetb200_arch_t* arch, int index, const float* weight,
+                        const float* bias, const float* bn_gamma, const float* bn_beta,
+                        const float* bn_mean, const float* bn_var, float bn_eps, void* blob_dev,
+                        void* stream) {
+    int rc = check_arch(arch);
+    if (rc) return rc;
+    auto t = layer_table(*arch);
+    if (index < 0 || index >= static_cast<int>(t.size())) return fail(UNETB200_EINVAL, "layer index out of range");
+    if (!weight || !blob_dev) return fail(UNETB200_EINVAL, "weight/blob pointer is NULL");
+    if (bn_gamma && (!bn_beta || !bn_mean || !bn_var))
+        return fail(UNETB200_EINVAL, "BatchNorm needs gamma, beta, mean and var together");
+    const unetb200_layer_t& l = t[index];
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    char* blob = static_cast<char*>(blob_dev);
+    float* db = reinterpret_cast<float*>(blob + l.b_off);
+    const int threads = 256;
+    switch (l.kind) {
+        case UNETB200_STEM: {
+            const int total = 9 * l.cin * l.cout;
+            ub::pack_stem_kernel<<<(total + threads - 1) / threads, threads, 0, s>>>(
+                weight, bias, bn_gamma, bn_beta, bn_mean, bn_var, bn_eps, l.cout, l.cin,
+                reinterpret_cast<float*>(blob + l.w_off), db);
+            break;
+        }
+        case UNETB200_CONV3X3: {
+            const uint64_t total = uint64_t(9) * l.cin * l.cout;
+            uint64_t blocks = (total + threads - 1) / threads;
+            if (blocks > 65535 * 4) blocks = 65535 * 4;
+            ub::pack_conv3x3_kernel<<<static_cast<unsigned>(blocks), threads, 0, s>>>(
+                weight, bias, bn_gamma, bn_beta, bn_mean, bn_var, bn_eps, l.cout, l.cin,
+                reinterpret_cast<uint16_t*>(blob + l.w_off), db);
+            break;
+        }
+        case UNETB200_CONVT2X2: {
+            const uint64_t total = uint64_t(4) * l.cin * l.cout;
+            uint64_t blocks = (total + threads - 1) / threads;
+            ub::pack_convt_kernel<<<static_cast<unsigned>(blocks), threads, 0, s>>>(
+                weight, bias, l.cin, l.cout, reinterpret_cast<uint16_t*>(blob + l.w_off), db);
+            break;
+        }
+        case UNETB200_HEAD: {
+            // Conv2d 1x1 weight [ncls][64][1][1] is already [ncls][64]
+            UB_CUDA(cudaMemcpyAsync(blob + l.w_off, weight, l.w_bytes, cudaMemcpyDeviceToDevice, s));
+            if (bias)
+                UB_CUDA(cudaMemcpyAsync(db, bias, l.b_bytes, cudaMemcpyDeviceToDevice, s));
+            else
+                UB_CUDA(cudaMemsetAsync(db, 0, l.b_bytes, s));
+            break;
+        }
+    }
+    UB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int unetb200_create(const unetb200_arch_t* arch, const void* blob_dev, uint64_t blob_bytes,
+                    int device, unetb200_handle_t* out) {
+    int rc = check_arch(arch);
+    if (rc) return rc;
+    if (!blob_dev || !out) return fail(UNETB200_EINVAL, "blob/out pointer is NULL");
+    if (blob_bytes < unetb200_packed_bytes(arch)) return fail(UNETB200_EINVAL, "weights blob too small");
+    UB_CUDA(cudaSetDevice(device));
+    if ((rc = check_sm100())) return rc;
+    if (!encode_tiled()) return fail(UNETB200_ECUDA, "cuTensorMapEncodeTiled entry point unavailable");
+    unetb200_handle_t h = new unetb200_handle_s();
+    h->arch = *arch;
+    h->layers = layer_table(*arch);
+    h->blob = static_cast<const char*>(blob_dev);
+    h->blob_bytes = blob_bytes;
+    h->device = device;
+    if ((rc = device_num_sms(&h->num_sms))) { delete h; return rc; }
+    cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&h->dbg), 64, cudaHostAllocMapped);
+    if (e != cudaSuccess) { delete h; return fail(UNETB200_ECUDA, "cudaHostAlloc(dbg) failed"); }
+    memset(h->dbg, 0, 64);
+    const char* env = getenv("UNETB200_AMODE");
+    if (env) h->amode = atoi(env);
+    env = getenv("UNETB200_BN_MAX");
+    if (env) h->bn_max = atoi(env);
+    *out = h;
+    return 0;
+}
+
+int unetb200_destroy(unetb200_handle_t h) {
+    if (!h) return 0;
+    for (cudaEvent_t e : h->events) cudaEventDestroy(e);
+    if (h->dbg) cudaFreeHost(h->dbg);
+    delete h;
+    return 0;
+}
+
+int unetb200_set_option(unetb200_handle_t h, const char* key, int value) {
+    if (!h || !key) return fail(UNETB200_EINVAL, "handle/key is NULL");
+    std::lock_guard<std::mutex> g(h->mu);
+    std::string k(key);
+    if (k == "amode") {
+        if (value < 0 || value > 2) return fail(UNETB200_EINVAL, "amode must be 0..2");
+        h->amode = value;
+    } else if (k == "bn_max") {
+        if (!(value == 64 || value == 128 || value == 256)) return fail(UNETB200_EINVAL, "bn_max must be 64/128/256");
+        h->bn_max = value;
+    } else if (k == "desc_mode") {
+        h->desc_mode = value ? 1 : 0;
+    } else if (k == "profile") {
+        h->profile = value ? 1 : 0;
+    } else {
+        return fail(UNETB200_EINVAL, "unknown option " + k);
+    }
+    h->plans.clear();
+    return 0;
+}
+
+int unetb200_get_option(unetb200_handle_t h, const char* key, int* value) {
+    if (!h || !key || !value) return fail(UNETB200_EINVAL, "handle/key/value is NULL");
+    std::string k(key);
+    if (k == "amode") *value = h->amode;
+    else if (k == "bn_max") *value = h->bn_max;
+    else if (k == "desc_mode") *value = h->desc_mode;
+    else if (k == "profile") *value = h->profile;
+    else if (k == "num_sms") *value = h->num_sms;
+    else return fail(UNETB200_EINVAL, "unknown option " + k);
+    return 0;
+}
+
+uint64_t unetb200_workspace_bytes(unetb200_handle_t h, int n, int height, int width) {
+    if (!h || n <= 0 || height <= 0 || width <= 0 || height % 16 || width % 16) return 0;
+    return ws_layout(n, height, width, h->arch.base_width).total;
+}
+
+int unetb200_forward(unetb200_handle_t h, const void* x, int x_fmt, int n, int height, int width,
+                     void* workspace, uint64_t workspace_bytes, float* logits, uint8_t* mask,
+                     const float* logit_thr, void* stream) {
+    if (!h) return fail(UNETB200_EINVAL, "handle is NULL");
+    if (!x || !workspace) return fail(UNETB200_EINVAL, "x/workspace pointer is NULL");
+    if (n <= 0 || height <= 0 || width <= 0) return fail(UNETB200_EINVAL, "empty input");
+    if (height % 16 || width % 16)
+        return fail(UNETB200_EINVAL,
+                    "H and W must be divisible by 16 (the reference fails in torch.cat otherwise), got " +
+                        std::to_string(height) + "x" + std::to_string(width));
+    if (!logits && !mask) return fail(UNETB200_EINVAL, "both outputs are NULL");
+    if (mask && !logit_thr) return fail(UNETB200_EINVAL, "mask requested without thresholds");
+    const uint64_t need = ws_layout(n, height, width, h->arch.base_width).total;
+    if (workspace_bytes < need)
+        return fail(UNETB200_ENOMEM, "workspace too small: need " + std::to_string(need) + " bytes");
+    if (reinterpret_cast<uintptr_t>(workspace) % 1024)
+        return fail(UNETB200_EINVAL, "workspace must be 1024-byte aligned");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    std::lock_guard<std::mutex> g(h->mu);
+    int dev = -1;
+    UB_CUDA(cudaGetDevice(&dev));
+    if (dev != h->device) UB_CUDA(cudaSetDevice(h->device));
+    PlanKey key(x, x_fmt, n, height, width, workspace, logits, mask, h->amode, h->bn_max);
+    auto it = h->plans.find(key);
+    if (it == h->plans.end()) {
+        Plan plan;
+        int rc = build_plan(h, x, x_fmt, n, height, width, workspace, logits, mask, &plan);
+        if (rc) return rc;
+        if (h->plans.size() > 64) h->plans.clear();
+        it = h->plans.emplace(key, std::move(plan)).first;
+    }
+    Plan& plan = it->second;
+    if (mask) {
+        Step& last = plan.steps.back();
+        for (int c = 0; c < h->arch.n_classes; ++c) last.cp.thr[c] = logit_thr[c];
+    }
+    const bool prof = h->profile != 0;
+    if (prof) {
+        while (h->events.size() < plan.steps.size() + 1) {
+            cudaEvent_t e;
+            UB_CUDA(cudaEventCreate(&e));
+            h->events.push_back(e);
+        }
+        UB_CUDA(cudaEventRecord(h->events[0], s));
+    }
+    int launches = 0;
+    for (size_t i = 0; i < plan.steps.size(); ++i) {
+        int rc = launch_step(plan.steps[i], s);
+        if (rc) return rc;
+        ++launches;
+        if (prof) UB_CUDA(cudaEventRecord(h->events[i + 1], s));
+    }
+    h->last_launches = launches;
+    h->timed = prof;
+    return 0;
+}
+
+int unetb200_layer_times(unetb200_handle_t h, float* ms, int count) {
+    if (!h || !ms) return fail(UNETB200_EINVAL, "handle/ms is NULL");
+    std::lock_guard<std::mutex> g(h->mu);
+    if (!h->timed) return fail(UNETB200_EINVAL, "last forward was not profiled (set option profile=1)");
+    const int nl = static_cast<int>(h->layers.size());
+    for (int i = 0; i < count; ++i) ms[i] = 0.f;
+    // steps follow the layer table except out_conv, which is fused into conv1.net.3
+    const int nsteps = h->last_launches;
+    UB_CUDA(cudaEventSynchronize(h->events[nsteps]));
+    for (int i = 0; i < nsteps && i < count && i < nl; ++i) {
+        float t = 0.f;
+        UB_CUDA(cudaEventElapsedTime(&t, h->events[i], h->events[i + 1]));
+        ms[i] = t;
+    }
+    return 0;
+}
+
+int unetb200_last_launch_count(unetb200_handle_t h) { return h ? h->last_launches : -1; }
+
+// ------------------------------------------------------------------ single-kernel hooks
+static int* g_hook_dbg() {
+    static int* dbg = nullptr;
+    if (!dbg) {
+        if (cudaHostAlloc(reinterpret_cast<void**>(&dbg), 64, cudaHostAllocMapped) != cudaSuccess)
+            dbg = nullptr;
+        else
+            memset(dbg, 0, 64);
+    }
+    return dbg;
+}
+
+int unetb200_conv3x3(const void* src0, int c0, const void* src1, int c1, const void* w_packed,
+                     const float* bias, int n, int height, int width, int cout, int relu, void* out,
+                     void* pool_out, int bn, int amode, int desc_mode, void* stream) {
+    int rc;
+    if ((rc = check_sm100())) return rc;
+    if (!src0 || !w_packed || !bias || !out) return fail(UNETB200_EINVAL, "NULL pointer");
+    if (pool_out && (height % 2 || width % 2)) return fail(UNETB200_EINVAL, "pool needs even H, W");
+    ConvDesc d;
+    d.src0 = src0; d.c0 = c0; d.src1 = src1; d.c1 = src1 ? c1 : 0;
+    d.w = w_packed; d.bias = bias; d.n = n; d.h = height; d.wd = width; d.cout = cout; d.relu = relu;
+    d.taps = 9; d.epi = pool_out ? ub::EPI_STORE_POOL : ub::EPI_STORE; d.out = out; d.pool = pool_out;
+    d.bn = bn; d.amode = amode; d.desc_mode = desc_mode; d.dbg = g_hook_dbg();
+    int sms = 0;
+    if ((rc = device_num_sms(&sms))) return rc;
+    Step st;
+    if ((rc = build_conv_step(d, sms, &st))) return rc;
+    return launch_step(st, static_cast<cudaStream_t>(stream));
+}
+
+int unetb200_conv3x3_head(const void* src0, int c0, const void* w_packed, const float* bias,
+                          const float* head_w, const float* head_b, int n_classes, int n, int height,
+                          int width, float* logits, uint8_t* mask, const float* logit_thr, int amode,
+                          int desc_mode, void* stream) {
+    int rc;
+    if ((rc = check_sm100())) return rc;
+    if (!src0 || !w_packed || !bias || !head_w || !head_b) return fail(UNETB200_EINVAL, "NULL pointer");
+    if (n_classes < 1 || n_classes > ub::kMaxClasses) return fail(UNETB200_EINVAL, "n_classes must be in 1..8");
+    if (mask && !logit_thr) return fail(UNETB200_EINVAL, "mask requested without thresholds");
+    ConvDesc d;
+    d.src0 = src0; d.c0 = c0; d.w = w_packed; d.bias = bias; d.n = n; d.h = height; d.wd = width;
+    d.cout = 64; d.relu = 1; d.taps = 9; d.epi = ub::EPI_HEAD; d.head_w = head_w; d.head_b = head_b;
+    d.ncls = n_classes; d.logits = logits; d.mask = mask; d.bn = 64; d.amode = amode;
+    d.desc_mode = desc_mode; d.dbg = g_hook_dbg();
+    int sms = 0;
+    if ((rc = device_num_sms(&sms))) return rc;
+    Step st;
+    if ((rc = build_conv_step(d, sms, &st))) return rc;
+    if (mask) for (int c = 0; c < n_classes; ++c) st.cp.thr[c] = logit_thr[c];
+    return launch_step(st, static_cast<cudaStream_t>(stream));
+}
+
+int unetb200_convt2x2(const void* src, int cin, const void* w_packed, const float* bias, int n,
+                      int height, int width, int cout, void* out, int bn, void* stream) {
+    int rc;
+    if ((rc = check_sm100())) return rc;
+    if (!src || !w_packed || !bias || !out) return fail(UNETB200_EINVAL, "NULL pointer");
+    ConvDesc d;
+    d.src0 = src; d.c0 = cin; d.w = w_packed; d.bias = bias; d.n = n; d.h = height; d.wd = width;
+    d.cout = cout; d.relu = 0; d.taps = 1; d.epi = ub::EPI_UPSAMPLE; d.out = out; d.bn = bn;
+    d.amode = ub::A_TAP; d.dbg = g_hook_dbg();
+    int sms = 0;
+    if ((rc = device_num_sms(&sms))) return rc;
+    Step st;
+    if ((rc = build_conv_step(d, sms, &st))) return rc;
+    return launch_step(st, static_cast<cudaStream_t>(stream));
+}
+
+int unetb200_stem(const void* x, int x_fmt, int cin, const float* w, const float* bias, int n,
+                  int height, int width, void* out, void* stream) {
+    if (!x || !w || !bias || !out) return fail(UNETB200_EINVAL, "NULL pointer");
+    Step st;
+    int rc = build_stem_step(x, x_fmt, cin, w, bias, n, height, width, out, &st);
+    if (rc) return rc;
+    return launch_step(st, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,149 @@
+"""Drop-in for the reference ``inference.py`` (reference inference.py:1-130).
+
+Same names, argument order and return types -- ``DEVICE``, ``IMG_SIZE``,
+``FIELDS``, ``load_model(checkpoint_path)``, ``preprocess(pil_img)``,
+``run_unet(pil_img, checkpoint_path) -> (masks, crops)`` -- so ``app_camera.py:16,787``
+keeps working unmodified.  Differences, all internal:
+
+* ``load_model`` caches the packed model per (checkpoint file, device) instead of
+  rebuilding it on every ``run_unet`` call (reference inference.py:58).
+* ``run_unet`` ships the resized uint8 frame to the GPU (0.79 MB instead of 3.1 MB
+  of float32); the ``/255`` of ``preprocess`` happens in the first CUDA kernel and
+  the sigmoid + per-class threshold (reference :72-79) in the last one, in logit
+  space, so only three uint8 masks come back.
+* ``run_unet_batch`` (new, additive) does the same for a list of images in one
+  batched forward.
+"""
+from __future__ import annotations
+
+import os
+import threading
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+from PIL import Image
+
+from .unet_model import UNet
+
+# ---------------------------------------------------------------- constants (reference :9-12)
+DEVICE = "cuda" if torch.cuda.is_available() else "cpu"
+IMG_SIZE = 512
+FIELDS = ["invoice_no", "date", "total_amount"]
+# sigmoid-probability thresholds per field (reference :75-79)
+THRESHOLDS = {"invoice_no": 0.25, "date": 0.40, "total_amount": 0.30}
+MAX_CHUNK = 64            # images per forward in the batched entry points
+
+_model_cache: Dict[tuple, UNet] = {}
+_cache_lock = threading.Lock()
+
+
+def load_model(checkpoint_path: str):
+    """Build ``UNet(3, 3)``, strictly load the state_dict, ``eval()`` (reference :17-24).
+
+    The result is cached per (real path, mtime, size, device): the reference re-reads the
+    124 MB checkpoint on every call, which costs ~1 s.
+    """
+    st = os.stat(checkpoint_path)
+    key = (os.path.realpath(checkpoint_path), st.st_mtime_ns, st.st_size, DEVICE)
+    with _cache_lock:
+        model = _model_cache.get(key)
+        if model is None:
+            model = UNet(n_channels=3, n_classes=3).to(DEVICE)
+            state = torch.load(checkpoint_path, map_location=DEVICE)
+            model.load_state_dict(state)
+            model.eval()
+            _model_cache.clear()          # keep one checkpoint resident
+            _model_cache[key] = model
+    return model
+
+
+def _resized_rgb_u8(pil_img: Image.Image) -> np.ndarray:
+    """``convert("RGB").resize((512, 512))`` -> uint8 (512, 512, 3)  (reference :35)."""
+    img = pil_img.convert("RGB").resize((IMG_SIZE, IMG_SIZE))
+    arr = np.asarray(img)
+    if arr.ndim != 3 or arr.shape[2] != 3:
+        raise ValueError(f"Invalid image shape: {arr.shape}")
+    return arr
+
+
+def preprocess(pil_img: Image.Image):
+    """PIL image -> float32 tensor ``[1, 3, 512, 512]`` in [0, 1] on ``DEVICE`` (reference :30-44)."""
+    arr = _resized_rgb_u8(pil_img).astype(np.float32) / 255.0
+    arr = arr.transpose(2, 0, 1)
+    return torch.from_numpy(np.ascontiguousarray(arr)).unsqueeze(0).to(DEVICE)
+
+
+def masks_to_crops(pil_img: Image.Image, masks: Dict[str, np.ndarray]) -> Dict[str, Optional[Image.Image]]:
+    """Mask -> bounding box -> crop of the ORIGINAL image (reference :84-127).
+
+    Box = min/max of the mask's pixel coordinates, scaled by (orig / 512) with ``int()``
+    truncation, grown by 15 % of its size, clamped to the image; an empty box, an empty
+    mask or a near-black crop (mean < 3) gives ``None``.
+    """
+    ow, oh = pil_img.size
+    sx, sy = ow / IMG_SIZE, oh / IMG_SIZE
+    crops: Dict[str, Optional[Image.Image]] = {}
+    for key, mask in masks.items():
+        rows = np.flatnonzero(mask.any(axis=1))
+        cols = np.flatnonzero(mask.any(axis=0))
+        if rows.size == 0 or cols.size == 0:
+            crops[key] = None
+            continue
+        x1, x2 = int(cols[0] * sx), int(cols[-1] * sx)
+        y1, y2 = int(rows[0] * sy), int(rows[-1] * sy)
+        px, py = int((x2 - x1) * 0.15), int((y2 - y1) * 0.15)
+        x1, y1 = max(0, x1 - px), max(0, y1 - py)
+        x2, y2 = min(ow, x2 + px), min(oh, y2 + py)
+        if x2 <= x1 or y2 <= y1:
+            crops[key] = None
+            continue
+        crop = pil_img.crop((x1, y1, x2, y2))
+        arr = np.array(crop)
+        crops[key] = None if (arr.size == 0 or arr.mean() < 3) else crop
+    return crops
+
+
+def _segment_u8(model: UNet, frames: np.ndarray) -> np.ndarray:
+    """uint8 frames (B, 512, 512, 3) -> uint8 masks (B, 3, 512, 512) through the CUDA engine."""
+    if DEVICE != "cuda":
+        raise RuntimeError("run_unet needs a CUDA (B200, sm_100a) device: there is no CPU path "
+                           "(the CPU oracle lives in oracle/ and is test-only)")
+    eng = model.engine(DEVICE)
+    thr = [THRESHOLDS[f] for f in FIELDS]
+    out = np.empty((frames.shape[0], len(FIELDS), IMG_SIZE, IMG_SIZE), dtype=np.uint8)
+    for lo in range(0, frames.shape[0], MAX_CHUNK):
+        chunk = torch.from_numpy(np.ascontiguousarray(frames[lo:lo + MAX_CHUNK])).pin_memory()
+        x = chunk.to(eng.device, non_blocking=True)
+        _, mask = eng.run(x, want_logits=False, thresholds=thr)
+        out[lo:lo + MAX_CHUNK] = mask.cpu().numpy()
+    return out
+
+
+def run_unet(pil_img: Image.Image, checkpoint_path: str):
+    """One image -> ``(masks, crops)`` exactly as the reference returns them (reference :50-129).
+
+    ``masks``: dict field -> ``np.bool_`` (512, 512); ``crops``: dict field -> ``PIL.Image`` or
+    ``None``; key order = ``FIELDS``.
+    """
+    model = load_model(checkpoint_path)
+    # the reference resizes twice (:63 then :35); the second resize is the identity
+    frame = _resized_rgb_u8(pil_img.resize((IMG_SIZE, IMG_SIZE)))
+    m = _segment_u8(model, frame[None])[0]
+    masks = {f: m[i].astype(bool) for i, f in enumerate(FIELDS)}
+    return masks, masks_to_crops(pil_img, masks)
+
+
+def run_unet_batch(pil_imgs: Sequence[Image.Image], checkpoint_path: str
+                   ) -> List[Tuple[Dict[str, np.ndarray], Dict[str, Optional[Image.Image]]]]:
+    """``run_unet`` for many images with one batched forward per 64 images (new entry point)."""
+    if len(pil_imgs) == 0:
+        return []
+    model = load_model(checkpoint_path)
+    frames = np.stack([_resized_rgb_u8(im.resize((IMG_SIZE, IMG_SIZE))) for im in pil_imgs])
+    m = _segment_u8(model, frames)
+    out = []
+    for b, im in enumerate(pil_imgs):
+        masks = {f: m[b, i].astype(bool) for i, f in enumerate(FIELDS)}
+        out.append((masks, masks_to_crops(im, masks)))
+    return out
