@@ -1,0 +1,312 @@
+#!/usr/bin/env python
+"""Headline benchmark: U-Net images/sec (BASELINE.json `metric`), configs[1] per GPU:
+fixture best_unet_model.pth, batch 64 x 3 x 512 x 512, bf16 tensor-core forward on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU forward (oracle port)
+
+One process per GPU (torchrun for N > 1); images are independent, so ranks shard the batch
+with no data-path collective ("scaling": "weak": 64 images per GPU per step).  Rank 0 prints
+ONE JSON line.  See DESIGN.md "Measurement" for what each field means.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "unet_forward_images_per_sec"
+UNIT = "images/s"
+GFLOP_PER_IMAGE_512 = 385.406          # algorithmic FLOPs of the 23 convs at 512x512
+
+
+def layer_flops(layer, h, w) -> float:
+    """Algorithmic FLOPs per image of one row of the layer table (padding taps counted)."""
+    hh, ww = h >> layer.level, w >> layer.level
+    if layer.kind in (0, 1):       # 3x3 convs (stem, conv3x3)
+        return 2.0 * hh * ww * layer.cout * layer.cin * 9
+    if layer.kind == 2:            # convT 2x2 s2: 4 output pixels per input pixel
+        return 2.0 * hh * ww * layer.cin * layer.cout * 4
+    return 2.0 * hh * ww * layer.cin * layer.cout      # 1x1 head
+
+
+def read_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return {"tflops": float(p["bf16_tflops_sustained"]), "tflops_burst": float(p["bf16_tflops"]),
+                "hbm_gbs": float(p["hbm_gbs"]), "source": "MEASURED_PEAKS.json (sustained bf16 figure: kernels timed inside a long step)"}
+    except Exception:
+        return {"tflops": 1400.0, "tflops_burst": 1590.0, "hbm_gbs": 6650.0,
+                "source": "fallback of B200_PROFILING.md (MEASURED_PEAKS.json absent)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [v.strip() for v in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); power.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_forward_rate(state, n_images: int, warmup: int, batch: int = 1):
+    """images/s of the oracle's fp32 CPU forward (the reference's algorithm on the host cores)."""
+    import torch
+    from oracle.unet_oracle import oracle_forward
+    from tw_invoice_unet_ocr_llm_b200.synthetic import synthetic_invoices
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    x = synthetic_invoices(batch, 512, 512, seed=42)
+    for _ in range(warmup):
+        oracle_forward(state, x)
+    times = []
+    for _ in range(max(1, n_images // batch)):
+        t0 = time.perf_counter()
+        oracle_forward(state, x)
+        times.append(time.perf_counter() - t0)
+    return batch / statistics.median(times), cores, times
+
+
+def run_reference(args, rank, world):
+    """`--impl reference`: the reference's own CPU implementation of the path.  The reference is
+    pure Python/PyTorch and cannot travel to the GPU box, so this times the oracle port (the same
+    torch.nn.functional CPU kernels, called functionally) on all host cores; rank 0 only."""
+    if rank != 0:
+        return
+    from tw_invoice_unet_ocr_llm_b200.synthetic import make_fixture_state
+    state = make_fixture_state()
+    per_step = 2                                     # bounded sample: 2 of the 64 images per step
+    rate, cores, times = cpu_forward_rate(state, per_step * args.steps, max(1, args.warmup), batch=per_step)
+    ms = 1e3 * statistics.median(times)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1] shape on the CPU path: fixture best_unet_model.pth, 3x512x512 "
+                               f"invoices, fp32 torch CPU forward, {per_step} images per step (bounded sample "
+                               "of the batch-64 step)", "image": "3x512x512", "batch_per_step": per_step},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} steps x {per_step} images, median step"},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="images per GPU per step")
+    ap.add_argument("--size", type=int, default=512)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--layers-out", default=None, help="write the per-layer table (JSON) here")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from tw_invoice_unet_ocr_llm_b200 import _native as nat
+    from tw_invoice_unet_ocr_llm_b200.launcher import GpuWorker
+    from tw_invoice_unet_ocr_llm_b200.synthetic import make_fixture_state, synthetic_invoices_u8
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA (B200) device: there is no CPU path for --impl b200")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    B, S = args.batch, args.size
+    state = make_fixture_state()
+    worker = GpuWorker(state, dev, chunk=B)          # public multi-GPU launcher building block
+    eng = worker.engine
+    thr = [0.25, 0.40, 0.30]
+
+    # synthetic invoice-shaped batch, distinct per rank; 8 distinct frames tiled to B
+    base = synthetic_invoices_u8(min(8, B), S, S, seed=7 + rank)
+    frames_u8 = np.concatenate([base] * ((B + len(base) - 1) // len(base)))[:B]
+    x_dev = torch.from_numpy(frames_u8.astype(np.float32) / 255.0).permute(0, 3, 1, 2).contiguous().to(dev)
+    logits = torch.empty((B, 3, S, S), dtype=torch.float32, device=dev)
+    mask = torch.empty((B, 3, S, S), dtype=torch.uint8, device=dev)
+
+    def step():
+        eng.run(x_dev, want_logits=True, thresholds=thr, logits_out=logits, mask_out=mask)
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    def timed(fn, k):
+        """K calls of fn bracketed by barrier + synchronize; device time via CUDA events on the
+        launching (current) stream; max over ranks."""
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        sync_all()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---------------- device-resident throughput (`value`)
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    total_ms = timed(step, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    launches_per_step = eng.last_launch_count()
+    ms_per_step = total_ms / args.steps
+    value = world * B / (ms_per_step / 1e3)
+
+    # ---------------- per-layer pass for the roofline (same K steps, events between launches)
+    eng.set_option("profile", 1)
+    step()
+    acc = None
+    sync_all()
+    for _ in range(args.steps):
+        step()
+        t = eng.layer_times_ms()
+        acc = t if acc is None else [a + b for a, b in zip(acc, t)]
+    eng.set_option("profile", 0)
+    layer_ms = [a / args.steps for a in acc]
+    layers = eng.layers
+    peaks = read_peaks()
+    table, tc_flops, tc_ms = [], 0.0, 0.0
+    for i, l in enumerate(layers):
+        if l.kind == nat.HEAD:
+            continue                                  # fused into conv1.net.3
+        fl = layer_flops(l, S, S) * B
+        if l.name.decode() == "conv1.net.3":
+            fl += layer_flops(layers[-1], S, S) * B
+        ms = layer_ms[i]
+        tf = fl / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
+        tensor = l.kind in (nat.CONV3X3, nat.CONVT2X2)
+        if tensor:
+            tc_flops += fl
+            tc_ms += ms
+        table.append({"layer": l.name.decode(), "kernel": "conv_tc_kernel (tcgen05)" if tensor else "stem_conv_kernel",
+                      "ms": round(ms, 4), "gflop": round(fl / 1e9, 2), "tflops": round(tf, 1),
+                      "frac_of_peak": round(tf / peaks["tflops"], 3)})
+    achieved = tc_flops / (tc_ms * 1e-3) / 1e12
+    roofline = {
+        "bound": "tensor", "kernel": "conv_tc_kernel<BN,TAPS,AMODE,EPI> (21 launches per step: 17 conv3x3 + 4 convT)",
+        "achieved": round(achieved, 1), "peak": peaks["tflops"], "unit": "TFLOP/s",
+        "frac": round(achieved / peaks["tflops"], 4), "traffic": None,
+        "peak_source": peaks["source"],
+        "how": "sum of algorithmic conv FLOPs of the 21 tcgen05 launches / sum of their CUDA-event durations "
+               "(events recorded between launches on the launching stream, averaged over the K steps)",
+        "share_of_step": round(tc_ms / sum(layer_ms), 4),
+    }
+    if args.layers_out and rank == 0:
+        with open(args.layers_out, "w") as f:
+            json.dump({"batch": B, "size": S, "layers": table, "ms_per_step_profiled": sum(layer_ms)}, f, indent=1)
+
+    # ---------------- end to end through the public launcher API: pinned host frames in, host masks out
+    frames_host = torch.from_numpy(frames_u8).pin_memory()
+    masks_host = torch.empty((B, 3, S, S), dtype=torch.uint8).pin_memory()
+
+    def e2e_step():
+        worker.segment(frames_host, masks_host)
+
+    for _ in range(args.warmup):
+        e2e_step()
+    e2e_ms = timed(e2e_step, args.steps) / args.steps
+    e2e = {"value": world * B / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms,
+           "h2d_bytes_per_step": int(frames_host.numel()), "d2h_bytes_per_step": int(masks_host.numel()),
+           "api": "tw_invoice_unet_ocr_llm_b200.launcher.GpuWorker.segment (uint8 frames -> uint8 masks)"}
+
+    # ---------------- CPU baseline (rank 0, N = 1 only): the oracle port on the host cores
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rate, cores, times = cpu_forward_rate(state, 8, 2, batch=1)
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{len(times)} single-image 3x512x512 fp32 forwards of the oracle after 2 warm-ups, median "
+                         f"{statistics.median(times):.3f} s"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"configs[1]: fixture best_unet_model.pth (seeded, same 136-key fp32 format), "
+                                   f"batch {B} x 3x{S}x{S} synthetic invoices per GPU, bf16 NHWC tensor-core forward, "
+                                   "fp32 NCHW input resident in HBM, outputs fp32 logits + uint8 masks",
+                       "batch_per_gpu": B, "image": f"3x{S}x{S}", "parallelism": f"dp{world} (batch sharding, no collective)",
+                       "l2": "no flush needed: per-step working set (~9 GB of activations, 201 MB input) exceeds the 126 MB L2",
+                       "gflop_per_image": GFLOP_PER_IMAGE_512 * (S * S) / (512 * 512),
+                       "achieved_tflops_whole_step": value / world * GFLOP_PER_IMAGE_512 * (S * S) / (512 * 512) / 1e3},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+            "gpu_launches": launches_per_step * args.steps,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -44,15 +44,17 @@ import os
 AMODES = [int(v) for v in os.environ.get("UNETB200_TEST_AMODES", "0,1,2").split(",")]
 
 
+@pytest.mark.parametrize("wstat", [0, 1])
 @pytest.mark.parametrize("amode", AMODES)
 @pytest.mark.parametrize("cin,cout,bn,n,h,w", [
     (64, 64, 64, 2, 32, 24),
+    (128, 64, 64, 1, 32, 32),       # conv1.net.0 shape class: two K slices, weight-stationary
     (128, 128, 128, 1, 48, 40),
     (64, 256, 256, 1, 16, 16),
     (192, 128, 64, 1, 20, 12),      # partial tiles in both directions
     (64, 64, 64, 3, 2, 2),          # smaller than one tile (deepest level of a 32x32 input)
 ])
-def test_conv3x3(cuda_dev, amode, cin, cout, bn, n, h, w):
+def test_conv3x3(cuda_dev, amode, wstat, cin, cout, bn, n, h, w):
     nat = _nat()
     g = torch.Generator(device="cpu").manual_seed(cin * 7 + cout + h)
     x = torch.randn((n, cin, h, w), generator=g).to(cuda_dev)
@@ -61,11 +63,11 @@ def test_conv3x3(cuda_dev, amode, cin, cout, bn, n, h, w):
     xb, wb = _nhwc_bf16(x), _pack3x3(wt)
     out = torch.full((n, h, w, cout), float("nan"), dtype=torch.bfloat16, device=cuda_dev)
     nat.check(nat.lib().unetb200_conv3x3(xb.data_ptr(), cin, None, 0, wb.data_ptr(), b.data_ptr(),
-                                         n, h, w, cout, 1, out.data_ptr(), None, bn, amode, 0, None))
+                                         n, h, w, cout, 1, out.data_ptr(), None, bn, amode, wstat, None))
     torch.cuda.synchronize()
     ref = F.relu(F.conv2d(_to_nchw_f32(xb), wb.float().reshape(3, 3, cout, cin).permute(2, 3, 0, 1),
                           b, padding=1))
-    _close(_to_nchw_f32(out), ref, f"conv3x3 amode={amode}")
+    _close(_to_nchw_f32(out), ref, f"conv3x3 amode={amode} wstat={wstat}")
 
 
 @pytest.mark.parametrize("amode", AMODES)
@@ -83,7 +85,7 @@ def test_conv3x3_two_sources_and_pool(cuda_dev, amode):
     pool = torch.full((n, h // 2, w // 2, cout), float("nan"), dtype=torch.bfloat16, device=cuda_dev)
     nat.check(nat.lib().unetb200_conv3x3(x0b.data_ptr(), c0, x1b.data_ptr(), c1, wb.data_ptr(),
                                          b.data_ptr(), n, h, w, cout, 1, out.data_ptr(),
-                                         pool.data_ptr(), 128, amode, 0, None))
+                                         pool.data_ptr(), 128, amode, 1, None))
     torch.cuda.synchronize()
     xin = torch.cat([_to_nchw_f32(x0b), _to_nchw_f32(x1b)], dim=1)
     ref = F.relu(F.conv2d(xin, wb.float().reshape(3, 3, cout, c0 + c1).permute(2, 3, 0, 1), b, padding=1))
@@ -148,7 +150,7 @@ def test_conv3x3_head(cuda_dev, amode):
     thr = (C.c_float * ncls)(-0.5, 0.0, 0.7)
     nat.check(nat.lib().unetb200_conv3x3_head(xb.data_ptr(), 64, wb.data_ptr(), b.data_ptr(),
                                               hw.data_ptr(), hb.data_ptr(), ncls, n, h, w,
-                                              logits.data_ptr(), mask.data_ptr(), thr, amode, 0, None))
+                                              logits.data_ptr(), mask.data_ptr(), thr, amode, 1, None))
     torch.cuda.synchronize()
     feat = F.relu(F.conv2d(_to_nchw_f32(xb), wb.float().reshape(3, 3, 64, 64).permute(2, 3, 0, 1), b, padding=1))
     ref = F.conv2d(feat, hw.reshape(ncls, 64, 1, 1), hb)

@@ -30,8 +30,14 @@
 // TMA zero-fills out-of-bounds box elements, which is the conv zero padding.
 //
 // Warp roles (256 threads, 1 CTA / SM, persistent over tiles):
-//   warp 0 : TMA producer          warp 1 : MMA issuer (one lane)
-//   warp 2 : TMEM allocator        warps 4-7 : epilogue (TMEM -> regs -> smem -> TMA store)
+//   warp 0 : TMA producer, activations      warp 1 : MMA issuer (one lane)
+//   warp 2 : TMEM allocator                 warp 3 : TMA producer, weights
+//   warps 4-7 : epilogue (TMEM -> regs -> smem -> TMA store)
+// Activations and weights have separate producers and separate mbarrier rings, so the
+// activation prefetch distance (HBM latency) does not depend on the weight ring depth.
+// Weight-stationary mode (`wstat`): when the whole [taps x Cin x BN] weight slab of the
+// layer fits in shared memory (the Cout = 64 layers and up1), it is loaded once per CTA
+// and the main loop streams activations only.
 // Two TMEM accumulators so the epilogue of tile i overlaps the MMAs of tile i+1.
 #pragma once
 #include "ptx.cuh"
@@ -64,7 +70,10 @@ struct ConvParams {
     int total_tiles;
     int relu;
     int ncls;
-    int desc_mode;           // A_HALO: 0 = base_offset 0, 1 = base_offset from address bits
+    int na, nb;              // ring depths: activation items / weight tiles (wstat: nb = all tiles)
+    int wstat;               // 1 = weight-stationary (see header)
+    int n_out;               // output staging buffers (1 or 2)
+    int off_b, off_out, off_pool, off_bar;   // smem carve-up, bytes from the 1024-aligned base
 };
 
 template <int BN, int TAPS, int AMODE>
@@ -74,25 +83,14 @@ struct ConvCfg {
     static constexpr int A_TX = A_ROWS * 128;
     static constexpr int A_STAGE = (A_TX + 1023) / 1024 * 1024;
     static constexpr int B_STAGE = BN * 128;
-    static constexpr int OUT_STAGE = 16384;
-    static constexpr int POOL_STAGE = 4096;
-    static constexpr int FIXED = 2 * OUT_STAGE + 2 * POOL_STAGE + 1024 /*barriers*/ + 1024 /*align*/ +
-                                 2304 /*static smem*/;
-    static constexpr int BUDGET = 232448 - FIXED;
-    // weights: enough stages to cover one A item's worth of taps plus slack
-    static constexpr int NB = BN == 256 ? 3 : (BN == 128 ? 5 : 8);
-    static constexpr int NA_RAW = (BUDGET - NB * B_STAGE) / A_STAGE;
-    static constexpr int NA = NA_RAW > 6 ? 6 : NA_RAW;
-    static_assert(NA >= 2, "need at least two activation stages");
-    static constexpr int OFF_A = 0;
-    static constexpr int OFF_B = OFF_A + NA * A_STAGE;
-    static constexpr int OFF_OUT = OFF_B + NB * B_STAGE;
-    static constexpr int OFF_POOL = OFF_OUT + 2 * OUT_STAGE;
-    static constexpr int OFF_BAR = OFF_POOL + 2 * POOL_STAGE;
-    static constexpr int NBAR = 2 * NA + 2 * NB + 4;
-    static constexpr int SMEM_BYTES = OFF_BAR + 1024 + 1024;   // barriers + alignment slack
     static constexpr int TMEM_COLS = 2 * BN;                   // 128 / 256 / 512
 };
+constexpr int kOutStage = 16384;      // 128 pixels x 64 channels bf16
+constexpr int kPoolStage = 4096;      // 32 pixels x 64 channels bf16
+constexpr int kMaxRing = 8;           // upper bound on na and (non-stationary) nb
+constexpr int kBarBytes = 1024;
+constexpr int kStaticSmem = 4096 + kMaxClasses * 64 * 4 + 64;   // s_bias + s_head_w + s_head_b
+constexpr int kSmemLimit = 232448;    // 227 KB per CTA on sm_100
 
 template <int BN, int TAPS, int AMODE, int EPI>
 __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
@@ -104,20 +102,21 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t sA = smem_base + Cfg::OFF_A;
-    const uint32_t sB = smem_base + Cfg::OFF_B;
-    const uint32_t sOut = smem_base + Cfg::OFF_OUT;
-    const uint32_t sPool = smem_base + Cfg::OFF_POOL;
-    const uint32_t sBar = smem_base + Cfg::OFF_BAR;
+    const uint32_t sA = smem_base;
+    const uint32_t sB = smem_base + p.off_b;
+    const uint32_t sOut = smem_base + p.off_out;
+    const uint32_t sPool = smem_base + p.off_pool;
+    const uint32_t sBar = smem_base + p.off_bar;
     const uint32_t bar_a_full = sBar;
-    const uint32_t bar_a_empty = bar_a_full + 8 * Cfg::NA;
-    const uint32_t bar_b_full = bar_a_empty + 8 * Cfg::NA;
-    const uint32_t bar_b_empty = bar_b_full + 8 * Cfg::NB;
-    const uint32_t bar_t_full = bar_b_empty + 8 * Cfg::NB;
+    const uint32_t bar_a_empty = bar_a_full + 8 * kMaxRing;
+    const uint32_t bar_b_full = bar_a_empty + 8 * kMaxRing;
+    const uint32_t bar_b_empty = bar_b_full + 8 * kMaxRing;
+    const uint32_t bar_t_full = bar_b_empty + 8 * kMaxRing;
     const uint32_t bar_t_empty = bar_t_full + 16;
     const uint32_t s_tmem_ptr = bar_t_empty + 16;
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));   // generic view of smem_base
 
+    __shared__ __align__(16) float s_bias[1024];
     __shared__ float s_head_w[kMaxClasses * 64];
     __shared__ float s_head_b[kMaxClasses];
 
@@ -132,11 +131,9 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
         if (EPI == EPI_STORE_POOL) tma_prefetch_desc(&p.tmPool);
     }
     if (warp == 1 && lane == 0) {
-        for (int i = 0; i < Cfg::NA; ++i) {
+        for (int i = 0; i < kMaxRing; ++i) {
             mbar_init(bar_a_full + 8 * i, 1);
             mbar_init(bar_a_empty + 8 * i, 1);
-        }
-        for (int i = 0; i < Cfg::NB; ++i) {
             mbar_init(bar_b_full + 8 * i, 1);
             mbar_init(bar_b_empty + 8 * i, 1);
         }
@@ -151,6 +148,7 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
         for (int i = threadIdx.x; i < p.ncls * 64; i += blockDim.x) s_head_w[i] = p.head_w[i];
         if (threadIdx.x < p.ncls) s_head_b[threadIdx.x] = p.head_b[threadIdx.x];
     }
+    for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) s_bias[i] = p.bias[i];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -161,11 +159,10 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
     const int tiles_per_img = p.tiles_x * p.tiles_y;
 
     if (warp == 0) {
-        // ============================ TMA producer ============================
+        // ===================== TMA producer: activations ======================
         if (lane == 0) {
-            uint32_t a_it = 0, b_it = 0;
+            uint32_t sa = 0, pa = 0;
             for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-                const int nb = t % p.n_blocks;
                 const int mt = t / p.n_blocks;
                 const int n = mt / tiles_per_img;
                 const int r = mt - n * tiles_per_img;
@@ -177,31 +174,45 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
                     const int ca = src0 ? (cs << 6) : (cs << 6) - p.C0;
 #pragma unroll 1
                     for (int item = 0; item < ITEMS; ++item) {
-                        {
-                            // box origin of this activation item
-                            int bx = x0, by = y0;
-                            if (TAPS == 9) {
-                                if (AMODE == A_TAP) { bx += item % 3 - 1; by += item / 3 - 1; }
-                                if (AMODE == A_COL3) { bx += item - 1; by -= 1; }
-                                if (AMODE == A_HALO) { bx -= 1; by -= 1; }
-                            }
-                            const uint32_t s = a_it % Cfg::NA, ph = (a_it / Cfg::NA) & 1;
-                            mbar_wait(bar_a_empty + 8 * s, ph ^ 1, 1, p.dbg);
-                            mbar_expect_tx(bar_a_full + 8 * s, Cfg::A_TX);
-                            tma_load_4d(sA + s * Cfg::A_STAGE, tmA, bar_a_full + 8 * s, ca, bx, by, n);
-                            ++a_it;
+                        // box origin of this activation item
+                        int bx = x0, by = y0;
+                        if (TAPS == 9) {
+                            if (AMODE == A_TAP) { bx += item % 3 - 1; by += item / 3 - 1; }
+                            if (AMODE == A_COL3) { bx += item - 1; by -= 1; }
+                            if (AMODE == A_HALO) { bx -= 1; by -= 1; }
                         }
+                        mbar_wait(bar_a_empty + 8 * sa, pa ^ 1, 1, p.dbg);
+                        mbar_expect_tx(bar_a_full + 8 * sa, Cfg::A_TX);
+                        tma_load_4d(sA + sa * Cfg::A_STAGE, tmA, bar_a_full + 8 * sa, ca, bx, by, n);
+                        if (++sa == static_cast<uint32_t>(p.na)) { sa = 0; pa ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 3) {
+        // ======================= TMA producer: weights ========================
+        if (lane == 0) {
+            if (p.wstat) {
+                // whole weight slab of this layer, once: slot = cs * TAPS + tap
+                mbar_expect_tx(bar_b_full, static_cast<uint32_t>(n_cs * TAPS) * Cfg::B_STAGE);
+                for (int cs = 0; cs < n_cs; ++cs)
+                    for (int tap = 0; tap < TAPS; ++tap)
+                        tma_load_3d(sB + (cs * TAPS + tap) * Cfg::B_STAGE, &p.tmB, bar_b_full,
+                                    cs << 6, 0, tap);
+            } else {
+                uint32_t sb = 0, pb = 0;
+                for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+                    const int nb = t % p.n_blocks;
+                    for (int cs = 0; cs < n_cs; ++cs) {
 #pragma unroll 1
-                        for (int tt = 0; tt < TPA; ++tt) {
-                            // weight tap index in the packed tensor (ky*3+kx)
-                            const int tap = TAPS == 1 ? 0 : (AMODE == A_COL3 ? tt * 3 + item
-                                                                             : item * TPA + tt);
-                            const uint32_t s = b_it % Cfg::NB, ph = (b_it / Cfg::NB) & 1;
-                            mbar_wait(bar_b_empty + 8 * s, ph ^ 1, 3, p.dbg);
-                            mbar_expect_tx(bar_b_full + 8 * s, Cfg::B_STAGE);
-                            tma_load_3d(sB + s * Cfg::B_STAGE, &p.tmB, bar_b_full + 8 * s, cs << 6,
+                        for (int i = 0; i < TAPS; ++i) {
+                            // same tap order as the MMA loop (A_COL3 walks column-major)
+                            const int tap = (TAPS == 9 && AMODE == A_COL3) ? (i % 3) * 3 + i / 3 : i;
+                            mbar_wait(bar_b_empty + 8 * sb, pb ^ 1, 3, p.dbg);
+                            mbar_expect_tx(bar_b_full + 8 * sb, Cfg::B_STAGE);
+                            tma_load_3d(sB + sb * Cfg::B_STAGE, &p.tmB, bar_b_full + 8 * sb, cs << 6,
                                         nb * BN, tap);
-                            ++b_it;
+                            if (++sb == static_cast<uint32_t>(p.nb)) { sb = 0; pb ^= 1; }
                         }
                     }
                 }
@@ -209,10 +220,21 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
         }
     } else if (warp == 1) {
         // ============================ MMA issuer ==============================
+        // One lane issues every tcgen05.mma of the CTA.  For N <= 128 an MMA retires in
+        // 32-64 cycles, so the issue path itself is kept to a couple of integer ops per MMA:
+        // descriptor high words are constants, low words are (base + constant) in 16-byte
+        // units, and mbarrier probes for the next stage are issued ahead of the MMAs.
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc_bf16(BN);
             constexpr uint32_t a_sbo = (TAPS == 9 && AMODE == A_HALO) ? 10 * 128 : 1024;
-            uint32_t a_it = 0, b_it = 0, tile_it = 0;
+            constexpr uint32_t a_hi = umma_desc_hi_sw128(a_sbo);
+            constexpr uint32_t b_hi = umma_desc_hi_sw128(1024);
+            uint32_t sa = 0, pa = 0, sb = 0, pb = 0, tile_it = 0;
+            if (p.wstat) {
+                mbar_wait(bar_b_full, 0, 8, p.dbg);
+                tc_fence_after();
+            }
+            const uint32_t b_lo0 = umma_desc_lo(sB);
             for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tile_it) {
                 const uint32_t acc = tile_it & 1, acc_ph = (tile_it >> 1) & 1;
                 mbar_wait(bar_t_empty + 8 * acc, acc_ph ^ 1, 4, p.dbg);
@@ -222,31 +244,52 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
                 for (int cs = 0; cs < n_cs; ++cs) {
 #pragma unroll 1
                     for (int item = 0; item < ITEMS; ++item) {
-                        const uint32_t sa = a_it % Cfg::NA, pa = (a_it / Cfg::NA) & 1;
                         mbar_wait(bar_a_full + 8 * sa, pa, 5, p.dbg);
-#pragma unroll 1
-                        for (int tt = 0; tt < TPA; ++tt) {
-                            const uint32_t sb = b_it % Cfg::NB, pb = (b_it / Cfg::NB) & 1;
-                            mbar_wait(bar_b_full + 8 * sb, pb, 6, p.dbg);
-                            tc_fence_after();
-                            uint32_t a_addr = sA + sa * Cfg::A_STAGE;
-                            if (TAPS == 9 && AMODE == A_COL3) a_addr += tt * 1024;
-                            if (TAPS == 9 && AMODE == A_HALO) a_addr += ((tt / 3) * 10 + (tt % 3)) * 128;
-                            const uint32_t b_addr = sB + sb * Cfg::B_STAGE;
-                            const uint32_t a_bo =
-                                (TAPS == 9 && AMODE == A_HALO && p.desc_mode == 1) ? ((a_addr >> 7) & 7) : 0;
+                        tc_fence_after();
+                        const uint32_t a_lo0 = umma_desc_lo(sA + sa * Cfg::A_STAGE);
+                        if (p.wstat) {
+                            // resident weights: slot = cs * TAPS + tap, no barrier traffic
+                            const uint32_t b_cs = b_lo0 + (cs * TAPS) * (Cfg::B_STAGE >> 4);
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                const uint64_t ad = umma_desc_sw128(a_addr + k * 32, a_sbo, a_bo);
-                                const uint64_t bd = umma_desc_sw128(b_addr + k * 32, 1024, 0);
-                                umma_bf16(d_tmem, ad, bd, idesc, accumulate);
-                                accumulate = 1;
+                            for (int tt = 0; tt < TPA; ++tt) {
+                                const int tap_c = TAPS == 1 ? 0 : (AMODE == A_COL3 ? tt * 3 : tt);
+                                const uint32_t tap_r = (TAPS == 9 && AMODE != A_HALO) ? item * (AMODE == A_COL3 ? 1 : TPA) : 0;
+                                const uint32_t a_off = TAPS == 1 ? 0
+                                                     : (AMODE == A_COL3 ? tt * (1024 >> 4)
+                                                     : (AMODE == A_HALO ? ((tt / 3) * 10 + (tt % 3)) * (128 >> 4) : 0));
+                                const uint32_t b_lo = b_cs + (tap_c + tap_r) * (Cfg::B_STAGE >> 4);
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    umma_bf16(d_tmem, umma_desc(a_lo0 + a_off + 2 * k, a_hi),
+                                              umma_desc(b_lo + 2 * k, b_hi), idesc, accumulate);
+                                    accumulate = 1;
+                                }
                             }
-                            umma_commit(bar_b_empty + 8 * sb);
-                            ++b_it;
+                        } else {
+                            bool ready = mbar_try_wait(bar_b_full + 8 * sb, pb);
+#pragma unroll
+                            for (int tt = 0; tt < TPA; ++tt) {
+                                if (!ready) mbar_wait(bar_b_full + 8 * sb, pb, 6, p.dbg);
+                                tc_fence_after();
+                                const uint32_t b_lo = b_lo0 + sb * (Cfg::B_STAGE >> 4);
+                                const uint32_t cur = sb;
+                                if (++sb == static_cast<uint32_t>(p.nb)) { sb = 0; pb ^= 1; }
+                                // probe the next weight stage now; the answer is needed after these MMAs
+                                ready = mbar_try_wait(bar_b_full + 8 * sb, pb);
+                                const uint32_t a_off = TAPS == 1 ? 0
+                                                     : (AMODE == A_COL3 ? tt * (1024 >> 4)
+                                                     : (AMODE == A_HALO ? ((tt / 3) * 10 + (tt % 3)) * (128 >> 4) : 0));
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    umma_bf16(d_tmem, umma_desc(a_lo0 + a_off + 2 * k, a_hi),
+                                              umma_desc(b_lo + 2 * k, b_hi), idesc, accumulate);
+                                    accumulate = 1;
+                                }
+                                umma_commit(bar_b_empty + 8 * cur);
+                            }
                         }
                         umma_commit(bar_a_empty + 8 * sa);
-                        ++a_it;
+                        if (++sa == static_cast<uint32_t>(p.na)) { sa = 0; pa ^= 1; }
                     }
                 }
                 umma_commit(bar_t_full + 8 * acc);
@@ -281,7 +324,7 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
                     tmem_ld_wait();
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
-                        float f = __uint_as_float(v[i]) + __ldg(p.bias + half * 32 + i);
+                        float f = __uint_as_float(v[i]) + s_bias[half * 32 + i];
                         f = p.relu ? fmaxf(f, 0.f) : f;
 #pragma unroll
                         for (int c = 0; c < kMaxClasses; ++c)
@@ -310,10 +353,13 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
                 const int gcol = nb * BN + j * 64;            // global column of this 64-wide chunk
                 const int tapo = EPI == EPI_UPSAMPLE ? gcol / p.Cout : 0;
                 const int ch0 = EPI == EPI_UPSAMPLE ? gcol - tapo * p.Cout : gcol;
-                const uint32_t obuf = sOut + (chunk_it & 1) * Cfg::OUT_STAGE;
-                const uint32_t pbuf = sPool + (chunk_it & 1) * Cfg::POOL_STAGE;
-                // staging buffer (chunk_it & 1) was last read by the store issued two chunks ago
-                if (et == 0) tma_store_wait_read<1>();
+                const uint32_t buf = p.n_out == 2 ? (chunk_it & 1) : 0;
+                const uint32_t obuf = sOut + buf * kOutStage;
+                const uint32_t pbuf = sPool + buf * kPoolStage;
+                // the staging buffer was last read by the store issued n_out chunks ago
+                if (et == 0) {
+                    if (p.n_out == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
+                }
                 named_bar_sync(1, 128);
                 uint32_t pk[32];
 #pragma unroll
@@ -323,8 +369,7 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
                     tmem_ld_wait();
 #pragma unroll
                     for (int i = 0; i < 32; i += 4) {
-                        const float4 b4 =
-                            __ldg(reinterpret_cast<const float4*>(p.bias + ch0 + half * 32 + i));
+                        const float4 b4 = *reinterpret_cast<const float4*>(s_bias + ch0 + half * 32 + i);
                         float f0 = __uint_as_float(v[i + 0]) + b4.x;
                         float f1 = __uint_as_float(v[i + 1]) + b4.y;
                         float f2 = __uint_as_float(v[i + 2]) + b4.z;

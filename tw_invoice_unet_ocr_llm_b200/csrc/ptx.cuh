@@ -186,16 +186,20 @@ __device__ __forceinline__ void tmem_ld_wait() {
 // Shared-memory matrix descriptor, K-major operand, 128-byte swizzle
 // (bit layout: cute/arch/mma_sm100_desc.hpp SmemDescriptor, version_=1).
 //   rows are 128 B (64 bf16 of K), 8-row groups are `sbo_bytes` apart.
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t sbo_bytes,
-                                                    uint32_t base_offset) {
-    uint64_t d = 0;
-    d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);          // start address
-    d |= static_cast<uint64_t>(1) << 16;                             // LBO (ignored, swizzled K-major)
-    d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;     // SBO
-    d |= static_cast<uint64_t>(1) << 46;                             // descriptor version (sm_100)
-    d |= static_cast<uint64_t>(base_offset & 7) << 49;               // swizzle base offset
-    d |= static_cast<uint64_t>(2) << 61;                             // SWIZZLE_128B
-    return d;
+// Split into a constant high word and a low word that is linear in the start address
+// (units of 16 B), so stepping along K (+32 B = +2) or to another tap is a single add.
+//   lo : [0,14) start address >> 4, [16,30) LBO >> 4 (= 1, ignored for swizzled K-major)
+//   hi : [0,14) SBO >> 4, [14,16) version = 1, [17,20) base offset = 0, [29,32) SWIZZLE_128B = 2
+// The swizzle XOR is applied by the hardware on absolute shared-memory address bits, so a
+// start address that is not 1024-byte aligned (the shifted halo views) needs no base offset.
+__host__ __device__ constexpr uint32_t umma_desc_hi_sw128(uint32_t sbo_bytes) {
+    return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) | (2u << 29);
+}
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr) {
+    return ((smem_addr & 0x3FFFF) >> 4) | (1u << 16);
+}
+__device__ __forceinline__ uint64_t umma_desc(uint32_t lo, uint32_t hi) {
+    return (static_cast<uint64_t>(hi) << 32) | lo;
 }
 // Instruction descriptor: bf16 x bf16 -> fp32, both operands K-major, M=128.
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int n) {

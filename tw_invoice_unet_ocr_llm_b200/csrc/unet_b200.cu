@@ -177,14 +177,16 @@ typedef void (*ConvKernel)(const ub::ConvParams);
 
 struct ConvLaunch {
     ConvKernel fn = nullptr;
-    int smem = 0;
+    int a_stage = 0, b_stage = 0;   // bytes per activation item / weight tile
+    int smem = 0;                   // dynamic shared memory of this launch (set by plan_smem)
 };
 
 template <int BN, int TAPS, int AMODE, int EPI>
 ConvLaunch conv_inst() {
     ConvLaunch l;
     l.fn = ub::conv_tc_kernel<BN, TAPS, AMODE, EPI>;
-    l.smem = ub::ConvCfg<BN, TAPS, AMODE>::SMEM_BYTES;
+    l.a_stage = ub::ConvCfg<BN, TAPS, AMODE>::A_STAGE;
+    l.b_stage = ub::ConvCfg<BN, TAPS, AMODE>::B_STAGE;
     return l;
 }
 
@@ -260,9 +262,49 @@ struct ConvDesc {
     int ncls = 0;
     float* logits = nullptr;
     uint8_t* mask = nullptr;
-    int bn = 128, amode = ub::A_COL3, desc_mode = 0;
+    int bn = 128, amode = ub::A_COL3;
+    int wstat = 1;              // allow weight-stationary mode when it fits
     int* dbg = nullptr;
 };
+
+// Shared-memory carve-up of one launch: [A ring][B ring or resident slab][out staging][pool
+// staging][barriers].  Weight-stationary when the layer has one column block and its whole
+// weight slab fits beside at least two activation stages.
+int plan_smem(ConvLaunch* cl, ub::ConvParams* p, int taps, int n_cs, int n_blocks, int bn, bool pool,
+              bool has_out, int allow_wstat) {
+    const int budget = ub::kSmemLimit - ub::kStaticSmem - 1024 /*alignment slack*/;
+    const int pool_b = pool ? 2 * ub::kPoolStage : 0;
+    const int slab = taps * n_cs * cl->b_stage;
+    int n_out = has_out ? 2 : 0, na = 0, nb = 0, wstat = 0;
+    if (allow_wstat && n_blocks == 1) {
+        for (int no = n_out; no >= (has_out ? 1 : 0) && !wstat; --no) {
+            const int rest = budget - ub::kBarBytes - pool_b - no * ub::kOutStage - slab;
+            if (rest >= 2 * cl->a_stage) {
+                wstat = 1;
+                n_out = no;
+                nb = taps * n_cs;
+                na = rest / cl->a_stage;
+            }
+        }
+    }
+    if (!wstat) {
+        nb = bn == 256 ? 3 : (bn == 128 ? 5 : 8);
+        const int rest = budget - ub::kBarBytes - pool_b - n_out * ub::kOutStage - nb * cl->b_stage;
+        na = rest / cl->a_stage;
+    }
+    if (na > ub::kMaxRing) na = ub::kMaxRing;
+    if (na < 2) return fail(UNETB200_EINVAL, "conv: shared memory plan does not fit");
+    p->na = na;
+    p->nb = nb;
+    p->wstat = wstat;
+    p->n_out = n_out ? n_out : 1;
+    p->off_b = na * cl->a_stage;
+    p->off_out = p->off_b + nb * cl->b_stage;
+    p->off_pool = p->off_out + n_out * ub::kOutStage;
+    p->off_bar = p->off_pool + pool_b;
+    cl->smem = p->off_bar + ub::kBarBytes + 1024;
+    return 0;
+}
 
 int build_conv_step(const ConvDesc& d, int num_sms, Step* st) {
     if (d.c0 <= 0 || d.c0 % 64 || d.c1 % 64 || d.c1 < 0)
@@ -332,7 +374,9 @@ int build_conv_step(const ConvDesc& d, int num_sms, Step* st) {
     p.total_tiles = static_cast<int>(total);
     p.relu = d.relu;
     p.ncls = d.ncls;
-    p.desc_mode = d.desc_mode;
+    if ((rc = plan_smem(&st->conv, &p, d.taps == 9 ? 9 : 1, cin / 64, p.n_blocks, bn,
+                        d.epi == ub::EPI_STORE_POOL, d.epi != ub::EPI_HEAD, d.wstat)))
+        return rc;
     st->grid = dim3(static_cast<unsigned>(total < num_sms ? total : num_sms));
     st->block = dim3(256);
     return 0;
@@ -350,7 +394,7 @@ int launch_step(Step& st, cudaStream_t stream) {
             if (it == configured.end() || !(it->second & (1 << dev))) {
                 UB_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(st.conv.fn),
                                              cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             st.conv.smem));
+                                             ub::kSmemLimit - ub::kStaticSmem));
                 configured[reinterpret_cast<const void*>(st.conv.fn)] |= (1 << dev);
             }
         }
@@ -405,7 +449,7 @@ int check_sm100() {
     return 0;
 }
 
-typedef std::tuple<const void*, int, int, int, int, void*, float*, uint8_t*, int, int> PlanKey;
+typedef std::tuple<const void*, int, int, int, int, void*, float*, uint8_t*> PlanKey;
 
 struct Plan {
     std::vector<Step> steps;
@@ -421,8 +465,8 @@ struct unetb200_handle_s {
     int device = 0;
     int num_sms = 0;
     int amode = ub::A_HALO;
-    int bn_max = 128;
-    int desc_mode = 0;
+    int bn_max = 256;
+    int wstat = 1;
     int profile = 0;
     int* dbg = nullptr;         // pinned, device-visible watchdog record
     std::map<PlanKey, Plan> plans;
@@ -478,7 +522,7 @@ int build_plan(unetb200_handle_t h, const void* x, int x_fmt, int n, int H, int 
         d.n = n; d.h = H >> lvl; d.wd = W >> lvl; d.cout = h->layers[li].cout;
         d.relu = 1; d.taps = 9; d.epi = pool ? ub::EPI_STORE_POOL : ub::EPI_STORE;
         d.out = out; d.pool = pool;
-        d.bn = h->bn_max; d.amode = h->amode; d.desc_mode = h->desc_mode; d.dbg = h->dbg;
+        d.bn = h->bn_max; d.amode = h->amode; d.wstat = h->wstat; d.dbg = h->dbg;
         Step st;
         if ((rc = build_conv_step(d, h->num_sms, &st))) return rc;
         st.layer = li;
@@ -491,7 +535,7 @@ int build_plan(unetb200_handle_t h, const void* x, int x_fmt, int n, int H, int 
         d.w = Wp(li); d.bias = Bp(li);
         d.n = n; d.h = H >> lvl; d.wd = W >> lvl; d.cout = h->layers[li].cout;
         d.relu = 0; d.taps = 1; d.epi = ub::EPI_UPSAMPLE; d.out = out;
-        d.bn = h->bn_max; d.amode = ub::A_TAP; d.dbg = h->dbg;
+        d.bn = h->bn_max; d.amode = ub::A_TAP; d.wstat = h->wstat; d.dbg = h->dbg;
         Step st;
         if ((rc = build_conv_step(d, h->num_sms, &st))) return rc;
         st.layer = li;
@@ -534,7 +578,7 @@ int build_plan(unetb200_handle_t h, const void* x, int x_fmt, int n, int H, int 
             d.n = n; d.h = H; d.wd = W; d.cout = bw; d.relu = 1; d.taps = 9; d.epi = ub::EPI_HEAD;
             d.head_w = reinterpret_cast<const float*>(Wp(22)); d.head_b = Bp(22);
             d.ncls = h->arch.n_classes; d.logits = logits; d.mask = mask;
-            d.bn = 64; d.amode = h->amode; d.desc_mode = h->desc_mode; d.dbg = h->dbg;
+            d.bn = 64; d.amode = h->amode; d.wstat = h->wstat; d.dbg = h->dbg;
             Step st;
             if ((rc = build_conv_step(d, h->num_sms, &st))) return rc;
             st.layer = 21;
@@ -651,6 +695,8 @@ int unetb200_create(const unetb200_arch_t* arch, const void* blob_dev, uint64_t 
     if (env) h->amode = atoi(env);
     env = getenv("UNETB200_BN_MAX");
     if (env) h->bn_max = atoi(env);
+    env = getenv("UNETB200_WSTAT");
+    if (env) h->wstat = atoi(env) ? 1 : 0;
     *out = h;
     return 0;
 }
@@ -673,8 +719,8 @@ int unetb200_set_option(unetb200_handle_t h, const char* key, int value) {
     } else if (k == "bn_max") {
         if (!(value == 64 || value == 128 || value == 256)) return fail(UNETB200_EINVAL, "bn_max must be 64/128/256");
         h->bn_max = value;
-    } else if (k == "desc_mode") {
-        h->desc_mode = value ? 1 : 0;
+    } else if (k == "wstat") {
+        h->wstat = value ? 1 : 0;
     } else if (k == "profile") {
         h->profile = value ? 1 : 0;
     } else {
@@ -689,7 +735,7 @@ int unetb200_get_option(unetb200_handle_t h, const char* key, int* value) {
     std::string k(key);
     if (k == "amode") *value = h->amode;
     else if (k == "bn_max") *value = h->bn_max;
-    else if (k == "desc_mode") *value = h->desc_mode;
+    else if (k == "wstat") *value = h->wstat;
     else if (k == "profile") *value = h->profile;
     else if (k == "num_sms") *value = h->num_sms;
     else return fail(UNETB200_EINVAL, "unknown option " + k);
@@ -723,7 +769,7 @@ int unetb200_forward(unetb200_handle_t h, const void* x, int x_fmt, int n, int h
     int dev = -1;
     UB_CUDA(cudaGetDevice(&dev));
     if (dev != h->device) UB_CUDA(cudaSetDevice(h->device));
-    PlanKey key(x, x_fmt, n, height, width, workspace, logits, mask, h->amode, h->bn_max);
+    PlanKey key(x, x_fmt, n, height, width, workspace, logits, mask);
     auto it = h->plans.find(key);
     if (it == h->plans.end()) {
         Plan plan;
@@ -791,7 +837,7 @@ static int* g_hook_dbg() {
 
 int unetb200_conv3x3(const void* src0, int c0, const void* src1, int c1, const void* w_packed,
                      const float* bias, int n, int height, int width, int cout, int relu, void* out,
-                     void* pool_out, int bn, int amode, int desc_mode, void* stream) {
+                     void* pool_out, int bn, int amode, int wstat, void* stream) {
     int rc;
     if ((rc = check_sm100())) return rc;
     if (!src0 || !w_packed || !bias || !out) return fail(UNETB200_EINVAL, "NULL pointer");
@@ -800,7 +846,7 @@ int unetb200_conv3x3(const void* src0, int c0, const void* src1, int c1, const v
     d.src0 = src0; d.c0 = c0; d.src1 = src1; d.c1 = src1 ? c1 : 0;
     d.w = w_packed; d.bias = bias; d.n = n; d.h = height; d.wd = width; d.cout = cout; d.relu = relu;
     d.taps = 9; d.epi = pool_out ? ub::EPI_STORE_POOL : ub::EPI_STORE; d.out = out; d.pool = pool_out;
-    d.bn = bn; d.amode = amode; d.desc_mode = desc_mode; d.dbg = g_hook_dbg();
+    d.bn = bn; d.amode = amode; d.wstat = wstat; d.dbg = g_hook_dbg();
     int sms = 0;
     if ((rc = device_num_sms(&sms))) return rc;
     Step st;
@@ -811,7 +857,7 @@ int unetb200_conv3x3(const void* src0, int c0, const void* src1, int c1, const v
 int unetb200_conv3x3_head(const void* src0, int c0, const void* w_packed, const float* bias,
                           const float* head_w, const float* head_b, int n_classes, int n, int height,
                           int width, float* logits, uint8_t* mask, const float* logit_thr, int amode,
-                          int desc_mode, void* stream) {
+                          int wstat, void* stream) {
     int rc;
     if ((rc = check_sm100())) return rc;
     if (!src0 || !w_packed || !bias || !head_w || !head_b) return fail(UNETB200_EINVAL, "NULL pointer");
@@ -821,7 +867,7 @@ int unetb200_conv3x3_head(const void* src0, int c0, const void* w_packed, const 
     d.src0 = src0; d.c0 = c0; d.w = w_packed; d.bias = bias; d.n = n; d.h = height; d.wd = width;
     d.cout = 64; d.relu = 1; d.taps = 9; d.epi = ub::EPI_HEAD; d.head_w = head_w; d.head_b = head_b;
     d.ncls = n_classes; d.logits = logits; d.mask = mask; d.bn = 64; d.amode = amode;
-    d.desc_mode = desc_mode; d.dbg = g_hook_dbg();
+    d.wstat = wstat; d.dbg = g_hook_dbg();
     int sms = 0;
     if ((rc = device_num_sms(&sms))) return rc;
     Step st;
