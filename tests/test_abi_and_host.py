@@ -1,0 +1,130 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/unetb200.h
+declares, argument validation works without a GPU, the drop-in modules keep the reference's
+surface, and the package never imports the oracle."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def nat():
+    import __graft_entry__ as g
+    g.build()
+    from tw_invoice_unet_ocr_llm_b200 import _native
+    return _native
+
+
+def test_header_symbols_all_exported(nat):
+    hdr = open(os.path.join(ROOT, "include", "unetb200.h")).read()
+    declared = set(re.findall(r"\b(unetb200_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(nat.SYMBOLS), declared ^ set(nat.SYMBOLS)
+    lib = nat.lib()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.unetb200_abi_version() == 1
+
+
+def test_layer_table_and_blob_layout(nat):
+    arch = nat.Arch(3, 3, 64)
+    layers = nat.layer_table(arch)
+    assert len(layers) == 23
+    names = [l.name.decode() for l in layers]
+    assert names[0] == "down1.net.0" and names[-1] == "out_conv" and names[10] == "up4"
+    # every conv of the reference module appears exactly once, in forward order
+    from tw_invoice_unet_ocr_llm_b200.unet_model import UNet
+    convs = [n for n, m in UNet().named_modules() if isinstance(m, (torch.nn.Conv2d, torch.nn.ConvTranspose2d))]
+    assert sorted(convs) == sorted(names)
+    end = 0
+    for l in layers:
+        assert l.w_off >= end and l.w_off % 256 == 0 and l.b_off >= l.w_off + l.w_bytes and l.b_off % 256 == 0
+        end = l.b_off + l.b_bytes
+    assert nat.lib().unetb200_packed_bytes(C.byref(arch)) >= end
+    total_w = sum(l.w_bytes for l in layers)
+    assert 62_000_000 < total_w < 62_300_000        # 31.04 M weights in bf16 ("62 MB")
+
+
+def test_argument_validation_without_gpu(nat):
+    lib = nat.lib()
+    bad = nat.Arch(3, 3, 32)
+    assert lib.unetb200_num_layers(C.byref(bad)) == -1
+    assert "base_width" in nat.last_error()
+    assert lib.unetb200_packed_bytes(C.byref(nat.Arch(2, 3, 64))) == 0
+    l = nat.Layer()
+    assert lib.unetb200_layer_info(C.byref(nat.Arch(3, 3, 64)), 99, C.byref(l)) == nat.EINVAL
+    assert lib.unetb200_forward(None, None, 0, 1, 64, 64, None, 0, None, None, None, None) == nat.EINVAL
+    assert lib.unetb200_workspace_bytes(None, 1, 64, 64) == 0
+    if not torch.cuda.is_available():
+        h = C.c_void_p()
+        rc = lib.unetb200_create(C.byref(nat.Arch(3, 3, 64)), C.c_void_p(16), 1 << 30, 0, C.byref(h))
+        assert rc in (nat.ECUDA, nat.EARCH) and nat.last_error()      # no device: loud failure, no fallback
+
+
+def test_module_surface_matches_reference(fixture_state):
+    from tw_invoice_unet_ocr_llm_b200 import inference as inf
+    from tw_invoice_unet_ocr_llm_b200.unet_model import DoubleConv, UNet
+    m = UNet()
+    assert (m.n_channels, m.n_classes) == (3, 3)
+    assert [n for n, _ in m.named_children()] == ["down1", "down2", "down3", "down4", "pool", "bottleneck",
+                                                  "up4", "conv4", "up3", "conv3", "up2", "conv2", "up1",
+                                                  "conv1", "out_conv"]
+    assert isinstance(m.down1, DoubleConv) and len(m.down1.net) == 6
+    assert float(m.out_conv.bias.detach()[0]) == -4.0                    # reference unet_model.py:53
+    res = m.load_state_dict(fixture_state, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    assert list(m.state_dict()) == list(fixture_state)
+    assert inf.IMG_SIZE == 512 and inf.FIELDS == ["invoice_no", "date", "total_amount"]
+    assert inf.DEVICE in ("cuda", "cpu")
+    for fn in ("load_model", "preprocess", "run_unet", "run_unet_batch"):
+        assert callable(getattr(inf, fn))
+
+
+def test_eval_forward_has_no_cpu_path(fixture_state):
+    from tw_invoice_unet_ocr_llm_b200.unet_model import UNet
+    m = UNet().eval()
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        m(torch.zeros(1, 3, 32, 32))
+
+
+def test_train_mode_forward_is_the_reference_graph(fixture_state):
+    """train.py:103,137 uses the same class in train mode: batch statistics + autograd keep working
+    and match the oracle when BatchNorm is frozen to running statistics."""
+    from oracle.unet_oracle import oracle_forward
+    from tw_invoice_unet_ocr_llm_b200.synthetic import synthetic_invoices
+    from tw_invoice_unet_ocr_llm_b200.unet_model import UNet
+    m = UNet()
+    m.load_state_dict(fixture_state)
+    m.train()
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            mod.eval()
+    x = synthetic_invoices(1, 32, 32, seed=1).requires_grad_(True)
+    z = m(x)
+    assert torch.allclose(z, oracle_forward(fixture_state, x.detach()), atol=1e-5)
+    z.sum().backward()
+    assert x.grad is not None and m.down1.net[0].weight.grad is not None
+
+
+def test_logit_thresholds():
+    from tw_invoice_unet_ocr_llm_b200.engine import logit_thresholds
+    thr = logit_thresholds([0.25, 0.40, 0.30])
+    assert np.allclose(thr, [-1.0986123, -0.4054651, -0.8472979], atol=1e-6)
+    z = torch.linspace(-3, 3, 20001)
+    for t, lt in zip([0.25, 0.40, 0.30], thr):
+        a = (torch.sigmoid(z) > t)
+        b = z > np.float32(lt)
+        assert int((a != b).sum()) <= 1
+
+
+def test_package_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "tw_invoice_unet_ocr_llm_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f

@@ -1,0 +1,111 @@
+"""Host logic of the multi-GPU launcher on CPU: shard/chunk arithmetic, order-preserving
+scatter/gather with fake workers, and the one-process-per-GPU gather over gloo (world 2)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from tw_invoice_unet_ocr_llm_b200.launcher import (MultiGpuSegmenter, chunk_bounds, gather_masks,
+                                                   shard_bounds)
+
+
+@pytest.mark.parametrize("total,world", [(512, 8), (512, 3), (5, 8), (0, 2), (64, 1), (1, 2)])
+def test_shard_bounds_partition(total, world):
+    spans = [shard_bounds(total, world, r) for r in range(world)]
+    assert spans[0][0] == 0 and spans[-1][1] == total
+    for (a, b), (c, d) in zip(spans, spans[1:]):
+        assert b == c and b >= a
+    sizes = [b - a for a, b in spans]
+    assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_bounds(total, world, world)
+
+
+def test_chunk_bounds():
+    assert chunk_bounds(0, 130, 64) == [(0, 64), (64, 128), (128, 130)]
+    assert chunk_bounds(5, 5, 64) == []
+    assert chunk_bounds(3, 10, 100) == [(3, 10)]
+    with pytest.raises(ValueError):
+        chunk_bounds(0, 1, 0)
+
+
+class FakeWorker:
+    """Stands in for GpuWorker: 'mask' = a deterministic function of each frame."""
+
+    def __init__(self, dev):
+        self.dev = dev
+        self.seen = []
+
+    def segment(self, frames, out):
+        self.seen.append(frames.shape[0])
+        f = frames.to(torch.int32)
+        out.copy_((f.sum(dim=(1, 2))[:, :, None, None] % 251).to(torch.uint8).expand_as(out))
+
+
+@pytest.mark.parametrize("b,ndev", [(10, 4), (3, 8), (64, 2), (1, 1)])
+def test_multi_gpu_segmenter_preserves_order(b, ndev):
+    rng = np.random.default_rng(b)
+    frames = rng.integers(0, 256, (b, 16, 16, 3), dtype=np.uint8)
+    seg = MultiGpuSegmenter(None, devices=list(range(ndev)), worker_factory=FakeWorker)
+    out = seg.segment(frames)
+    assert out.shape == (b, 3, 16, 16) and out.dtype == torch.uint8
+    expect = (frames.astype(np.int64).sum(axis=(1, 2)) % 251).astype(np.uint8)
+    assert np.array_equal(out[:, :, 0, 0].numpy(), expect)
+    assert sum(sum(w.seen) for w in seg.workers) == b
+    with pytest.raises(ValueError):
+        seg.segment(np.zeros((2, 16, 16, 4), dtype=np.uint8))
+
+
+def test_worker_error_propagates():
+    class Boom(FakeWorker):
+        def segment(self, frames, out):
+            raise RuntimeError("device lost")
+    seg = MultiGpuSegmenter(None, devices=[0, 1], worker_factory=Boom)
+    with pytest.raises(RuntimeError, match="device lost"):
+        seg.segment(np.zeros((4, 16, 16, 3), dtype=np.uint8))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _gloo_rank(rank, world, port, total, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        lo, hi = shard_bounds(total, world, rank)
+        local = torch.arange(lo, hi, dtype=torch.uint8).view(-1, 1, 1, 1).expand(-1, 3, 4, 4).contiguous()
+        full = gather_masks(local, total)
+        if rank == 0:
+            q.put(full.numpy())
+        else:
+            assert full is None
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("total", [7, 8])
+def test_gather_masks_gloo_world2(total):
+    """The N>1 layout of bench.py / torchrun: each rank owns a contiguous shard, rank 0 gathers
+    the uint8 masks on the host; no GPU collective exists on the data path."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gloo_rank, args=(r, 2, port, total, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    full = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert full.shape == (total, 3, 4, 4)
+    assert np.array_equal(full[:, 0, 0, 0], np.arange(total, dtype=np.uint8))
