@@ -89,7 +89,7 @@ int unetb200_create(const unetb200_arch_t* arch, const void* blob_dev, uint64_t 
                     int device, unetb200_handle_t* out);
 int unetb200_destroy(unetb200_handle_t h);
 
-/* options: "amode" (UNETB200_A_*), "bn_max" (64/128/256), "wstat" (0/1), "profile" (0/1) */
+/* options: "amode" (UNETB200_A_*), "bn_max" (64/128/256), "wstat" (0/1), "stem_tc" (0/1), "profile" (0/1) */
 int unetb200_set_option(unetb200_handle_t h, const char* key, int value);
 int unetb200_get_option(unetb200_handle_t h, const char* key, int* value);
 
@@ -129,7 +129,13 @@ int unetb200_conv3x3_head(const void* src0, int c0, const void* w_packed, const 
 /* ConvTranspose2d(k=2,s=2): src [N,H,W,cin] bf16 -> out [N,2H,2W,cout] bf16. w_packed [4*cout][cin]. */
 int unetb200_convt2x2(const void* src, int cin, const void* w_packed, const float* bias, int n,
                       int height, int width, int cout, void* out, int bn, void* stream);
-/* First conv (n_channels -> 64) + ReLU: x (format x_fmt) -> out [N,H,W,64] bf16. w fp32 [9*cin][64]. */
+/* First conv on the tensor cores (n_channels 1 or 3): w_tc = the bf16 hi/lo [64][128] layout that
+ * unetb200_pack_layer(index 0) writes at blob + w_off + unetb200_stem_tc_offset(cin). */
+int unetb200_stem_tc(const void* x, int x_fmt, int cin, const void* w_tc, const float* bias, int n,
+                     int height, int width, void* out, void* stream);
+uint64_t unetb200_stem_tc_offset(int cin);
+/* First conv (n_channels -> 64) + ReLU on the CUDA cores (any n_channels in {1,3,4}):
+ * x (format x_fmt) -> out [N,H,W,64] bf16. w fp32 [9*cin][64] (start of the stem's blob region). */
 int unetb200_stem(const void* x, int x_fmt, int cin, const float* w, const float* bias, int n,
                   int height, int width, void* out, void* stream);
 

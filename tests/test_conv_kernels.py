@@ -132,6 +132,50 @@ def test_stem(cuda_dev, fmt):
     _close(_to_nchw_f32(out), ref, f"stem {fmt}")
 
 
+@pytest.mark.parametrize("fmt", ["f32", "u8"])
+@pytest.mark.parametrize("n,h,w", [(2, 40, 48), (1, 16, 16), (3, 4, 6)])
+def test_stem_tensor_core(cuda_dev, fmt, n, h, w):
+    """First conv on the tensor cores: in-kernel im2col, bf16 hi/lo split GEMM.  Must be as
+    accurate as the fp32 CUDA-core stem (error dominated by the single bf16 output rounding),
+    and exercises unetb200_pack_layer's BatchNorm fold for layer 0."""
+    import ctypes as C
+    nat = _nat()
+    g = torch.Generator(device="cpu").manual_seed(13 + h)
+    u8 = torch.randint(0, 256, (n, h, w, 3), generator=g, dtype=torch.uint8)
+    xf = (u8.float() / 255.0).permute(0, 3, 1, 2).contiguous().to(cuda_dev)
+    wt = (torch.randn((64, 3, 3, 3), generator=g) / 5.0).to(cuda_dev)
+    b = torch.randn((64,), generator=g).to(cuda_dev)
+    gamma = (0.5 + torch.rand((64,), generator=g)).to(cuda_dev)
+    beta = torch.randn((64,), generator=g).to(cuda_dev) * 0.2
+    mean = torch.randn((64,), generator=g).to(cuda_dev) * 0.1
+    var = (0.5 + torch.rand((64,), generator=g)).to(cuda_dev)
+    arch = nat.Arch(3, 3, 64)
+    layers = nat.layer_table(arch)
+    blob = torch.zeros(int(nat.lib().unetb200_packed_bytes(C.byref(arch))), dtype=torch.uint8, device=cuda_dev)
+    nat.check(nat.lib().unetb200_pack_layer(C.byref(arch), 0, wt.data_ptr(), b.data_ptr(), gamma.data_ptr(),
+                                            beta.data_ptr(), mean.data_ptr(), var.data_ptr(), 1e-5,
+                                            blob.data_ptr(), None))
+    l0 = layers[0]
+    w_tc = blob.data_ptr() + l0.w_off + int(nat.lib().unetb200_stem_tc_offset(3))
+    bias = blob.data_ptr() + l0.b_off
+    out = torch.full((n, h, w, 64), float("nan"), dtype=torch.bfloat16, device=cuda_dev)
+    src = xf if fmt == "f32" else u8.to(cuda_dev)
+    nat.check(nat.lib().unetb200_stem_tc(src.data_ptr(), 0 if fmt == "f32" else 1, 3, w_tc, bias,
+                                         n, h, w, out.data_ptr(), None))
+    torch.cuda.synchronize()
+    ref = F.relu(F.batch_norm(F.conv2d(xf, wt, b, padding=1), mean, var, gamma, beta, False, 0.0, 1e-5))
+    got = _to_nchw_f32(out)
+    err = (got - ref).abs()
+    tol = ref.abs() * 2.0 ** -8 + 1e-3          # one bf16 rounding (2^-9 rel) + hi/lo split residue
+    assert not (err > tol).any(), f"stem_tc {fmt}: max err {float(err.max()):.4g}"
+    # and the CUDA-core stem, fed from the same blob, agrees to the same tolerance
+    out2 = torch.full_like(out, float("nan"))
+    nat.check(nat.lib().unetb200_stem(src.data_ptr(), 0 if fmt == "f32" else 1, 3, blob.data_ptr() + l0.w_off,
+                                      bias, n, h, w, out2.data_ptr(), None))
+    torch.cuda.synchronize()
+    assert not ((_to_nchw_f32(out2) - ref).abs() > tol).any()
+
+
 @pytest.mark.parametrize("amode", AMODES)
 def test_conv3x3_head(cuda_dev, amode):
     """conv1.net.3 + out_conv 1x1 + logit-space threshold in one kernel (unet_model.py:86,

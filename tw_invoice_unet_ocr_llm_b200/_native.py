@@ -60,6 +60,8 @@ SYMBOLS = {
                                    C.POINTER(_F), _I, _I, _VP]),
     "unetb200_convt2x2": (_I, [_VP, _I, _VP, _VP, _I, _I, _I, _I, _VP, _I, _VP]),
     "unetb200_stem": (_I, [_VP, _I, _I, _VP, _VP, _I, _I, _I, _VP, _VP]),
+    "unetb200_stem_tc": (_I, [_VP, _I, _I, _VP, _VP, _I, _I, _I, _VP, _VP]),
+    "unetb200_stem_tc_offset": (_U64, [_I]),
 }
 
 _lib = None

@@ -28,6 +28,12 @@
 //             but relies on the swizzle being a function of the absolute smem
 //             address (validated on hardware by tests/test_conv_kernels.py).
 // TMA zero-fills out-of-bounds box elements, which is the conv zero padding.
+//   A_STEM  : first conv of the network (Cin = n_channels <= 3, K = 9*Cin <= 27): four extra
+//             warps build the im2col rows themselves, straight from the user's fp32 NCHW /
+//             uint8 NHWC tensor, as bf16 hi + lo pairs (x = hi + lo to 16 significand bits);
+//             the GEMM is x_hi*w_hi + x_lo*w_hi + x_hi*w_lo over two 64-wide K slices, i.e.
+//             fp32-class accuracy from bf16 MMAs.  The layer is HBM-bound (it writes 64 bf16
+//             channels per pixel), the extra MMAs are free.
 //
 // Warp roles (256 threads, 1 CTA / SM, persistent over tiles):
 //   warp 0 : TMA producer, activations      warp 1 : MMA issuer (one lane)
@@ -45,7 +51,7 @@
 namespace ub {
 
 enum : int { EPI_STORE = 0, EPI_STORE_POOL = 1, EPI_HEAD = 2, EPI_UPSAMPLE = 3 };
-enum : int { A_TAP = 0, A_COL3 = 1, A_HALO = 2 };
+enum : int { A_TAP = 0, A_COL3 = 1, A_HALO = 2, A_STEM = 3 };
 
 constexpr int kMaxClasses = 8;
 
@@ -74,6 +80,9 @@ struct ConvParams {
     int wstat;               // 1 = weight-stationary (see header)
     int n_out;               // output staging buffers (1 or 2)
     int off_b, off_out, off_pool, off_bar;   // smem carve-up, bytes from the 1024-aligned base
+    int off_patch;           // A_STEM: 2 x [Cin][18][10] fp32 input halo patches
+    const void* stem_x;      // A_STEM: network input (format stem_fmt), see stem.cuh
+    int stem_fmt;
 };
 
 template <int BN, int TAPS, int AMODE>
@@ -92,9 +101,12 @@ constexpr int kBarBytes = 1024;
 constexpr int kStaticSmem = 4096 + kMaxClasses * 64 * 4 + 64;   // s_bias + s_head_w + s_head_b
 constexpr int kSmemLimit = 232448;    // 227 KB per CTA on sm_100
 
-template <int BN, int TAPS, int AMODE, int EPI>
-__global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
+template <int BN, int TAPS, int AMODE, int EPI, int CIN = 0>
+__global__ void __launch_bounds__(AMODE == A_STEM ? 384 : 256, 1)
+conv_tc_kernel(const __grid_constant__ ConvParams p) {
     static_assert(TAPS == 9 || TAPS == 1, "3x3 conv or per-tap GEMM");
+    static_assert(AMODE != A_STEM || (TAPS == 1 && BN == 64 && CIN >= 1 && 9 * CIN <= 32),
+                  "stem: im2col rows of <= 32 taps, 64 output channels");
     static_assert(EPI != EPI_HEAD || BN == 64, "fused head needs all 64 channels in one tile");
     using Cfg = ConvCfg<BN, TAPS, AMODE>;
     constexpr int TPA = Cfg::TPA;
@@ -132,7 +144,7 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < kMaxRing; ++i) {
-            mbar_init(bar_a_full + 8 * i, 1);
+            mbar_init(bar_a_full + 8 * i, AMODE == A_STEM ? 128 : 1);   // stem: every im2col thread arrives
             mbar_init(bar_a_empty + 8 * i, 1);
             mbar_init(bar_b_full + 8 * i, 1);
             mbar_init(bar_b_empty + 8 * i, 1);
@@ -158,9 +170,112 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
     const int n_cs = (p.C0 + p.C1) >> 6;            // 64-channel slices along K
     const int tiles_per_img = p.tiles_x * p.tiles_y;
 
-    if (warp == 0) {
+    if (AMODE == A_STEM && warp >= 8) {
+        // ================== im2col producer (first conv only) =================
+        // thread r builds A row r = output pixel (y0 + r/8, x0 + r%8) of the tile:
+        //   slice 0 (ring item 0): k in [0,32) = bf16 hi of the 9*CIN taps, [32,64) = bf16 lo
+        //   slice 1 (ring item 1): k in [0,32) = hi again (multiplies w_lo); upper half unused
+        constexpr int CI = CIN > 0 ? CIN : 1;                    // (CIN == 0 only in dead instantiations)
+        constexpr int KS = 9 * CI;
+        constexpr int PE = CI * 180;                             // patch elements: [CIN][18][10]
+        constexpr int NL = (PE + 127) / 128;
+        const int r = threadIdx.x - 256;
+        float* s_patch = reinterpret_cast<float*>(smem_gen + p.off_patch);
+        const int hh = r >> 3, ww = r & 7;
+        auto fetch = [&](int t, float (&regs)[NL]) {
+            const int n = t / tiles_per_img;
+            const int rr = t - n * tiles_per_img;
+            const int y0 = (rr / p.tiles_x) * 16 - 1, x0 = (rr % p.tiles_x) * 8 - 1;
+#pragma unroll
+            for (int i = 0; i < NL; ++i) {
+                const int e = r + i * 128;
+                float v = 0.f;
+                if (e < PE) {
+                    const int ci = e / 180, rem = e - ci * 180;
+                    const int y = y0 + rem / 10, x = x0 + rem % 10;
+                    if (y >= 0 && y < p.H && x >= 0 && x < p.W) {
+                        if (p.stem_fmt == 0) {
+                            v = __ldg(static_cast<const float*>(p.stem_x) +
+                                      ((static_cast<size_t>(n) * CI + ci) * p.H + y) * p.W + x);
+                        } else {
+                            const uint8_t u = __ldg(static_cast<const uint8_t*>(p.stem_x) +
+                                                    ((static_cast<size_t>(n) * p.H + y) * p.W + x) * CI + ci);
+                            v = __fdiv_rn(static_cast<float>(u), 255.0f);   // inference.py:36 (`/ 255.0`)
+                        }
+                    }
+                }
+                regs[i] = v;
+            }
+        };
+        auto publish = [&](int buf, const float (&regs)[NL]) {
+#pragma unroll
+            for (int i = 0; i < NL; ++i) {
+                const int e = r + i * 128;
+                if (e < PE) s_patch[buf * PE + e] = regs[i];
+            }
+        };
+        float regs[NL];
+        uint32_t sa = 0, pa = 0;
+        int it = 0;
+        int t = blockIdx.x;
+        if (t < p.total_tiles) {
+            fetch(t, regs);
+            publish(0, regs);
+        }
+        named_bar_sync(3, 128);
+        for (; t < p.total_tiles; t += gridDim.x, ++it) {
+            const int tn = t + gridDim.x;
+            if (tn < p.total_tiles) fetch(tn, regs);             // global loads in flight during the build
+            const float* pt = s_patch + (it & 1) * PE;
+            uint32_t hi[16], lo[16];                             // 32 bf16 each, zero padded past KS
+#pragma unroll
+            for (int k2 = 0; k2 < 16; ++k2) {
+                float v[2], h[2];
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int k = 2 * k2 + j;
+                    if (k < KS) {
+                        const int tap = k / CI, ci = k - tap * CI;
+                        v[j] = pt[ci * 180 + (hh + tap / 3) * 10 + (ww + tap % 3)];
+                    } else {
+                        v[j] = 0.f;
+                    }
+                }
+                hi[k2] = pack_bf16x2(v[0], v[1]);
+                h[0] = __uint_as_float(hi[k2] << 16);
+                h[1] = __uint_as_float(hi[k2] & 0xffff0000u);
+                lo[k2] = pack_bf16x2(v[0] - h[0], v[1] - h[1]);
+            }
+            // ---- slice 0: [hi | lo]
+            mbar_wait(bar_a_empty + 8 * sa, pa ^ 1, 1, p.dbg);
+            {
+                const uint32_t row = sA + sa * Cfg::A_STAGE + r * 128;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    st_shared_v4(row + ((c ^ (r & 7)) << 4), hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+                    st_shared_v4(row + (((c + 4) ^ (r & 7)) << 4), lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+                }
+            }
+            fence_proxy_async_smem();
+            mbar_arrive(bar_a_full + 8 * sa);
+            if (++sa == static_cast<uint32_t>(p.na)) { sa = 0; pa ^= 1; }
+            // ---- slice 1: [hi | (unused)]
+            mbar_wait(bar_a_empty + 8 * sa, pa ^ 1, 2, p.dbg);
+            {
+                const uint32_t row = sA + sa * Cfg::A_STAGE + r * 128;
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    st_shared_v4(row + ((c ^ (r & 7)) << 4), hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+            }
+            fence_proxy_async_smem();
+            mbar_arrive(bar_a_full + 8 * sa);
+            if (++sa == static_cast<uint32_t>(p.na)) { sa = 0; pa ^= 1; }
+            if (tn < p.total_tiles) publish((it + 1) & 1, regs);
+            named_bar_sync(3, 128);
+        }
+    } else if (warp == 0) {
         // ===================== TMA producer: activations ======================
-        if (lane == 0) {
+        if (lane == 0 && AMODE != A_STEM) {
             uint32_t sa = 0, pa = 0;
             for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
                 const int mt = t / p.n_blocks;
@@ -260,6 +375,7 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
                                 const uint32_t b_lo = b_cs + (tap_c + tap_r) * (Cfg::B_STAGE >> 4);
 #pragma unroll
                                 for (int k = 0; k < 4; ++k) {
+                                    if (AMODE == A_STEM && cs == 1 && k >= 2) break;   // slice 1 holds 32 taps only
                                     umma_bf16(d_tmem, umma_desc(a_lo0 + a_off + 2 * k, a_hi),
                                               umma_desc(b_lo + 2 * k, b_hi), idesc, accumulate);
                                     accumulate = 1;

@@ -105,6 +105,10 @@ struct LayerSpec {
     int kind, cin, cout, level;
 };
 
+// The stem's weight region holds two layouts: fp32 [9*cin][cout] for the CUDA-core kernel
+// (stem.cuh), then bf16 hi/lo [cout][128] for the tensor-core stem (conv_tc.cuh, A_STEM).
+uint64_t stem_tc_offset(int cin, int cout) { return (uint64_t(9) * cin * cout * 4 + 255) / 256 * 256; }
+
 std::vector<unetb200_layer_t> layer_table(const unetb200_arch_t& a) {
     const int w = a.base_width;
     const LayerSpec specs[] = {
@@ -146,7 +150,7 @@ std::vector<unetb200_layer_t> layer_table(const unetb200_arch_t& a) {
         l.level = s.level;
         uint64_t wb = 0;
         switch (s.kind) {
-            case UNETB200_STEM: wb = uint64_t(9) * s.cin * s.cout * 4; break;
+            case UNETB200_STEM: wb = stem_tc_offset(s.cin, s.cout) + uint64_t(s.cout) * 128 * 2; break;
             case UNETB200_CONV3X3: wb = uint64_t(9) * s.cin * s.cout * 2; break;
             case UNETB200_CONVT2X2: wb = uint64_t(4) * s.cin * s.cout * 2; break;
             case UNETB200_HEAD: wb = uint64_t(s.cin) * s.cout * 4; break;
@@ -209,7 +213,23 @@ ConvLaunch conv3_pick_amode(int amode, int epi) {
     }
 }
 
-ConvLaunch pick_conv(int taps, int bn, int amode, int epi) {
+template <int CIN>
+ConvLaunch stem_inst() {
+    ConvLaunch l;
+    l.fn = ub::conv_tc_kernel<64, 1, ub::A_STEM, ub::EPI_STORE, CIN>;
+    l.a_stage = ub::ConvCfg<64, 1, ub::A_STEM>::A_STAGE;
+    l.b_stage = ub::ConvCfg<64, 1, ub::A_STEM>::B_STAGE;
+    return l;
+}
+
+ConvLaunch pick_conv(int taps, int bn, int amode, int epi, int stem_cin = 0) {
+    if (amode == ub::A_STEM) {
+        switch (stem_cin) {
+            case 1: return stem_inst<1>();
+            case 3: return stem_inst<3>();
+        }
+        return ConvLaunch();
+    }
     if (taps == 1) {
         switch (bn) {
             case 64: return conv_inst<64, 1, ub::A_TAP, ub::EPI_UPSAMPLE>();
@@ -264,6 +284,8 @@ struct ConvDesc {
     uint8_t* mask = nullptr;
     int bn = 128, amode = ub::A_COL3;
     int wstat = 1;              // allow weight-stationary mode when it fits
+    const void* stem_x = nullptr;   // A_STEM: network input, its format and channel count
+    int stem_fmt = 0, stem_cin = 0;
     int* dbg = nullptr;
 };
 
@@ -271,8 +293,8 @@ struct ConvDesc {
 // staging][barriers].  Weight-stationary when the layer has one column block and its whole
 // weight slab fits beside at least two activation stages.
 int plan_smem(ConvLaunch* cl, ub::ConvParams* p, int taps, int n_cs, int n_blocks, int bn, bool pool,
-              bool has_out, int allow_wstat) {
-    const int budget = ub::kSmemLimit - ub::kStaticSmem - 1024 /*alignment slack*/;
+              bool has_out, int allow_wstat, int patch_bytes) {
+    const int budget = ub::kSmemLimit - ub::kStaticSmem - 1024 /*alignment slack*/ - patch_bytes;
     const int pool_b = pool ? 2 * ub::kPoolStage : 0;
     const int slab = taps * n_cs * cl->b_stage;
     int n_out = has_out ? 2 : 0, na = 0, nb = 0, wstat = 0;
@@ -293,6 +315,7 @@ int plan_smem(ConvLaunch* cl, ub::ConvParams* p, int taps, int n_cs, int n_block
         na = rest / cl->a_stage;
     }
     if (na > ub::kMaxRing) na = ub::kMaxRing;
+    if (patch_bytes && !wstat) return fail(UNETB200_EINVAL, "stem: weights must be resident");
     if (na < 2) return fail(UNETB200_EINVAL, "conv: shared memory plan does not fit");
     p->na = na;
     p->nb = nb;
@@ -302,15 +325,20 @@ int plan_smem(ConvLaunch* cl, ub::ConvParams* p, int taps, int n_cs, int n_block
     p->off_out = p->off_b + nb * cl->b_stage;
     p->off_pool = p->off_out + n_out * ub::kOutStage;
     p->off_bar = p->off_pool + pool_b;
-    cl->smem = p->off_bar + ub::kBarBytes + 1024;
+    p->off_patch = p->off_bar + ub::kBarBytes;
+    cl->smem = p->off_patch + patch_bytes + 1024;
     return 0;
 }
 
 int build_conv_step(const ConvDesc& d, int num_sms, Step* st) {
+    const bool stem = d.amode == ub::A_STEM;
     if (d.c0 <= 0 || d.c0 % 64 || d.c1 % 64 || d.c1 < 0)
         return fail(UNETB200_EINVAL, "conv: source channels must be multiples of 64");
+    if (stem && (d.taps != 1 || d.cout != 64 || d.c0 != 128 || d.c1 != 0 || !d.stem_x ||
+                 d.epi != ub::EPI_STORE))
+        return fail(UNETB200_EINVAL, "stem: bad configuration");
     if (d.cout % 64) return fail(UNETB200_EINVAL, "conv: cout must be a multiple of 64");
-    const int cols = d.taps == 1 ? 4 * d.cout : d.cout;
+    const int cols = (d.taps == 1 && !stem) ? 4 * d.cout : d.cout;
     int bn = d.bn;
     if (d.epi == ub::EPI_HEAD) bn = 64;
     if (bn > cols) bn = cols;
@@ -319,7 +347,7 @@ int build_conv_step(const ConvDesc& d, int num_sms, Step* st) {
     if (d.epi == ub::EPI_HEAD && d.cout != 64)
         return fail(UNETB200_EINVAL, "fused head needs cout == 64");
     st->kind = 1;
-    st->conv = pick_conv(d.taps, bn, d.amode, d.epi);
+    st->conv = pick_conv(d.taps, bn, d.amode, d.epi, d.stem_cin);
     if (!st->conv.fn) return fail(UNETB200_EINVAL, "conv: no kernel for this configuration");
     ub::ConvParams& p = st->cp;
     memset(&p, 0, sizeof p);
@@ -327,11 +355,21 @@ int build_conv_step(const ConvDesc& d, int num_sms, Step* st) {
     if (d.taps == 9 && d.amode == ub::A_COL3) boxH = 18;
     if (d.taps == 9 && d.amode == ub::A_HALO) { boxW = 10; boxH = 18; }
     int rc;
-    if ((rc = make_act_map(&p.tmA0, d.src0, d.c0, d.wd, d.h, d.n, boxW, boxH))) return rc;
-    if (d.c1 > 0) {
-        if ((rc = make_act_map(&p.tmA1, d.src1, d.c1, d.wd, d.h, d.n, boxW, boxH))) return rc;
-    } else {
+    if (stem) {
+        p.stem_x = d.stem_x;
+        p.stem_fmt = d.stem_fmt;
+        // tmA0/tmA1 are never used by the stem (its A rows are built in-kernel); keep them valid
+        if ((rc = make_act_map(&p.tmA0, d.out, d.cout, d.wd, d.h, d.n, 8, 16))) return rc;
         p.tmA1 = p.tmA0;
+    } else if ((rc = make_act_map(&p.tmA0, d.src0, d.c0, d.wd, d.h, d.n, boxW, boxH))) {
+        return rc;
+    }
+    if (!stem) {
+        if (d.c1 > 0) {
+            if ((rc = make_act_map(&p.tmA1, d.src1, d.c1, d.wd, d.h, d.n, boxW, boxH))) return rc;
+        } else {
+            p.tmA1 = p.tmA0;
+        }
     }
     const int cin = d.c0 + d.c1;
     if ((rc = make_w_map(&p.tmB, d.w, cin, cols, d.taps == 9 ? 9 : 1, bn))) return rc;
@@ -375,10 +413,11 @@ int build_conv_step(const ConvDesc& d, int num_sms, Step* st) {
     p.relu = d.relu;
     p.ncls = d.ncls;
     if ((rc = plan_smem(&st->conv, &p, d.taps == 9 ? 9 : 1, cin / 64, p.n_blocks, bn,
-                        d.epi == ub::EPI_STORE_POOL, d.epi != ub::EPI_HEAD, d.wstat)))
+                        d.epi == ub::EPI_STORE_POOL, d.epi != ub::EPI_HEAD, stem ? 1 : d.wstat,
+                        stem ? 2 * d.stem_cin * 180 * 4 : 0)))
         return rc;
     st->grid = dim3(static_cast<unsigned>(total < num_sms ? total : num_sms));
-    st->block = dim3(256);
+    st->block = dim3(stem ? 384 : 256);
     return 0;
 }
 
@@ -431,6 +470,20 @@ int build_stem_step(const void* x, int x_fmt, int cin, const float* w, const flo
     return 0;
 }
 
+// First conv on the tensor cores (conv_tc.cuh, A_STEM): im2col rows built in-kernel from the
+// user's tensor, hi/lo-split bf16 GEMM over two K slices against the [64][128] packed weights.
+int build_stem_tc_step(const void* x, int x_fmt, int cin, const void* w_tc, const float* bias, int n,
+                       int h, int wd, void* out, int num_sms, int* dbg, Step* st) {
+    if (x_fmt != UNETB200_X_F32_NCHW && x_fmt != UNETB200_X_U8_NHWC)
+        return fail(UNETB200_EINVAL, "unknown x_fmt");
+    if (!(cin == 1 || cin == 3)) return fail(UNETB200_EINVAL, "tensor-core stem: n_channels must be 1 or 3");
+    ConvDesc d;
+    d.c0 = 128; d.w = w_tc; d.bias = bias; d.n = n; d.h = h; d.wd = wd; d.cout = 64; d.relu = 1;
+    d.taps = 1; d.epi = ub::EPI_STORE; d.out = out; d.bn = 64; d.amode = ub::A_STEM;
+    d.stem_x = x; d.stem_fmt = x_fmt; d.stem_cin = cin; d.dbg = dbg;
+    return build_conv_step(d, num_sms, st);
+}
+
 int device_num_sms(int* out) {
     int dev = 0;
     UB_CUDA(cudaGetDevice(&dev));
@@ -467,6 +520,7 @@ struct unetb200_handle_s {
     int amode = ub::A_HALO;
     int bn_max = 256;
     int wstat = 1;
+    int stem_tc = 1;            // first conv on the tensor cores (n_channels <= 3)
     int profile = 0;
     int* dbg = nullptr;         // pinned, device-visible watchdog record
     std::map<PlanKey, Plan> plans;
@@ -545,9 +599,15 @@ int build_plan(unetb200_handle_t h, const void* x, int x_fmt, int n, int H, int 
     // ---- encoder (unet_model.py:56-66)
     {
         Step st;
-        if ((rc = build_stem_step(x, x_fmt, h->arch.n_channels,
-                                  reinterpret_cast<const float*>(Wp(0)), Bp(0), n, H, W, P(L.a[0]), &st)))
+        if (h->stem_tc && h->arch.n_channels <= 3) {
+            if ((rc = build_stem_tc_step(x, x_fmt, h->arch.n_channels,
+                                         h->blob + h->layers[0].w_off + stem_tc_offset(h->arch.n_channels, bw),
+                                         Bp(0), n, H, W, P(L.a[0]), h->num_sms, h->dbg, &st)))
+                return rc;
+        } else if ((rc = build_stem_step(x, x_fmt, h->arch.n_channels, reinterpret_cast<const float*>(Wp(0)),
+                                         Bp(0), n, H, W, P(L.a[0]), &st))) {
             return rc;
+        }
         st.layer = 0;
         plan->steps.push_back(st);
     }
@@ -640,6 +700,9 @@ int unetb200_pack_layer(const unetb200_arch_t* arch, int index, const float* wei
             ub::pack_stem_kernel<<<(total + threads - 1) / threads, threads, 0, s>>>(
                 weight, bias, bn_gamma, bn_beta, bn_mean, bn_var, bn_eps, l.cout, l.cin,
                 reinterpret_cast<float*>(blob + l.w_off), db);
+            ub::pack_stem_tc_kernel<<<(l.cout * 128 + threads - 1) / threads, threads, 0, s>>>(
+                weight, bn_gamma, bn_var, bn_eps, l.cout, l.cin,
+                reinterpret_cast<uint16_t*>(blob + l.w_off + stem_tc_offset(l.cin, l.cout)));
             break;
         }
         case UNETB200_CONV3X3: {
@@ -697,6 +760,8 @@ int unetb200_create(const unetb200_arch_t* arch, const void* blob_dev, uint64_t 
     if (env) h->bn_max = atoi(env);
     env = getenv("UNETB200_WSTAT");
     if (env) h->wstat = atoi(env) ? 1 : 0;
+    env = getenv("UNETB200_STEM_TC");
+    if (env) h->stem_tc = atoi(env) ? 1 : 0;
     *out = h;
     return 0;
 }
@@ -721,6 +786,8 @@ int unetb200_set_option(unetb200_handle_t h, const char* key, int value) {
         h->bn_max = value;
     } else if (k == "wstat") {
         h->wstat = value ? 1 : 0;
+    } else if (k == "stem_tc") {
+        h->stem_tc = value ? 1 : 0;
     } else if (k == "profile") {
         h->profile = value ? 1 : 0;
     } else {
@@ -736,6 +803,7 @@ int unetb200_get_option(unetb200_handle_t h, const char* key, int* value) {
     if (k == "amode") *value = h->amode;
     else if (k == "bn_max") *value = h->bn_max;
     else if (k == "wstat") *value = h->wstat;
+    else if (k == "stem_tc") *value = h->stem_tc;
     else if (k == "profile") *value = h->profile;
     else if (k == "num_sms") *value = h->num_sms;
     else return fail(UNETB200_EINVAL, "unknown option " + k);
@@ -889,6 +957,21 @@ int unetb200_convt2x2(const void* src, int cin, const void* w_packed, const floa
     if ((rc = device_num_sms(&sms))) return rc;
     Step st;
     if ((rc = build_conv_step(d, sms, &st))) return rc;
+    return launch_step(st, static_cast<cudaStream_t>(stream));
+}
+
+uint64_t unetb200_stem_tc_offset(int cin) { return stem_tc_offset(cin, 64); }
+
+int unetb200_stem_tc(const void* x, int x_fmt, int cin, const void* w_tc, const float* bias, int n,
+                     int height, int width, void* out, void* stream) {
+    int rc;
+    if ((rc = check_sm100())) return rc;
+    if (!x || !w_tc || !bias || !out) return fail(UNETB200_EINVAL, "NULL pointer");
+    int sms = 0;
+    if ((rc = device_num_sms(&sms))) return rc;
+    Step st;
+    if ((rc = build_stem_tc_step(x, x_fmt, cin, w_tc, bias, n, height, width, out, sms, g_hook_dbg(), &st)))
+        return rc;
     return launch_step(st, static_cast<cudaStream_t>(stream));
 }
 
