@@ -79,6 +79,7 @@ struct ConvParams {
     int na, nb;              // ring depths: activation items / weight tiles (wstat: nb = all tiles)
     int wstat;               // 1 = weight-stationary (see header)
     int n_out;               // output staging buffers (1 or 2)
+    int pf_items;            // activation items prefetched into L2 ahead of the smem ring (0 = off)
     int off_b, off_out, off_pool, off_bar;   // smem carve-up, bytes from the 1024-aligned base
     int off_patch;           // A_STEM: 2 x [Cin][18][10] fp32 input halo patches
     const void* stem_x;      // A_STEM: network input (format stem_fmt), see stem.cuh
@@ -101,9 +102,11 @@ constexpr int kBarBytes = 1024;
 constexpr int kStaticSmem = 4096 + kMaxClasses * 64 * 4 + 64;   // s_bias + s_head_w + s_head_b
 constexpr int kSmemLimit = 232448;    // 227 KB per CTA on sm_100
 
-template <int BN, int TAPS, int AMODE, int EPI, int CIN = 0>
+// X: A_STEM -> n_channels of the network input; EPI_HEAD -> n_classes (0 = generic, up to 8).
+template <int BN, int TAPS, int AMODE, int EPI, int X = 0>
 __global__ void __launch_bounds__(AMODE == A_STEM ? 384 : 256, 1)
 conv_tc_kernel(const __grid_constant__ ConvParams p) {
+    constexpr int CIN = X;
     static_assert(TAPS == 9 || TAPS == 1, "3x3 conv or per-tap GEMM");
     static_assert(AMODE != A_STEM || (TAPS == 1 && BN == 64 && CIN >= 1 && 9 * CIN <= 32),
                   "stem: im2col rows of <= 32 taps, 64 output channels");
@@ -129,7 +132,7 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));   // generic view of smem_base
 
     __shared__ __align__(16) float s_bias[1024];
-    __shared__ float s_head_w[kMaxClasses * 64];
+    __shared__ __align__(16) float s_head_w[kMaxClasses * 64];
     __shared__ float s_head_b[kMaxClasses];
 
     const int warp = threadIdx.x >> 5;
@@ -157,8 +160,9 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
     }
     if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(s_tmem_ptr);
     if (EPI == EPI_HEAD) {
-        for (int i = threadIdx.x; i < p.ncls * 64; i += blockDim.x) s_head_w[i] = p.head_w[i];
-        if (threadIdx.x < p.ncls) s_head_b[threadIdx.x] = p.head_b[threadIdx.x];
+        for (int i = threadIdx.x; i < kMaxClasses * 64; i += blockDim.x)
+            s_head_w[i] = i < p.ncls * 64 ? p.head_w[i] : 0.f;
+        if (threadIdx.x < kMaxClasses) s_head_b[threadIdx.x] = threadIdx.x < p.ncls ? p.head_b[threadIdx.x] : 0.f;
     }
     for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) s_bias[i] = p.bias[i];
     tc_fence_before();
@@ -276,32 +280,48 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
     } else if (warp == 0) {
         // ===================== TMA producer: activations ======================
         if (lane == 0 && AMODE != A_STEM) {
-            uint32_t sa = 0, pa = 0;
-            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-                const int mt = t / p.n_blocks;
-                const int n = mt / tiles_per_img;
+            // flat walk over this CTA's activation items: idx -> (tile, 64-channel slice, item)
+            const int ipt = n_cs * ITEMS;
+            const int my_tiles = blockIdx.x < p.total_tiles
+                                     ? (p.total_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
+                                           static_cast<int>(gridDim.x)
+                                     : 0;
+            const int n_items = my_tiles * ipt;
+            auto locate = [&](int idx, const CUtensorMap*& tm, int& ca, int& bx, int& by, int& n) {
+                const int tl = idx / ipt, rem = idx - tl * ipt;
+                const int cs = rem / ITEMS, item = rem - cs * ITEMS;
+                const int mt = (static_cast<int>(blockIdx.x) + tl * static_cast<int>(gridDim.x)) / p.n_blocks;
+                n = mt / tiles_per_img;
                 const int r = mt - n * tiles_per_img;
-                const int y0 = (r / p.tiles_x) * 16;
-                const int x0 = (r % p.tiles_x) * 8;
-                for (int cs = 0; cs < n_cs; ++cs) {
-                    const bool src0 = (cs << 6) < p.C0;
-                    const CUtensorMap* tmA = src0 ? &p.tmA0 : &p.tmA1;
-                    const int ca = src0 ? (cs << 6) : (cs << 6) - p.C0;
-#pragma unroll 1
-                    for (int item = 0; item < ITEMS; ++item) {
-                        // box origin of this activation item
-                        int bx = x0, by = y0;
-                        if (TAPS == 9) {
-                            if (AMODE == A_TAP) { bx += item % 3 - 1; by += item / 3 - 1; }
-                            if (AMODE == A_COL3) { bx += item - 1; by -= 1; }
-                            if (AMODE == A_HALO) { bx -= 1; by -= 1; }
-                        }
-                        mbar_wait(bar_a_empty + 8 * sa, pa ^ 1, 1, p.dbg);
-                        mbar_expect_tx(bar_a_full + 8 * sa, Cfg::A_TX);
-                        tma_load_4d(sA + sa * Cfg::A_STAGE, tmA, bar_a_full + 8 * sa, ca, bx, by, n);
-                        if (++sa == static_cast<uint32_t>(p.na)) { sa = 0; pa ^= 1; }
-                    }
+                by = (r / p.tiles_x) * 16;
+                bx = (r % p.tiles_x) * 8;
+                const bool src0 = (cs << 6) < p.C0;
+                tm = src0 ? &p.tmA0 : &p.tmA1;
+                ca = src0 ? (cs << 6) : (cs << 6) - p.C0;
+                if (TAPS == 9) {
+                    if (AMODE == A_TAP) { bx += item % 3 - 1; by += item / 3 - 1; }
+                    if (AMODE == A_COL3) { bx += item - 1; by -= 1; }
+                    if (AMODE == A_HALO) { bx -= 1; by -= 1; }
                 }
+            };
+            const CUtensorMap* tm;
+            int ca, bx, by, n;
+            const int pf = p.pf_items;
+            for (int i = 0; i < pf && i < n_items; ++i) {
+                locate(i, tm, ca, bx, by, n);
+                tma_prefetch_4d(tm, ca, bx, by, n);
+            }
+            uint32_t sa = 0, pa = 0;
+            for (int i = 0; i < n_items; ++i) {
+                if (pf > 0 && i + pf < n_items) {
+                    locate(i + pf, tm, ca, bx, by, n);
+                    tma_prefetch_4d(tm, ca, bx, by, n);
+                }
+                locate(i, tm, ca, bx, by, n);
+                mbar_wait(bar_a_empty + 8 * sa, pa ^ 1, 1, p.dbg);
+                mbar_expect_tx(bar_a_full + 8 * sa, Cfg::A_TX);
+                tma_load_4d(sA + sa * Cfg::A_STAGE, tm, bar_a_full + 8 * sa, ca, bx, by, n);
+                if (++sa == static_cast<uint32_t>(p.na)) { sa = 0; pa ^= 1; }
             }
         }
     } else if (warp == 3) {
@@ -430,21 +450,38 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
             const uint32_t t_addr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
 
             if (EPI == EPI_HEAD) {
-                float z[kMaxClasses];
+                // out_conv 1x1 (unet_model.py:86) from the fp32 accumulators, NC classes at once;
+                // s_head_w rows past n_classes are zero so the generic variant needs no predicates
+                constexpr int NC = X > 0 ? X : kMaxClasses;
+                float z[NC];
 #pragma unroll
-                for (int c = 0; c < kMaxClasses; ++c) z[c] = c < p.ncls ? s_head_b[c] : 0.f;
+                for (int c = 0; c < NC; ++c) z[c] = s_head_b[c];
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
                     uint32_t v[32];
                     tmem_ld32(t_addr + half * 32, v);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        float f = __uint_as_float(v[i]) + s_bias[half * 32 + i];
-                        f = p.relu ? fmaxf(f, 0.f) : f;
+                    for (int i = 0; i < 32; i += 4) {
+                        const float4 b4 = *reinterpret_cast<const float4*>(s_bias + half * 32 + i);
+                        float f0 = __uint_as_float(v[i + 0]) + b4.x;
+                        float f1 = __uint_as_float(v[i + 1]) + b4.y;
+                        float f2 = __uint_as_float(v[i + 2]) + b4.z;
+                        float f3 = __uint_as_float(v[i + 3]) + b4.w;
+                        if (p.relu) {
+                            f0 = fmaxf(f0, 0.f);
+                            f1 = fmaxf(f1, 0.f);
+                            f2 = fmaxf(f2, 0.f);
+                            f3 = fmaxf(f3, 0.f);
+                        }
 #pragma unroll
-                        for (int c = 0; c < kMaxClasses; ++c)
-                            if (c < p.ncls) z[c] = fmaf(f, s_head_w[c * 64 + half * 32 + i], z[c]);
+                        for (int c = 0; c < NC; ++c) {
+                            const float4 w4 = *reinterpret_cast<const float4*>(s_head_w + c * 64 + half * 32 + i);
+                            z[c] = fmaf(f0, w4.x, z[c]);
+                            z[c] = fmaf(f1, w4.y, z[c]);
+                            z[c] = fmaf(f2, w4.z, z[c]);
+                            z[c] = fmaf(f3, w4.w, z[c]);
+                        }
                     }
                 }
                 tc_fence_before();
@@ -453,7 +490,7 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
                 const int y = y0 + (row >> 3), x = x0 + (row & 7);
                 if (y < p.H && x < p.W) {
 #pragma unroll
-                    for (int c = 0; c < kMaxClasses; ++c) {
+                    for (int c = 0; c < NC; ++c) {
                         if (c < p.ncls) {
                             const size_t o = ((static_cast<size_t>(n) * p.ncls + c) * p.H + y) * p.W + x;
                             if (p.logits) p.logits[o] = z[c];

@@ -185,10 +185,10 @@ struct ConvLaunch {
     int smem = 0;                   // dynamic shared memory of this launch (set by plan_smem)
 };
 
-template <int BN, int TAPS, int AMODE, int EPI>
+template <int BN, int TAPS, int AMODE, int EPI, int X = 0>
 ConvLaunch conv_inst() {
     ConvLaunch l;
-    l.fn = ub::conv_tc_kernel<BN, TAPS, AMODE, EPI>;
+    l.fn = ub::conv_tc_kernel<BN, TAPS, AMODE, EPI, X>;
     l.a_stage = ub::ConvCfg<BN, TAPS, AMODE>::A_STAGE;
     l.b_stage = ub::ConvCfg<BN, TAPS, AMODE>::B_STAGE;
     return l;
@@ -222,7 +222,7 @@ ConvLaunch stem_inst() {
     return l;
 }
 
-ConvLaunch pick_conv(int taps, int bn, int amode, int epi, int stem_cin = 0) {
+ConvLaunch pick_conv(int taps, int bn, int amode, int epi, int stem_cin = 0, int ncls = 0) {
     if (amode == ub::A_STEM) {
         switch (stem_cin) {
             case 1: return stem_inst<1>();
@@ -239,10 +239,12 @@ ConvLaunch pick_conv(int taps, int bn, int amode, int epi, int stem_cin = 0) {
         return ConvLaunch();
     }
     if (epi == ub::EPI_HEAD) {
+        // n_classes == 3 (the reference's configuration) has its own instantiation
+        const bool three = ncls == 3;
         switch (amode) {
-            case ub::A_TAP: return conv_inst<64, 9, ub::A_TAP, ub::EPI_HEAD>();
-            case ub::A_COL3: return conv_inst<64, 9, ub::A_COL3, ub::EPI_HEAD>();
-            case ub::A_HALO: return conv_inst<64, 9, ub::A_HALO, ub::EPI_HEAD>();
+            case ub::A_TAP: return three ? conv_inst<64, 9, ub::A_TAP, ub::EPI_HEAD, 3>() : conv_inst<64, 9, ub::A_TAP, ub::EPI_HEAD>();
+            case ub::A_COL3: return three ? conv_inst<64, 9, ub::A_COL3, ub::EPI_HEAD, 3>() : conv_inst<64, 9, ub::A_COL3, ub::EPI_HEAD>();
+            case ub::A_HALO: return three ? conv_inst<64, 9, ub::A_HALO, ub::EPI_HEAD, 3>() : conv_inst<64, 9, ub::A_HALO, ub::EPI_HEAD>();
         }
         return ConvLaunch();
     }
@@ -284,6 +286,7 @@ struct ConvDesc {
     uint8_t* mask = nullptr;
     int bn = 128, amode = ub::A_COL3;
     int wstat = 1;              // allow weight-stationary mode when it fits
+    int pf_items = 0;           // L2 prefetch distance (activation ring items)
     const void* stem_x = nullptr;   // A_STEM: network input, its format and channel count
     int stem_fmt = 0, stem_cin = 0;
     int* dbg = nullptr;
@@ -347,7 +350,7 @@ int build_conv_step(const ConvDesc& d, int num_sms, Step* st) {
     if (d.epi == ub::EPI_HEAD && d.cout != 64)
         return fail(UNETB200_EINVAL, "fused head needs cout == 64");
     st->kind = 1;
-    st->conv = pick_conv(d.taps, bn, d.amode, d.epi, d.stem_cin);
+    st->conv = pick_conv(d.taps, bn, d.amode, d.epi, d.stem_cin, d.ncls);
     if (!st->conv.fn) return fail(UNETB200_EINVAL, "conv: no kernel for this configuration");
     ub::ConvParams& p = st->cp;
     memset(&p, 0, sizeof p);
@@ -412,6 +415,7 @@ int build_conv_step(const ConvDesc& d, int num_sms, Step* st) {
     p.total_tiles = static_cast<int>(total);
     p.relu = d.relu;
     p.ncls = d.ncls;
+    p.pf_items = d.pf_items;
     if ((rc = plan_smem(&st->conv, &p, d.taps == 9 ? 9 : 1, cin / 64, p.n_blocks, bn,
                         d.epi == ub::EPI_STORE_POOL, d.epi != ub::EPI_HEAD, stem ? 1 : d.wstat,
                         stem ? 2 * d.stem_cin * 180 * 4 : 0)))
@@ -521,6 +525,7 @@ struct unetb200_handle_s {
     int bn_max = 256;
     int wstat = 1;
     int stem_tc = 1;            // first conv on the tensor cores (n_channels <= 3)
+    int pf_items = 0;           // L2 prefetch distance of the activation producer, in ring items (measured: no gain)
     int profile = 0;
     int* dbg = nullptr;         // pinned, device-visible watchdog record
     std::map<PlanKey, Plan> plans;
@@ -576,7 +581,7 @@ int build_plan(unetb200_handle_t h, const void* x, int x_fmt, int n, int H, int 
         d.n = n; d.h = H >> lvl; d.wd = W >> lvl; d.cout = h->layers[li].cout;
         d.relu = 1; d.taps = 9; d.epi = pool ? ub::EPI_STORE_POOL : ub::EPI_STORE;
         d.out = out; d.pool = pool;
-        d.bn = h->bn_max; d.amode = h->amode; d.wstat = h->wstat; d.dbg = h->dbg;
+        d.bn = h->bn_max; d.amode = h->amode; d.wstat = h->wstat; d.pf_items = h->pf_items; d.dbg = h->dbg;
         Step st;
         if ((rc = build_conv_step(d, h->num_sms, &st))) return rc;
         st.layer = li;
@@ -589,7 +594,7 @@ int build_plan(unetb200_handle_t h, const void* x, int x_fmt, int n, int H, int 
         d.w = Wp(li); d.bias = Bp(li);
         d.n = n; d.h = H >> lvl; d.wd = W >> lvl; d.cout = h->layers[li].cout;
         d.relu = 0; d.taps = 1; d.epi = ub::EPI_UPSAMPLE; d.out = out;
-        d.bn = h->bn_max; d.amode = ub::A_TAP; d.wstat = h->wstat; d.dbg = h->dbg;
+        d.bn = h->bn_max; d.amode = ub::A_TAP; d.wstat = h->wstat; d.pf_items = h->pf_items; d.dbg = h->dbg;
         Step st;
         if ((rc = build_conv_step(d, h->num_sms, &st))) return rc;
         st.layer = li;
@@ -638,7 +643,7 @@ int build_plan(unetb200_handle_t h, const void* x, int x_fmt, int n, int H, int 
             d.n = n; d.h = H; d.wd = W; d.cout = bw; d.relu = 1; d.taps = 9; d.epi = ub::EPI_HEAD;
             d.head_w = reinterpret_cast<const float*>(Wp(22)); d.head_b = Bp(22);
             d.ncls = h->arch.n_classes; d.logits = logits; d.mask = mask;
-            d.bn = 64; d.amode = h->amode; d.wstat = h->wstat; d.dbg = h->dbg;
+            d.bn = 64; d.amode = h->amode; d.wstat = h->wstat; d.pf_items = h->pf_items; d.dbg = h->dbg;
             Step st;
             if ((rc = build_conv_step(d, h->num_sms, &st))) return rc;
             st.layer = 21;
@@ -760,6 +765,8 @@ int unetb200_create(const unetb200_arch_t* arch, const void* blob_dev, uint64_t 
     if (env) h->bn_max = atoi(env);
     env = getenv("UNETB200_WSTAT");
     if (env) h->wstat = atoi(env) ? 1 : 0;
+    env = getenv("UNETB200_PF_ITEMS");
+    if (env) h->pf_items = atoi(env);
     env = getenv("UNETB200_STEM_TC");
     if (env) h->stem_tc = atoi(env) ? 1 : 0;
     *out = h;
@@ -788,6 +795,9 @@ int unetb200_set_option(unetb200_handle_t h, const char* key, int value) {
         h->wstat = value ? 1 : 0;
     } else if (k == "stem_tc") {
         h->stem_tc = value ? 1 : 0;
+    } else if (k == "pf_items") {
+        if (value < 0 || value > 64) return fail(UNETB200_EINVAL, "pf_items must be in 0..64");
+        h->pf_items = value;
     } else if (k == "profile") {
         h->profile = value ? 1 : 0;
     } else {
@@ -804,6 +814,7 @@ int unetb200_get_option(unetb200_handle_t h, const char* key, int* value) {
     else if (k == "bn_max") *value = h->bn_max;
     else if (k == "wstat") *value = h->wstat;
     else if (k == "stem_tc") *value = h->stem_tc;
+    else if (k == "pf_items") *value = h->pf_items;
     else if (k == "profile") *value = h->profile;
     else if (k == "num_sms") *value = h->num_sms;
     else return fail(UNETB200_EINVAL, "unknown option " + k);
