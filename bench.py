@@ -172,6 +172,7 @@ def main():
     torch.cuda.set_device(dev)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep NCCL's banner off stdout (one JSON line)
         dist.init_process_group("nccl", device_id=dev)
 
     B, S = args.batch, args.size
