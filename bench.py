@@ -148,6 +148,8 @@ def main():
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--layers-out", default=None, help="write the per-layer table (JSON) here")
+    ap.add_argument("--e2e-chunk", type=int, default=64,
+                    help="images per forward inside the end-to-end call (copies of chunk i+1 overlap chunk i)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -177,7 +179,7 @@ def main():
 
     B, S = args.batch, args.size
     state = make_fixture_state()
-    worker = GpuWorker(state, dev, chunk=B)          # public multi-GPU launcher building block
+    worker = GpuWorker(state, dev, chunk=min(B, args.e2e_chunk))   # public multi-GPU launcher building block
     eng = worker.engine
     thr = [0.25, 0.40, 0.30]
 
@@ -279,7 +281,26 @@ def main():
     e2e_ms = timed(e2e_step, args.steps) / args.steps
     e2e = {"value": world * B / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms,
            "h2d_bytes_per_step": int(frames_host.numel()), "d2h_bytes_per_step": int(masks_host.numel()),
+           "chunk": worker.chunk,
            "api": "tw_invoice_unet_ocr_llm_b200.launcher.GpuWorker.segment (uint8 frames -> uint8 masks)"}
+
+    # ---------------- batch-1 latency (BASELINE.json configs[4]): one resident 3x512x512 frame ->
+    # logits + masks, synchronised per call; p50/p95 over 200 calls (rank 0, informational)
+    lat = None
+    if rank == 0:
+        x1 = x_dev[:1].contiguous()
+        l1 = torch.empty((1, 3, S, S), dtype=torch.float32, device=dev)
+        m1 = torch.empty((1, 3, S, S), dtype=torch.uint8, device=dev)
+        ts = []
+        for i in range(220):
+            t0 = time.perf_counter()
+            eng.run(x1, want_logits=True, thresholds=thr, logits_out=l1, mask_out=m1)
+            torch.cuda.synchronize(dev)
+            if i >= 20:
+                ts.append((time.perf_counter() - t0) * 1e3)
+        ts.sort()
+        lat = {"p50_ms": ts[len(ts) // 2], "p95_ms": ts[int(len(ts) * 0.95)], "calls": len(ts),
+               "what": "engine.run on one resident 3x512x512 frame, host-synchronised per call"}
 
     # ---------------- CPU baseline (rank 0, N = 1 only): the oracle port on the host cores
     cpu = None
@@ -301,7 +322,7 @@ def main():
                        "l2": "no flush needed: per-step working set (~9 GB of activations, 201 MB input) exceeds the 126 MB L2",
                        "gflop_per_image": GFLOP_PER_IMAGE_512 * (S * S) / (512 * 512),
                        "achieved_tflops_whole_step": value / world * GFLOP_PER_IMAGE_512 * (S * S) / (512 * 512) / 1e3},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "latency_b1": lat, "clocks": clocks,
             "gpu_launches": launches_per_step * args.steps,
         }
         print(json.dumps(line), flush=True)

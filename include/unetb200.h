@@ -89,7 +89,8 @@ int unetb200_create(const unetb200_arch_t* arch, const void* blob_dev, uint64_t 
                     int device, unetb200_handle_t* out);
 int unetb200_destroy(unetb200_handle_t h);
 
-/* options: "amode" (UNETB200_A_*), "bn_max" (64/128/256), "wstat" (0/1), "stem_tc" (0/1), "profile" (0/1) */
+/* options: "amode" (UNETB200_A_*), "bn_max" (64/128/256), "wstat" (0/1), "stem_tc" (0/1), "pair" (0 never / 1 everywhere / 2 auto),
+ * "n_out_max" (1..4), "pf_items" (0..64), "profile" (0/1) */
 int unetb200_set_option(unetb200_handle_t h, const char* key, int value);
 int unetb200_get_option(unetb200_handle_t h, const char* key, int* value);
 
@@ -117,7 +118,8 @@ int unetb200_last_launch_count(unetb200_handle_t h);
 /* ---- single-kernel entry points (unit parity tests; same code paths as forward) ---- */
 /* 3x3 conv + bias + optional ReLU over NHWC bf16.  src1/c1 = second (skip) source or NULL/0.
  * w_packed: [9][cout][c0+c1] bf16, bias fp32[cout].  pool_out nullable (2x2 max-pool 2nd output).
- * bn in {64,128,256}, amode in UNETB200_A_*, wstat = 1 allows the weight-stationary variant. */
+ * bn in {64,128,256}, amode in UNETB200_A_*; `wstat` is a flag word: bit 0 allows the weight-stationary
+ * variant, bit 1 selects the CTA-pair (cta_group::2) variant (A_HALO only). */
 int unetb200_conv3x3(const void* src0, int c0, const void* src1, int c1, const void* w_packed,
                      const float* bias, int n, int height, int width, int cout, int relu, void* out,
                      void* pool_out, int bn, int amode, int wstat, void* stream);
@@ -126,7 +128,8 @@ int unetb200_conv3x3_head(const void* src0, int c0, const void* w_packed, const 
                           const float* head_w, const float* head_b, int n_classes, int n, int height,
                           int width, float* logits, uint8_t* mask, const float* logit_thr, int amode,
                           int wstat, void* stream);
-/* ConvTranspose2d(k=2,s=2): src [N,H,W,cin] bf16 -> out [N,2H,2W,cout] bf16. w_packed [4*cout][cin]. */
+/* ConvTranspose2d(k=2,s=2): src [N,H,W,cin] bf16 -> out [N,2H,2W,cout] bf16. w_packed [4*cout][cin].
+ * bn in {64,128,256}; bn | 0x1000 selects the CTA-pair variant. */
 int unetb200_convt2x2(const void* src, int cin, const void* w_packed, const float* bias, int n,
                       int height, int width, int cout, void* out, int bn, void* stream);
 /* First conv on the tensor cores (n_channels 1 or 3): w_tc = the bf16 hi/lo [64][128] layout that

@@ -44,7 +44,7 @@ import os
 AMODES = [int(v) for v in os.environ.get("UNETB200_TEST_AMODES", "0,1,2").split(",")]
 
 
-@pytest.mark.parametrize("wstat", [0, 1])
+@pytest.mark.parametrize("wstat", [0, 1, 2, 3])       # bit 0: weight-stationary allowed, bit 1: CTA pair
 @pytest.mark.parametrize("amode", AMODES)
 @pytest.mark.parametrize("cin,cout,bn,n,h,w", [
     (64, 64, 64, 2, 32, 24),
@@ -53,9 +53,12 @@ AMODES = [int(v) for v in os.environ.get("UNETB200_TEST_AMODES", "0,1,2").split(
     (64, 256, 256, 1, 16, 16),
     (192, 128, 64, 1, 20, 12),      # partial tiles in both directions
     (64, 64, 64, 3, 2, 2),          # smaller than one tile (deepest level of a 32x32 input)
+    (128, 256, 128, 3, 16, 8),      # 3 pixel tiles x 2 column blocks: odd-tail pair + streamed weights
 ])
 def test_conv3x3(cuda_dev, amode, wstat, cin, cout, bn, n, h, w):
     nat = _nat()
+    if wstat & 2 and amode != 2:
+        pytest.skip("CTA-pair kernels are instantiated for A_HALO only")
     g = torch.Generator(device="cpu").manual_seed(cin * 7 + cout + h)
     x = torch.randn((n, cin, h, w), generator=g).to(cuda_dev)
     wt = (torch.randn((cout, cin, 3, 3), generator=g) / (3.0 * cin ** 0.5)).to(cuda_dev)
@@ -70,10 +73,13 @@ def test_conv3x3(cuda_dev, amode, wstat, cin, cout, bn, n, h, w):
     _close(_to_nchw_f32(out), ref, f"conv3x3 amode={amode} wstat={wstat}")
 
 
+@pytest.mark.parametrize("pair", [0, 1])
 @pytest.mark.parametrize("amode", AMODES)
-def test_conv3x3_two_sources_and_pool(cuda_dev, amode):
+def test_conv3x3_two_sources_and_pool(cuda_dev, amode, pair):
     """cat([up, skip]) as two K ranges + fused 2x2 max-pool second output (unet_model.py:57,71)."""
     nat = _nat()
+    if pair and amode != 2:
+        pytest.skip("CTA-pair kernels are instantiated for A_HALO only")
     n, c0, c1, cout, h, w = 2, 64, 128, 128, 32, 16
     g = torch.Generator(device="cpu").manual_seed(5)
     x0 = torch.randn((n, c0, h, w), generator=g).to(cuda_dev)
@@ -85,7 +91,7 @@ def test_conv3x3_two_sources_and_pool(cuda_dev, amode):
     pool = torch.full((n, h // 2, w // 2, cout), float("nan"), dtype=torch.bfloat16, device=cuda_dev)
     nat.check(nat.lib().unetb200_conv3x3(x0b.data_ptr(), c0, x1b.data_ptr(), c1, wb.data_ptr(),
                                          b.data_ptr(), n, h, w, cout, 1, out.data_ptr(),
-                                         pool.data_ptr(), 128, amode, 1, None))
+                                         pool.data_ptr(), 128, amode, 1 | (pair << 1), None))
     torch.cuda.synchronize()
     xin = torch.cat([_to_nchw_f32(x0b), _to_nchw_f32(x1b)], dim=1)
     ref = F.relu(F.conv2d(xin, wb.float().reshape(3, 3, cout, c0 + c1).permute(2, 3, 0, 1), b, padding=1))
@@ -94,10 +100,12 @@ def test_conv3x3_two_sources_and_pool(cuda_dev, amode):
     assert torch.equal(_to_nchw_f32(pool), F.max_pool2d(_to_nchw_f32(out), 2))
 
 
+@pytest.mark.parametrize("pair", [0, 1])
 @pytest.mark.parametrize("cin,cout,bn", [(128, 64, 128), (256, 128, 64), (128, 64, 256)])
-def test_convt2x2(cuda_dev, cin, cout, bn):
+def test_convt2x2(cuda_dev, cin, cout, bn, pair):
     nat = _nat()
-    n, h, w = 2, 16, 24
+    n, h, w = (2, 16, 24) if not pair else (3, 16, 8)      # 3 tiles: the odd-tail pair path
+    bn |= pair << 12
     g = torch.Generator(device="cpu").manual_seed(cin + cout)
     x = torch.randn((n, cin, h, w), generator=g).to(cuda_dev)
     wt = (torch.randn((cin, cout, 2, 2), generator=g) / cin ** 0.5).to(cuda_dev)
@@ -176,11 +184,14 @@ def test_stem_tensor_core(cuda_dev, fmt, n, h, w):
     assert not ((_to_nchw_f32(out2) - ref).abs() > tol).any()
 
 
+@pytest.mark.parametrize("pair", [0, 1])
 @pytest.mark.parametrize("amode", AMODES)
-def test_conv3x3_head(cuda_dev, amode):
+def test_conv3x3_head(cuda_dev, amode, pair):
     """conv1.net.3 + out_conv 1x1 + logit-space threshold in one kernel (unet_model.py:86,
     inference.py:72-79)."""
     nat = _nat()
+    if pair and amode != 2:
+        pytest.skip("CTA-pair kernels are instantiated for A_HALO only")
     n, h, w, ncls = 2, 32, 32, 3
     g = torch.Generator(device="cpu").manual_seed(3)
     x = torch.randn((n, 64, h, w), generator=g).to(cuda_dev)
@@ -194,7 +205,7 @@ def test_conv3x3_head(cuda_dev, amode):
     thr = (C.c_float * ncls)(-0.5, 0.0, 0.7)
     nat.check(nat.lib().unetb200_conv3x3_head(xb.data_ptr(), 64, wb.data_ptr(), b.data_ptr(),
                                               hw.data_ptr(), hb.data_ptr(), ncls, n, h, w,
-                                              logits.data_ptr(), mask.data_ptr(), thr, amode, 1, None))
+                                              logits.data_ptr(), mask.data_ptr(), thr, amode, 1 | (pair << 1), None))
     torch.cuda.synchronize()
     feat = F.relu(F.conv2d(_to_nchw_f32(xb), wb.float().reshape(3, 3, 64, 64).permute(2, 3, 0, 1), b, padding=1))
     ref = F.conv2d(feat, hw.reshape(ncls, 64, 1, 1), hb)

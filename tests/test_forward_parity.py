@@ -107,6 +107,24 @@ def test_weight_stationary_identical(model, cuda_dev):
     assert torch.equal(z0, z1)
 
 
+def test_cta_pairs_identical(model, cuda_dev):
+    """cta_group::2 launches (one M = 256 UMMA over two CTAs) accumulate every output element in
+    the same order as two M = 128 UMMAs: bit-identical logits.  3 x 48 x 80 gives odd tile counts."""
+    from tw_invoice_unet_ocr_llm_b200.synthetic import synthetic_invoices
+    x = synthetic_invoices(3, 48, 80, seed=50).to(cuda_dev)
+    eng = model.engine(cuda_dev)
+    keep = eng.get_option("pair")
+    try:
+        eng.set_option("pair", 0)
+        z0, _ = eng.run(x)
+        eng.set_option("pair", 1)
+        z1, _ = eng.run(x)
+        torch.cuda.synchronize()
+    finally:
+        eng.set_option("pair", keep)
+    assert torch.equal(z0, z1)
+
+
 def test_u8_input_and_masks(model, fixture_state, cuda_dev):
     """uint8 NHWC ingest (/255 in-kernel, inference.py:36) == float path, bit for bit; fused
     logit-space threshold == sigmoid(z) > t on the returned logits (inference.py:72-79)."""

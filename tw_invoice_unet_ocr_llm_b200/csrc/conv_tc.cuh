@@ -28,8 +28,8 @@
 //             but relies on the swizzle being a function of the absolute smem
 //             address (validated on hardware by tests/test_conv_kernels.py).
 // TMA zero-fills out-of-bounds box elements, which is the conv zero padding.
-//   A_STEM  : first conv of the network (Cin = n_channels <= 3, K = 9*Cin <= 27): four extra
-//             warps build the im2col rows themselves, straight from the user's fp32 NCHW /
+//   A_STEM  : first conv of the network (Cin = n_channels <= 3, K = 9*Cin <= 27): eight extra
+//             warps (two groups of 128 threads taking alternate tiles) build the im2col rows themselves, straight from the user's fp32 NCHW /
 //             uint8 NHWC tensor, as bf16 hi + lo pairs (x = hi + lo to 16 significand bits);
 //             the GEMM is x_hi*w_hi + x_lo*w_hi + x_hi*w_lo over two 64-wide K slices, i.e.
 //             fp32-class accuracy from bf16 MMAs.  The layer is HBM-bound (it writes 64 bf16
@@ -44,7 +44,17 @@
 // Weight-stationary mode (`wstat`): when the whole [taps x Cin x BN] weight slab of the
 // layer fits in shared memory (the Cout = 64 layers and up1), it is loaded once per CTA
 // and the main loop streams activations only.
-// Two TMEM accumulators so the epilogue of tile i overlaps the MMAs of tile i+1.
+// Two to four TMEM accumulators (512 columns / BN) so the epilogue of tile i overlaps the MMAs
+// of the following tiles.
+//
+// CTA pairs (`PAIR`, cluster of 2, tcgen05 cta_group::2): two CTAs on one TPC take two pixel
+// tiles of the same column block; one UMMA of M = 256 spans both.  Each CTA stages its own
+// activation patch and only HALF of the weight rows (BN/2), which halves the weight smem
+// fill and cuts the shared-memory operand fetch per MMA from (128 + N) to (128 + N/2) rows
+// -- the limiter of the N = 64 / 128 layers.  The leader CTA (rank 0) issues every MMA;
+// "full" barriers live in the leader and count both CTAs' TMA bytes; "empty" / "accumulator
+// ready" barriers are signalled in both CTAs by multicast tcgen05.commit; the peer's epilogue
+// warps hand the accumulator back with remote mbarrier arrives.
 #pragma once
 #include "ptx.cuh"
 
@@ -78,7 +88,7 @@ struct ConvParams {
     int ncls;
     int na, nb;              // ring depths: activation items / weight tiles (wstat: nb = all tiles)
     int wstat;               // 1 = weight-stationary (see header)
-    int n_out;               // output staging buffers (1 or 2)
+    int n_out;               // output (and pool) staging buffers, 1..4
     int pf_items;            // activation items prefetched into L2 ahead of the smem ring (0 = off)
     int off_b, off_out, off_pool, off_bar;   // smem carve-up, bytes from the 1024-aligned base
     int off_patch;           // A_STEM: 2 x [Cin][18][10] fp32 input halo patches
@@ -86,14 +96,19 @@ struct ConvParams {
     int stem_fmt;
 };
 
-template <int BN, int TAPS, int AMODE>
+template <int BN, int TAPS, int AMODE, bool PAIR = false>
 struct ConvCfg {
     static constexpr int TPA = TAPS == 1 ? 1 : (AMODE == A_TAP ? 1 : (AMODE == A_COL3 ? 3 : 9));
     static constexpr int A_ROWS = TAPS == 1 ? 128 : (AMODE == A_TAP ? 128 : (AMODE == A_COL3 ? 144 : 180));
     static constexpr int A_TX = A_ROWS * 128;
     static constexpr int A_STAGE = (A_TX + 1023) / 1024 * 1024;
-    static constexpr int B_STAGE = BN * 128;
-    static constexpr int TMEM_COLS = 2 * BN;                   // 128 / 256 / 512
+    static constexpr int B_TAP = (PAIR ? BN / 2 : BN) * 128;     // one tap's weight rows (a CTA pair splits them)
+    // taps per weight ring stage / per TMA box: thin per-tap tiles (<= 8 KB, A_HALO) are grouped by three so a
+    // stage covers 12 MMAs and the (cross-CTA) barrier traffic drops 3x
+    static constexpr int TPB = (TAPS == 9 && AMODE == A_HALO && B_TAP <= 8192) ? 3 : 1;   // (all 9 taps of a slice are one A item only in A_HALO)
+    static constexpr int B_STAGE = TPB * B_TAP;
+    static constexpr int NACC = BN == 256 ? 2 : 4;             // accumulator stages in TMEM
+    static constexpr int TMEM_COLS = NACC * BN;                // 256 / 512 / 512 columns
 };
 constexpr int kOutStage = 16384;      // 128 pixels x 64 channels bf16
 constexpr int kPoolStage = 4096;      // 32 pixels x 64 channels bf16
@@ -103,15 +118,16 @@ constexpr int kStaticSmem = 4096 + kMaxClasses * 64 * 4 + 64;   // s_bias + s_he
 constexpr int kSmemLimit = 232448;    // 227 KB per CTA on sm_100
 
 // X: A_STEM -> n_channels of the network input; EPI_HEAD -> n_classes (0 = generic, up to 8).
-template <int BN, int TAPS, int AMODE, int EPI, int X = 0>
-__global__ void __launch_bounds__(AMODE == A_STEM ? 384 : 256, 1)
+template <int BN, int TAPS, int AMODE, int EPI, int X = 0, bool PAIR = false>
+__global__ void __launch_bounds__(AMODE == A_STEM ? 512 : 256, 1)
 conv_tc_kernel(const __grid_constant__ ConvParams p) {
     constexpr int CIN = X;
+    static_assert(!(PAIR && AMODE == A_STEM), "the stem runs unpaired");
     static_assert(TAPS == 9 || TAPS == 1, "3x3 conv or per-tap GEMM");
     static_assert(AMODE != A_STEM || (TAPS == 1 && BN == 64 && CIN >= 1 && 9 * CIN <= 32),
                   "stem: im2col rows of <= 32 taps, 64 output channels");
     static_assert(EPI != EPI_HEAD || BN == 64, "fused head needs all 64 channels in one tile");
-    using Cfg = ConvCfg<BN, TAPS, AMODE>;
+    using Cfg = ConvCfg<BN, TAPS, AMODE, PAIR>;
     constexpr int TPA = Cfg::TPA;
     constexpr int ITEMS = TAPS / TPA;
 
@@ -127,8 +143,8 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
     const uint32_t bar_b_full = bar_a_empty + 8 * kMaxRing;
     const uint32_t bar_b_empty = bar_b_full + 8 * kMaxRing;
     const uint32_t bar_t_full = bar_b_empty + 8 * kMaxRing;
-    const uint32_t bar_t_empty = bar_t_full + 16;
-    const uint32_t s_tmem_ptr = bar_t_empty + 16;
+    const uint32_t bar_t_empty = bar_t_full + 32;
+    const uint32_t s_tmem_ptr = bar_t_empty + 32;
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));   // generic view of smem_base
 
     __shared__ __align__(16) float s_bias[1024];
@@ -147,18 +163,21 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < kMaxRing; ++i) {
-            mbar_init(bar_a_full + 8 * i, AMODE == A_STEM ? 128 : 1);   // stem: every im2col thread arrives
+            // full: one producer arrive per CTA of the pair (stem: every im2col thread arrives)
+            mbar_init(bar_a_full + 8 * i, AMODE == A_STEM ? 128 : (PAIR ? 2 : 1));
             mbar_init(bar_a_empty + 8 * i, 1);
-            mbar_init(bar_b_full + 8 * i, 1);
+            mbar_init(bar_b_full + 8 * i, PAIR ? 2 : 1);
             mbar_init(bar_b_empty + 8 * i, 1);
         }
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < Cfg::NACC; ++i) {
             mbar_init(bar_t_full + 8 * i, 1);
-            mbar_init(bar_t_empty + 8 * i, 4);   // one arrive per epilogue warp
+            mbar_init(bar_t_empty + 8 * i, PAIR ? 8 : 4);   // one arrive per epilogue warp (of both CTAs)
         }
         mbar_fence_init();
     }
-    if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(s_tmem_ptr);
+    if (warp == 2) {
+        if (PAIR) tmem_alloc_pair<Cfg::TMEM_COLS>(s_tmem_ptr); else tmem_alloc<Cfg::TMEM_COLS>(s_tmem_ptr);
+    }
     if (EPI == EPI_HEAD) {
         for (int i = threadIdx.x; i < kMaxClasses * 64; i += blockDim.x)
             s_head_w[i] = i < p.ncls * 64 ? p.head_w[i] : 0.f;
@@ -166,13 +185,30 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
     }
     for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) s_bias[i] = p.bias[i];
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all(); else __syncthreads();   // barriers of both CTAs initialised before any remote arrive
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(
         smem_gen + (s_tmem_ptr - smem_base));
 
     const int n_cs = (p.C0 + p.C1) >> 6;            // 64-channel slices along K
     const int tiles_per_img = p.tiles_x * p.tiles_y;
+
+    // Work units.  Unpaired: unit = (pixel tile mt, column block nb), one per CTA.  Paired: unit =
+    // (pixel-tile pair, nb); CTA `rank` of the pair takes pixel tile 2*g + rank.  A pair whose second
+    // tile does not exist (odd tile count) recomputes the last tile and skips its stores.
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0;
+    const int m_tiles = tiles_per_img * p.NIMG;
+    const int n_units = PAIR ? ((m_tiles + 1) >> 1) * p.n_blocks : m_tiles * p.n_blocks;
+    const int first_unit = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+    const int unit_stride = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+    auto decode = [&](int u, int& mt, int& nb) -> bool {
+        nb = u % p.n_blocks;
+        const int g = u / p.n_blocks;
+        mt = PAIR ? 2 * g + static_cast<int>(rank) : g;
+        const bool valid = mt < m_tiles;
+        if (!valid) mt = m_tiles - 1;
+        return valid;
+    };
 
     if (AMODE == A_STEM && warp >= 8) {
         // ================== im2col producer (first conv only) =================
@@ -183,8 +219,9 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
         constexpr int KS = 9 * CI;
         constexpr int PE = CI * 180;                             // patch elements: [CIN][18][10]
         constexpr int NL = (PE + 127) / 128;
-        const int r = threadIdx.x - 256;
-        float* s_patch = reinterpret_cast<float*>(smem_gen + p.off_patch);
+        const int grp = (threadIdx.x - 256) >> 7;                // producer group: takes tiles it % 2 == grp
+        const int r = (threadIdx.x - 256) & 127;
+        float* s_patch = reinterpret_cast<float*>(smem_gen + p.off_patch) + grp * 2 * PE;
         const int hh = r >> 3, ww = r & 7;
         auto fetch = [&](int t, float (&regs)[NL]) {
             const int n = t / tiles_per_img;
@@ -219,16 +256,16 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
             }
         };
         float regs[NL];
-        uint32_t sa = 0, pa = 0;
-        int it = 0;
-        int t = blockIdx.x;
+        const int stride = 2 * static_cast<int>(gridDim.x);
+        int it = 0;                                              // this group's tile counter
+        int t = static_cast<int>(blockIdx.x) + grp * static_cast<int>(gridDim.x);
         if (t < p.total_tiles) {
             fetch(t, regs);
             publish(0, regs);
         }
-        named_bar_sync(3, 128);
-        for (; t < p.total_tiles; t += gridDim.x, ++it) {
-            const int tn = t + gridDim.x;
+        named_bar_sync(3 + grp, 128);
+        for (; t < p.total_tiles; t += stride, ++it) {
+            const int tn = t + stride;
             if (tn < p.total_tiles) fetch(tn, regs);             // global loads in flight during the build
             const float* pt = s_patch + (it & 1) * PE;
             uint32_t hi[16], lo[16];                             // 32 bf16 each, zero padded past KS
@@ -250,47 +287,48 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
                 h[1] = __uint_as_float(hi[k2] & 0xffff0000u);
                 lo[k2] = pack_bf16x2(v[0] - h[0], v[1] - h[1]);
             }
+            // ring items of this CTA-local tile (2 * it + grp): slice 0 then slice 1
+            const uint32_t item0 = 2u * (2u * static_cast<uint32_t>(it) + grp);
+            const uint32_t na = static_cast<uint32_t>(p.na);
             // ---- slice 0: [hi | lo]
-            mbar_wait(bar_a_empty + 8 * sa, pa ^ 1, 1, p.dbg);
             {
+                const uint32_t sa = item0 % na, pa = (item0 / na) & 1;
+                mbar_wait(bar_a_empty + 8 * sa, pa ^ 1, 1, p.dbg);
                 const uint32_t row = sA + sa * Cfg::A_STAGE + r * 128;
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     st_shared_v4(row + ((c ^ (r & 7)) << 4), hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
                     st_shared_v4(row + (((c + 4) ^ (r & 7)) << 4), lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
                 }
+                fence_proxy_async_smem();
+                mbar_arrive(bar_a_full + 8 * sa);
             }
-            fence_proxy_async_smem();
-            mbar_arrive(bar_a_full + 8 * sa);
-            if (++sa == static_cast<uint32_t>(p.na)) { sa = 0; pa ^= 1; }
             // ---- slice 1: [hi | (unused)]
-            mbar_wait(bar_a_empty + 8 * sa, pa ^ 1, 2, p.dbg);
             {
+                const uint32_t sa = (item0 + 1) % na, pa = ((item0 + 1) / na) & 1;
+                mbar_wait(bar_a_empty + 8 * sa, pa ^ 1, 2, p.dbg);
                 const uint32_t row = sA + sa * Cfg::A_STAGE + r * 128;
 #pragma unroll
                 for (int c = 0; c < 4; ++c)
                     st_shared_v4(row + ((c ^ (r & 7)) << 4), hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+                fence_proxy_async_smem();
+                mbar_arrive(bar_a_full + 8 * sa);
             }
-            fence_proxy_async_smem();
-            mbar_arrive(bar_a_full + 8 * sa);
-            if (++sa == static_cast<uint32_t>(p.na)) { sa = 0; pa ^= 1; }
             if (tn < p.total_tiles) publish((it + 1) & 1, regs);
-            named_bar_sync(3, 128);
+            named_bar_sync(3 + grp, 128);
         }
     } else if (warp == 0) {
         // ===================== TMA producer: activations ======================
         if (lane == 0 && AMODE != A_STEM) {
             // flat walk over this CTA's activation items: idx -> (tile, 64-channel slice, item)
             const int ipt = n_cs * ITEMS;
-            const int my_tiles = blockIdx.x < p.total_tiles
-                                     ? (p.total_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
-                                           static_cast<int>(gridDim.x)
-                                     : 0;
-            const int n_items = my_tiles * ipt;
+            const int my_units = first_unit < n_units ? (n_units - first_unit + unit_stride - 1) / unit_stride : 0;
+            const int n_items = my_units * ipt;
             auto locate = [&](int idx, const CUtensorMap*& tm, int& ca, int& bx, int& by, int& n) {
                 const int tl = idx / ipt, rem = idx - tl * ipt;
                 const int cs = rem / ITEMS, item = rem - cs * ITEMS;
-                const int mt = (static_cast<int>(blockIdx.x) + tl * static_cast<int>(gridDim.x)) / p.n_blocks;
+                int mt, nb_unused;
+                decode(first_unit + tl * unit_stride, mt, nb_unused);
                 n = mt / tiles_per_img;
                 const int r = mt - n * tiles_per_img;
                 by = (r / p.tiles_x) * 16;
@@ -319,34 +357,56 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
                 }
                 locate(i, tm, ca, bx, by, n);
                 mbar_wait(bar_a_empty + 8 * sa, pa ^ 1, 1, p.dbg);
-                mbar_expect_tx(bar_a_full + 8 * sa, Cfg::A_TX);
-                tma_load_4d(sA + sa * Cfg::A_STAGE, tm, bar_a_full + 8 * sa, ca, bx, by, n);
+                if (PAIR) {
+                    // both CTAs' bytes are counted on the leader's barrier
+                    const uint32_t fb = mapa_shared(bar_a_full + 8 * sa, 0);
+                    if (rank == 0) mbar_expect_tx(bar_a_full + 8 * sa, 2 * Cfg::A_TX); else mbar_arrive_cluster(fb);
+                    tma_load_4d_pair(sA + sa * Cfg::A_STAGE, tm, fb, ca, bx, by, n);
+                } else {
+                    mbar_expect_tx(bar_a_full + 8 * sa, Cfg::A_TX);
+                    tma_load_4d(sA + sa * Cfg::A_STAGE, tm, bar_a_full + 8 * sa, ca, bx, by, n);
+                }
                 if (++sa == static_cast<uint32_t>(p.na)) { sa = 0; pa ^= 1; }
             }
         }
     } else if (warp == 3) {
         // ======================= TMA producer: weights ========================
         if (lane == 0) {
+            const int row_off = PAIR ? static_cast<int>(rank) * (BN / 2) : 0;   // this CTA's half of the weight rows
             if (p.wstat) {
                 // whole weight slab of this layer, once: slot = cs * TAPS + tap
-                mbar_expect_tx(bar_b_full, static_cast<uint32_t>(n_cs * TAPS) * Cfg::B_STAGE);
+                const uint32_t bytes = static_cast<uint32_t>(n_cs * TAPS) * Cfg::B_TAP;
+                const uint32_t fb = PAIR ? mapa_shared(bar_b_full, 0) : bar_b_full;
+                if (!PAIR) mbar_expect_tx(bar_b_full, bytes);
+                else if (rank == 0) mbar_expect_tx(bar_b_full, 2 * bytes);
+                else mbar_arrive_cluster(fb);
                 for (int cs = 0; cs < n_cs; ++cs)
-                    for (int tap = 0; tap < TAPS; ++tap)
-                        tma_load_3d(sB + (cs * TAPS + tap) * Cfg::B_STAGE, &p.tmB, bar_b_full,
-                                    cs << 6, 0, tap);
+                    for (int tap = 0; tap < TAPS; tap += Cfg::TPB) {      // one box = TPB consecutive taps
+                        const uint32_t dst = sB + (cs * TAPS + tap) * Cfg::B_TAP;
+                        if (PAIR) tma_load_3d_pair(dst, &p.tmB, fb, cs << 6, row_off, tap);
+                        else tma_load_3d(dst, &p.tmB, fb, cs << 6, 0, tap);
+                    }
             } else {
                 uint32_t sb = 0, pb = 0;
-                for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-                    const int nb = t % p.n_blocks;
+                for (int u = first_unit; u < n_units; u += unit_stride) {
+                    const int nb = u % p.n_blocks;
                     for (int cs = 0; cs < n_cs; ++cs) {
 #pragma unroll 1
-                        for (int i = 0; i < TAPS; ++i) {
-                            // same tap order as the MMA loop (A_COL3 walks column-major)
+                        for (int i = 0; i < TAPS; i += Cfg::TPB) {
+                            // same tap order as the MMA loop (A_COL3 walks column-major, TPB == 1 there)
                             const int tap = (TAPS == 9 && AMODE == A_COL3) ? (i % 3) * 3 + i / 3 : i;
                             mbar_wait(bar_b_empty + 8 * sb, pb ^ 1, 3, p.dbg);
-                            mbar_expect_tx(bar_b_full + 8 * sb, Cfg::B_STAGE);
-                            tma_load_3d(sB + sb * Cfg::B_STAGE, &p.tmB, bar_b_full + 8 * sb, cs << 6,
-                                        nb * BN, tap);
+                            if (PAIR) {
+                                const uint32_t fb = mapa_shared(bar_b_full + 8 * sb, 0);
+                                if (rank == 0) mbar_expect_tx(bar_b_full + 8 * sb, 2 * Cfg::B_STAGE);
+                                else mbar_arrive_cluster(fb);
+                                tma_load_3d_pair(sB + sb * Cfg::B_STAGE, &p.tmB, fb, cs << 6,
+                                                 nb * BN + row_off, tap);
+                            } else {
+                                mbar_expect_tx(bar_b_full + 8 * sb, Cfg::B_STAGE);
+                                tma_load_3d(sB + sb * Cfg::B_STAGE, &p.tmB, bar_b_full + 8 * sb, cs << 6,
+                                            nb * BN, tap);
+                            }
                             if (++sb == static_cast<uint32_t>(p.nb)) { sb = 0; pb ^= 1; }
                         }
                     }
@@ -359,8 +419,8 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
         // 32-64 cycles, so the issue path itself is kept to a couple of integer ops per MMA:
         // descriptor high words are constants, low words are (base + constant) in 16-byte
         // units, and mbarrier probes for the next stage are issued ahead of the MMAs.
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(BN);
+        if (lane == 0 && rank == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(BN, PAIR ? 256 : 128);
             constexpr uint32_t a_sbo = (TAPS == 9 && AMODE == A_HALO) ? 10 * 128 : 1024;
             constexpr uint32_t a_hi = umma_desc_hi_sw128(a_sbo);
             constexpr uint32_t b_hi = umma_desc_hi_sw128(1024);
@@ -370,8 +430,8 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
                 tc_fence_after();
             }
             const uint32_t b_lo0 = umma_desc_lo(sB);
-            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tile_it) {
-                const uint32_t acc = tile_it & 1, acc_ph = (tile_it >> 1) & 1;
+            for (int u = first_unit; u < n_units; u += unit_stride, ++tile_it) {
+                const uint32_t acc = tile_it % Cfg::NACC, acc_ph = (tile_it / Cfg::NACC) & 1;
                 mbar_wait(bar_t_empty + 8 * acc, acc_ph ^ 1, 4, p.dbg);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
@@ -384,7 +444,7 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
                         const uint32_t a_lo0 = umma_desc_lo(sA + sa * Cfg::A_STAGE);
                         if (p.wstat) {
                             // resident weights: slot = cs * TAPS + tap, no barrier traffic
-                            const uint32_t b_cs = b_lo0 + (cs * TAPS) * (Cfg::B_STAGE >> 4);
+                            const uint32_t b_cs = b_lo0 + (cs * TAPS) * (Cfg::B_TAP >> 4);
 #pragma unroll
                             for (int tt = 0; tt < TPA; ++tt) {
                                 const int tap_c = TAPS == 1 ? 0 : (AMODE == A_COL3 ? tt * 3 : tt);
@@ -392,43 +452,54 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
                                 const uint32_t a_off = TAPS == 1 ? 0
                                                      : (AMODE == A_COL3 ? tt * (1024 >> 4)
                                                      : (AMODE == A_HALO ? ((tt / 3) * 10 + (tt % 3)) * (128 >> 4) : 0));
-                                const uint32_t b_lo = b_cs + (tap_c + tap_r) * (Cfg::B_STAGE >> 4);
+                                const uint32_t b_lo = b_cs + (tap_c + tap_r) * (Cfg::B_TAP >> 4);
 #pragma unroll
                                 for (int k = 0; k < 4; ++k) {
                                     if (AMODE == A_STEM && cs == 1 && k >= 2) break;   // slice 1 holds 32 taps only
-                                    umma_bf16(d_tmem, umma_desc(a_lo0 + a_off + 2 * k, a_hi),
-                                              umma_desc(b_lo + 2 * k, b_hi), idesc, accumulate);
+                                    if (PAIR) umma_bf16_pair(d_tmem, umma_desc(a_lo0 + a_off + 2 * k, a_hi),
+                                                             umma_desc(b_lo + 2 * k, b_hi), idesc, accumulate);
+                                    else umma_bf16(d_tmem, umma_desc(a_lo0 + a_off + 2 * k, a_hi),
+                                                   umma_desc(b_lo + 2 * k, b_hi), idesc, accumulate);
                                     accumulate = 1;
                                 }
                             }
                         } else {
+                            constexpr int TPB = Cfg::TPB;
                             bool ready = mbar_try_wait(bar_b_full + 8 * sb, pb);
+                            uint32_t cur = sb, b_stage_lo = 0;
 #pragma unroll
                             for (int tt = 0; tt < TPA; ++tt) {
-                                if (!ready) mbar_wait(bar_b_full + 8 * sb, pb, 6, p.dbg);
-                                tc_fence_after();
-                                const uint32_t b_lo = b_lo0 + sb * (Cfg::B_STAGE >> 4);
-                                const uint32_t cur = sb;
-                                if (++sb == static_cast<uint32_t>(p.nb)) { sb = 0; pb ^= 1; }
-                                // probe the next weight stage now; the answer is needed after these MMAs
-                                ready = mbar_try_wait(bar_b_full + 8 * sb, pb);
+                                if (tt % TPB == 0) {
+                                    if (!ready) mbar_wait(bar_b_full + 8 * sb, pb, 6, p.dbg);
+                                    tc_fence_after();
+                                    b_stage_lo = b_lo0 + sb * (Cfg::B_STAGE >> 4);
+                                    cur = sb;
+                                    if (++sb == static_cast<uint32_t>(p.nb)) { sb = 0; pb ^= 1; }
+                                    // probe the next weight stage now; the answer is needed after these MMAs
+                                    ready = mbar_try_wait(bar_b_full + 8 * sb, pb);
+                                }
+                                const uint32_t b_lo = b_stage_lo + (tt % TPB) * (Cfg::B_TAP >> 4);
                                 const uint32_t a_off = TAPS == 1 ? 0
                                                      : (AMODE == A_COL3 ? tt * (1024 >> 4)
                                                      : (AMODE == A_HALO ? ((tt / 3) * 10 + (tt % 3)) * (128 >> 4) : 0));
 #pragma unroll
                                 for (int k = 0; k < 4; ++k) {
-                                    umma_bf16(d_tmem, umma_desc(a_lo0 + a_off + 2 * k, a_hi),
-                                              umma_desc(b_lo + 2 * k, b_hi), idesc, accumulate);
+                                    if (PAIR) umma_bf16_pair(d_tmem, umma_desc(a_lo0 + a_off + 2 * k, a_hi),
+                                                             umma_desc(b_lo + 2 * k, b_hi), idesc, accumulate);
+                                    else umma_bf16(d_tmem, umma_desc(a_lo0 + a_off + 2 * k, a_hi),
+                                                   umma_desc(b_lo + 2 * k, b_hi), idesc, accumulate);
                                     accumulate = 1;
                                 }
-                                umma_commit(bar_b_empty + 8 * cur);
+                                if (tt % TPB == TPB - 1) {
+                                    if (PAIR) umma_commit_pair(bar_b_empty + 8 * cur); else umma_commit(bar_b_empty + 8 * cur);
+                                }
                             }
                         }
-                        umma_commit(bar_a_empty + 8 * sa);
+                        if (PAIR) umma_commit_pair(bar_a_empty + 8 * sa); else umma_commit(bar_a_empty + 8 * sa);
                         if (++sa == static_cast<uint32_t>(p.na)) { sa = 0; pa ^= 1; }
                     }
                 }
-                umma_commit(bar_t_full + 8 * acc);
+                if (PAIR) umma_commit_pair(bar_t_full + 8 * acc); else umma_commit(bar_t_full + 8 * acc);
             }
         }
     } else if (warp >= 4) {
@@ -437,14 +508,19 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
         const int row = q * 32 + lane;          // pixel row of the tile: h = row/8, w = row%8
         const int et = threadIdx.x - 128;       // 0..127
         uint32_t tile_it = 0, chunk_it = 0;
-        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tile_it) {
-            const int nb = t % p.n_blocks;
-            const int mt = t / p.n_blocks;
+        // hand-back of an accumulator: arrive on the (leader's) barrier the MMA issuer waits on
+        auto release_acc = [&](uint32_t acc) {
+            if (PAIR) mbar_arrive_cluster(mapa_shared(bar_t_empty + 8 * acc, 0));
+            else mbar_arrive(bar_t_empty + 8 * acc);
+        };
+        for (int u = first_unit; u < n_units; u += unit_stride, ++tile_it) {
+            int mt, nb;
+            const bool valid = decode(u, mt, nb);
             const int n = mt / tiles_per_img;
             const int r = mt - n * tiles_per_img;
             const int y0 = (r / p.tiles_x) * 16;
             const int x0 = (r % p.tiles_x) * 8;
-            const uint32_t acc = tile_it & 1, acc_ph = (tile_it >> 1) & 1;
+            const uint32_t acc = tile_it % Cfg::NACC, acc_ph = (tile_it / Cfg::NACC) & 1;
             mbar_wait(bar_t_full + 8 * acc, acc_ph, 7, p.dbg);
             tc_fence_after();
             const uint32_t t_addr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
@@ -486,9 +562,9 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar_t_empty + 8 * acc);
+                if (lane == 0) release_acc(acc);
                 const int y = y0 + (row >> 3), x = x0 + (row & 7);
-                if (y < p.H && x < p.W) {
+                if (valid && y < p.H && x < p.W) {
 #pragma unroll
                     for (int c = 0; c < NC; ++c) {
                         if (c < p.ncls) {
@@ -506,12 +582,17 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
                 const int gcol = nb * BN + j * 64;            // global column of this 64-wide chunk
                 const int tapo = EPI == EPI_UPSAMPLE ? gcol / p.Cout : 0;
                 const int ch0 = EPI == EPI_UPSAMPLE ? gcol - tapo * p.Cout : gcol;
-                const uint32_t buf = p.n_out == 2 ? (chunk_it & 1) : 0;
+                const uint32_t buf = chunk_it % static_cast<uint32_t>(p.n_out);
                 const uint32_t obuf = sOut + buf * kOutStage;
                 const uint32_t pbuf = sPool + buf * kPoolStage;
                 // the staging buffer was last read by the store issued n_out chunks ago
                 if (et == 0) {
-                    if (p.n_out == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
+                    switch (p.n_out) {
+                        case 4: tma_store_wait_read<3>(); break;
+                        case 3: tma_store_wait_read<2>(); break;
+                        case 2: tma_store_wait_read<1>(); break;
+                        default: tma_store_wait_read<0>(); break;
+                    }
                 }
                 named_bar_sync(1, 128);
                 uint32_t pk[32];
@@ -540,7 +621,7 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
                 if (j == BN / 64 - 1) {   // accumulator fully drained -> hand it back to the MMA warp
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_t_empty + 8 * acc);
+                    if (lane == 0) release_acc(acc);
                 }
 #pragma unroll
                 for (int c16 = 0; c16 < 8; ++c16)
@@ -564,7 +645,7 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
                 }
                 fence_proxy_async_smem();
                 named_bar_sync(2, 128);
-                if (et == 0) {
+                if (et == 0 && valid) {
                     if (EPI == EPI_UPSAMPLE)
                         tma_store_4d(&p.tmOut[tapo], obuf, ch0, x0, y0, n);
                     else
@@ -579,10 +660,10 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
     }
 
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all(); else __syncthreads();   // the peer may still signal this CTA's barriers until here
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+        if (PAIR) tmem_dealloc_pair<Cfg::TMEM_COLS>(tmem_base); else tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
     }
 }
 

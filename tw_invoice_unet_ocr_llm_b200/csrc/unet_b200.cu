@@ -83,12 +83,12 @@ int make_act_map(CUtensorMap* m, const void* base, int C, int W, int H, int N, i
 }
 
 // weights: dims (CinTot, rows, taps)
-int make_w_map(CUtensorMap* m, const void* base, int cin, int rows, int taps, int bn) {
+int make_w_map(CUtensorMap* m, const void* base, int cin, int rows, int taps, int bn, int box_taps = 1) {
     EncodeTiledFn enc = encode_tiled();
     if (!enc) return fail(UNETB200_ECUDA, "cuTensorMapEncodeTiled entry point unavailable");
     cuuint64_t dims[3] = {uint64_t(cin), uint64_t(rows), uint64_t(taps)};
     cuuint64_t strides[2] = {uint64_t(cin) * 2, uint64_t(rows) * cin * 2};
-    cuuint32_t box[3] = {64, uint32_t(bn), 1};
+    cuuint32_t box[3] = {64, uint32_t(bn), uint32_t(box_taps)};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides,
                      box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -181,17 +181,33 @@ typedef void (*ConvKernel)(const ub::ConvParams);
 
 struct ConvLaunch {
     ConvKernel fn = nullptr;
-    int a_stage = 0, b_stage = 0;   // bytes per activation item / weight tile
+    int a_stage = 0, b_stage = 0;   // bytes per activation item / weight ring stage
+    int b_tap = 0, tpb = 1;         // bytes of one tap's weight tile, taps per stage (= per TMA box)
     int smem = 0;                   // dynamic shared memory of this launch (set by plan_smem)
+    bool pair = false;              // launched as clusters of 2 CTAs (cta_group::2)
 };
 
-template <int BN, int TAPS, int AMODE, int EPI, int X = 0>
+template <int BN, int TAPS, int AMODE, int EPI, int X = 0, bool PAIR = false>
 ConvLaunch conv_inst() {
     ConvLaunch l;
-    l.fn = ub::conv_tc_kernel<BN, TAPS, AMODE, EPI, X>;
-    l.a_stage = ub::ConvCfg<BN, TAPS, AMODE>::A_STAGE;
-    l.b_stage = ub::ConvCfg<BN, TAPS, AMODE>::B_STAGE;
+    l.fn = ub::conv_tc_kernel<BN, TAPS, AMODE, EPI, X, PAIR>;
+    l.a_stage = ub::ConvCfg<BN, TAPS, AMODE, PAIR>::A_STAGE;
+    l.b_stage = ub::ConvCfg<BN, TAPS, AMODE, PAIR>::B_STAGE;
+    l.b_tap = ub::ConvCfg<BN, TAPS, AMODE, PAIR>::B_TAP;
+    l.tpb = ub::ConvCfg<BN, TAPS, AMODE, PAIR>::TPB;
+    l.pair = PAIR;
     return l;
+}
+
+// CTA-pair instantiations exist for the production staging mode (A_HALO) and the up-convs.
+template <int BN>
+ConvLaunch pair_pick(int taps, int epi) {
+    if (taps == 1) return conv_inst<BN, 1, ub::A_TAP, ub::EPI_UPSAMPLE, 0, true>();
+    switch (epi) {
+        case ub::EPI_STORE: return conv_inst<BN, 9, ub::A_HALO, ub::EPI_STORE, 0, true>();
+        case ub::EPI_STORE_POOL: return conv_inst<BN, 9, ub::A_HALO, ub::EPI_STORE_POOL, 0, true>();
+    }
+    return ConvLaunch();
 }
 
 template <int BN, int AMODE>
@@ -219,10 +235,22 @@ ConvLaunch stem_inst() {
     l.fn = ub::conv_tc_kernel<64, 1, ub::A_STEM, ub::EPI_STORE, CIN>;
     l.a_stage = ub::ConvCfg<64, 1, ub::A_STEM>::A_STAGE;
     l.b_stage = ub::ConvCfg<64, 1, ub::A_STEM>::B_STAGE;
+    l.b_tap = ub::ConvCfg<64, 1, ub::A_STEM>::B_TAP;
     return l;
 }
 
-ConvLaunch pick_conv(int taps, int bn, int amode, int epi, int stem_cin = 0, int ncls = 0) {
+ConvLaunch pick_conv(int taps, int bn, int amode, int epi, int stem_cin = 0, int ncls = 0, bool pair = false) {
+    if (pair && amode != ub::A_STEM && (taps == 1 || amode == ub::A_HALO)) {
+        if (epi == ub::EPI_HEAD)
+            return ncls == 3 ? conv_inst<64, 9, ub::A_HALO, ub::EPI_HEAD, 3, true>()
+                             : conv_inst<64, 9, ub::A_HALO, ub::EPI_HEAD, 0, true>();
+        switch (bn) {
+            case 64: return pair_pick<64>(taps, epi);
+            case 128: return pair_pick<128>(taps, epi);
+            case 256: return pair_pick<256>(taps, epi);
+        }
+        return ConvLaunch();
+    }
     if (amode == ub::A_STEM) {
         switch (stem_cin) {
             case 1: return stem_inst<1>();
@@ -287,6 +315,8 @@ struct ConvDesc {
     int bn = 128, amode = ub::A_COL3;
     int wstat = 1;              // allow weight-stationary mode when it fits
     int pf_items = 0;           // L2 prefetch distance (activation ring items)
+    int n_out_max = 4;          // store staging slots for weight-stationary launches
+    int pair = 0;               // CTA pairs (cta_group::2) where an instantiation exists
     const void* stem_x = nullptr;   // A_STEM: network input, its format and channel count
     int stem_fmt = 0, stem_cin = 0;
     int* dbg = nullptr;
@@ -296,25 +326,32 @@ struct ConvDesc {
 // staging][barriers].  Weight-stationary when the layer has one column block and its whole
 // weight slab fits beside at least two activation stages.
 int plan_smem(ConvLaunch* cl, ub::ConvParams* p, int taps, int n_cs, int n_blocks, int bn, bool pool,
-              bool has_out, int allow_wstat, int patch_bytes) {
+              bool has_out, int allow_wstat, int patch_bytes, int n_out_max) {
     const int budget = ub::kSmemLimit - ub::kStaticSmem - 1024 /*alignment slack*/ - patch_bytes;
-    const int pool_b = pool ? 2 * ub::kPoolStage : 0;
-    const int slab = taps * n_cs * cl->b_stage;
+    const int slab = taps * n_cs * cl->b_tap;
+    const int per_out = ub::kOutStage + (pool ? ub::kPoolStage : 0);   // one staging slot (+ its pool slot)
     int n_out = has_out ? 2 : 0, na = 0, nb = 0, wstat = 0;
     if (allow_wstat && n_blocks == 1) {
-        for (int no = n_out; no >= (has_out ? 1 : 0) && !wstat; --no) {
-            const int rest = budget - ub::kBarBytes - pool_b - no * ub::kOutStage - slab;
-            if (rest >= 2 * cl->a_stage) {
-                wstat = 1;
-                n_out = no;
-                nb = taps * n_cs;
-                na = rest / cl->a_stage;
+        // resident weights: as many store staging slots as fit beside >= 3 (else >= 2) activation stages;
+        // TMA stores of the thin-K layers drain slowly, deep staging keeps the epilogue warps busy
+        const int lo = has_out ? 1 : 0, hi = has_out ? n_out_max : 0;
+        for (int want_na = 3; want_na >= 2 && !wstat; --want_na) {
+            for (int no = hi; no >= lo && !wstat; --no) {
+                const int rest = budget - ub::kBarBytes - no * per_out - slab;
+                if (rest >= want_na * cl->a_stage) {
+                    wstat = 1;
+                    n_out = no;
+                    nb = taps * n_cs;        // (in units of one tap's tile)
+                    na = rest / cl->a_stage;
+                }
             }
         }
     }
     if (!wstat) {
-        nb = bn == 256 ? 3 : (bn == 128 ? 5 : 8);
-        const int rest = budget - ub::kBarBytes - pool_b - n_out * ub::kOutStage - nb * cl->b_stage;
+        // weight ring: ~96 / 80 / 64 KB for BN = 256 / 128 / 64 (a CTA pair stages half rows -> twice the depth)
+        nb = (bn == 256 ? 3 * 32768 : (bn == 128 ? 5 * 16384 : 8 * 8192)) / cl->b_stage;
+        if (nb > ub::kMaxRing) nb = ub::kMaxRing;
+        const int rest = budget - ub::kBarBytes - n_out * per_out - nb * cl->b_stage;
         na = rest / cl->a_stage;
     }
     if (na > ub::kMaxRing) na = ub::kMaxRing;
@@ -325,9 +362,9 @@ int plan_smem(ConvLaunch* cl, ub::ConvParams* p, int taps, int n_cs, int n_block
     p->wstat = wstat;
     p->n_out = n_out ? n_out : 1;
     p->off_b = na * cl->a_stage;
-    p->off_out = p->off_b + nb * cl->b_stage;
+    p->off_out = p->off_b + (wstat ? slab : nb * cl->b_stage);
     p->off_pool = p->off_out + n_out * ub::kOutStage;
-    p->off_bar = p->off_pool + pool_b;
+    p->off_bar = p->off_pool + (pool ? n_out * ub::kPoolStage : 0);
     p->off_patch = p->off_bar + ub::kBarBytes;
     cl->smem = p->off_patch + patch_bytes + 1024;
     return 0;
@@ -350,7 +387,7 @@ int build_conv_step(const ConvDesc& d, int num_sms, Step* st) {
     if (d.epi == ub::EPI_HEAD && d.cout != 64)
         return fail(UNETB200_EINVAL, "fused head needs cout == 64");
     st->kind = 1;
-    st->conv = pick_conv(d.taps, bn, d.amode, d.epi, d.stem_cin, d.ncls);
+    st->conv = pick_conv(d.taps, bn, d.amode, d.epi, d.stem_cin, d.ncls, d.pair != 0);
     if (!st->conv.fn) return fail(UNETB200_EINVAL, "conv: no kernel for this configuration");
     ub::ConvParams& p = st->cp;
     memset(&p, 0, sizeof p);
@@ -375,7 +412,8 @@ int build_conv_step(const ConvDesc& d, int num_sms, Step* st) {
         }
     }
     const int cin = d.c0 + d.c1;
-    if ((rc = make_w_map(&p.tmB, d.w, cin, cols, d.taps == 9 ? 9 : 1, bn))) return rc;
+    if ((rc = make_w_map(&p.tmB, d.w, cin, cols, d.taps == 9 ? 9 : 1, st->conv.pair ? bn / 2 : bn, st->conv.tpb)))
+        return rc;
     if (d.epi == ub::EPI_UPSAMPLE) {
         const int ho = 2 * d.h, wo = 2 * d.wd;
         for (int tap = 0; tap < 4; ++tap) {
@@ -418,10 +456,17 @@ int build_conv_step(const ConvDesc& d, int num_sms, Step* st) {
     p.pf_items = d.pf_items;
     if ((rc = plan_smem(&st->conv, &p, d.taps == 9 ? 9 : 1, cin / 64, p.n_blocks, bn,
                         d.epi == ub::EPI_STORE_POOL, d.epi != ub::EPI_HEAD, stem ? 1 : d.wstat,
-                        stem ? 2 * d.stem_cin * 180 * 4 : 0)))
+                        stem ? 4 * d.stem_cin * 180 * 4 : 0, d.n_out_max)))
         return rc;
-    st->grid = dim3(static_cast<unsigned>(total < num_sms ? total : num_sms));
-    st->block = dim3(stem ? 384 : 256);
+    if (st->conv.pair) {
+        const long long m_tiles = 1LL * p.tiles_x * p.tiles_y * d.n;
+        const long long units = (m_tiles + 1) / 2 * p.n_blocks;
+        const long long pairs = units < num_sms / 2 ? units : num_sms / 2;
+        st->grid = dim3(static_cast<unsigned>(2 * pairs));
+    } else {
+        st->grid = dim3(static_cast<unsigned>(total < num_sms ? total : num_sms));
+    }
+    st->block = dim3(stem ? 512 : 256);
     return 0;
 }
 
@@ -441,7 +486,24 @@ int launch_step(Step& st, cudaStream_t stream) {
                 configured[reinterpret_cast<const void*>(st.conv.fn)] |= (1 << dev);
             }
         }
-        st.conv.fn<<<st.grid, st.block, st.conv.smem, stream>>>(st.cp);
+        if (st.conv.pair) {
+            cudaLaunchConfig_t cfg;
+            memset(&cfg, 0, sizeof cfg);
+            cfg.gridDim = st.grid;
+            cfg.blockDim = st.block;
+            cfg.dynamicSmemBytes = st.conv.smem;
+            cfg.stream = stream;
+            cudaLaunchAttribute attr;
+            attr.id = cudaLaunchAttributeClusterDimension;
+            attr.val.clusterDim.x = 2;
+            attr.val.clusterDim.y = 1;
+            attr.val.clusterDim.z = 1;
+            cfg.attrs = &attr;
+            cfg.numAttrs = 1;
+            UB_CUDA(cudaLaunchKernelEx(&cfg, st.conv.fn, st.cp));
+        } else {
+            st.conv.fn<<<st.grid, st.block, st.conv.smem, stream>>>(st.cp);
+        }
     } else {
         switch (st.stem_cin) {
             case 1: ub::stem_conv_kernel<1><<<st.grid, st.block, 0, stream>>>(st.sp); break;
@@ -526,6 +588,8 @@ struct unetb200_handle_s {
     int wstat = 1;
     int stem_tc = 1;            // first conv on the tensor cores (n_channels <= 3)
     int pf_items = 0;           // L2 prefetch distance of the activation producer, in ring items (measured: no gain)
+    int n_out_max = 4;          // store staging slots for weight-stationary launches
+    int pair = 2;               // CTA pairs (cta_group::2): 0 = never, 1 = wherever instantiated, 2 = where measured faster
     int profile = 0;
     int* dbg = nullptr;         // pinned, device-visible watchdog record
     std::map<PlanKey, Plan> plans;
@@ -581,7 +645,9 @@ int build_plan(unetb200_handle_t h, const void* x, int x_fmt, int n, int H, int 
         d.n = n; d.h = H >> lvl; d.wd = W >> lvl; d.cout = h->layers[li].cout;
         d.relu = 1; d.taps = 9; d.epi = pool ? ub::EPI_STORE_POOL : ub::EPI_STORE;
         d.out = out; d.pool = pool;
-        d.bn = h->bn_max; d.amode = h->amode; d.wstat = h->wstat; d.pf_items = h->pf_items; d.dbg = h->dbg;
+        d.bn = h->bn_max; d.amode = h->amode; d.wstat = h->wstat; d.pf_items = h->pf_items; d.n_out_max = h->n_out_max; d.dbg = h->dbg;
+        // measured on B200 (profiles/): pairs win for column blocks >= 128, lose for the thin-K Cout = 64 layers
+        d.pair = h->pair == 1 || (h->pair == 2 && d.cout >= 128 && h->bn_max >= 128);
         Step st;
         if ((rc = build_conv_step(d, h->num_sms, &st))) return rc;
         st.layer = li;
@@ -594,7 +660,7 @@ int build_plan(unetb200_handle_t h, const void* x, int x_fmt, int n, int H, int 
         d.w = Wp(li); d.bias = Bp(li);
         d.n = n; d.h = H >> lvl; d.wd = W >> lvl; d.cout = h->layers[li].cout;
         d.relu = 0; d.taps = 1; d.epi = ub::EPI_UPSAMPLE; d.out = out;
-        d.bn = h->bn_max; d.amode = ub::A_TAP; d.wstat = h->wstat; d.pf_items = h->pf_items; d.dbg = h->dbg;
+        d.bn = h->bn_max; d.amode = ub::A_TAP; d.wstat = h->wstat; d.pf_items = h->pf_items; d.n_out_max = h->n_out_max; d.pair = h->pair == 1; d.dbg = h->dbg;
         Step st;
         if ((rc = build_conv_step(d, h->num_sms, &st))) return rc;
         st.layer = li;
@@ -643,7 +709,7 @@ int build_plan(unetb200_handle_t h, const void* x, int x_fmt, int n, int H, int 
             d.n = n; d.h = H; d.wd = W; d.cout = bw; d.relu = 1; d.taps = 9; d.epi = ub::EPI_HEAD;
             d.head_w = reinterpret_cast<const float*>(Wp(22)); d.head_b = Bp(22);
             d.ncls = h->arch.n_classes; d.logits = logits; d.mask = mask;
-            d.bn = 64; d.amode = h->amode; d.wstat = h->wstat; d.pf_items = h->pf_items; d.dbg = h->dbg;
+            d.bn = 64; d.amode = h->amode; d.wstat = h->wstat; d.pf_items = h->pf_items; d.n_out_max = h->n_out_max; d.pair = h->pair == 1; d.dbg = h->dbg;
             Step st;
             if ((rc = build_conv_step(d, h->num_sms, &st))) return rc;
             st.layer = 21;
@@ -765,6 +831,10 @@ int unetb200_create(const unetb200_arch_t* arch, const void* blob_dev, uint64_t 
     if (env) h->bn_max = atoi(env);
     env = getenv("UNETB200_WSTAT");
     if (env) h->wstat = atoi(env) ? 1 : 0;
+    env = getenv("UNETB200_PAIR");
+    if (env) h->pair = atoi(env);
+    env = getenv("UNETB200_N_OUT_MAX");
+    if (env) h->n_out_max = atoi(env);
     env = getenv("UNETB200_PF_ITEMS");
     if (env) h->pf_items = atoi(env);
     env = getenv("UNETB200_STEM_TC");
@@ -795,6 +865,12 @@ int unetb200_set_option(unetb200_handle_t h, const char* key, int value) {
         h->wstat = value ? 1 : 0;
     } else if (k == "stem_tc") {
         h->stem_tc = value ? 1 : 0;
+    } else if (k == "pair") {
+        if (value < 0 || value > 2) return fail(UNETB200_EINVAL, "pair must be 0, 1 or 2");
+        h->pair = value;
+    } else if (k == "n_out_max") {
+        if (value < 1 || value > 4) return fail(UNETB200_EINVAL, "n_out_max must be in 1..4");
+        h->n_out_max = value;
     } else if (k == "pf_items") {
         if (value < 0 || value > 64) return fail(UNETB200_EINVAL, "pf_items must be in 0..64");
         h->pf_items = value;
@@ -815,6 +891,8 @@ int unetb200_get_option(unetb200_handle_t h, const char* key, int* value) {
     else if (k == "wstat") *value = h->wstat;
     else if (k == "stem_tc") *value = h->stem_tc;
     else if (k == "pf_items") *value = h->pf_items;
+    else if (k == "n_out_max") *value = h->n_out_max;
+    else if (k == "pair") *value = h->pair;
     else if (k == "profile") *value = h->profile;
     else if (k == "num_sms") *value = h->num_sms;
     else return fail(UNETB200_EINVAL, "unknown option " + k);
@@ -925,7 +1003,7 @@ int unetb200_conv3x3(const void* src0, int c0, const void* src1, int c1, const v
     d.src0 = src0; d.c0 = c0; d.src1 = src1; d.c1 = src1 ? c1 : 0;
     d.w = w_packed; d.bias = bias; d.n = n; d.h = height; d.wd = width; d.cout = cout; d.relu = relu;
     d.taps = 9; d.epi = pool_out ? ub::EPI_STORE_POOL : ub::EPI_STORE; d.out = out; d.pool = pool_out;
-    d.bn = bn; d.amode = amode; d.wstat = wstat; d.dbg = g_hook_dbg();
+    d.bn = bn; d.amode = amode; d.wstat = wstat & 1; d.pair = (wstat >> 1) & 1; d.dbg = g_hook_dbg();
     int sms = 0;
     if ((rc = device_num_sms(&sms))) return rc;
     Step st;
@@ -946,7 +1024,7 @@ int unetb200_conv3x3_head(const void* src0, int c0, const void* w_packed, const 
     d.src0 = src0; d.c0 = c0; d.w = w_packed; d.bias = bias; d.n = n; d.h = height; d.wd = width;
     d.cout = 64; d.relu = 1; d.taps = 9; d.epi = ub::EPI_HEAD; d.head_w = head_w; d.head_b = head_b;
     d.ncls = n_classes; d.logits = logits; d.mask = mask; d.bn = 64; d.amode = amode;
-    d.wstat = wstat; d.dbg = g_hook_dbg();
+    d.wstat = wstat & 1; d.pair = (wstat >> 1) & 1; d.dbg = g_hook_dbg();
     int sms = 0;
     if ((rc = device_num_sms(&sms))) return rc;
     Step st;
@@ -962,7 +1040,8 @@ int unetb200_convt2x2(const void* src, int cin, const void* w_packed, const floa
     if (!src || !w_packed || !bias || !out) return fail(UNETB200_EINVAL, "NULL pointer");
     ConvDesc d;
     d.src0 = src; d.c0 = cin; d.w = w_packed; d.bias = bias; d.n = n; d.h = height; d.wd = width;
-    d.cout = cout; d.relu = 0; d.taps = 1; d.epi = ub::EPI_UPSAMPLE; d.out = out; d.bn = bn;
+    d.cout = cout; d.relu = 0; d.taps = 1; d.epi = ub::EPI_UPSAMPLE; d.out = out; d.bn = bn & 0xfff;
+    d.pair = (bn >> 12) & 1;     // bit 12 of `bn` selects the CTA-pair variant
     d.amode = ub::A_TAP; d.dbg = g_hook_dbg();
     int sms = 0;
     if ((rc = device_num_sms(&sms))) return rc;
