@@ -148,6 +148,7 @@ def main():
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--layers-out", default=None, help="write the per-layer table (JSON) here")
+    ap.add_argument("--graph", type=int, default=0, help="1: replay the step as a CUDA graph")
     ap.add_argument("--e2e-chunk", type=int, default=64,
                     help="images per forward inside the end-to-end call (copies of chunk i+1 overlap chunk i)")
     args = ap.parse_args()
@@ -174,7 +175,7 @@ def main():
     torch.cuda.set_device(dev)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep NCCL's banner off stdout (one JSON line)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's version banner must not land on stdout
         dist.init_process_group("nccl", device_id=dev)
 
     B, S = args.batch, args.size
@@ -217,6 +218,19 @@ def main():
     # ---------------- device-resident throughput (`value`)
     for _ in range(args.warmup):
         step()
+    if args.graph:
+        torch.cuda.synchronize(dev)
+        g = torch.cuda.CUDAGraph()
+        cap = torch.cuda.Stream(dev)
+        with torch.cuda.stream(cap):
+            step()
+            torch.cuda.synchronize(dev)
+            with torch.cuda.graph(g, stream=cap):
+                step()
+        eager_step = step
+        step = g.replay
+        for _ in range(args.warmup):
+            step()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -227,6 +241,8 @@ def main():
     value = world * B / (ms_per_step / 1e3)
 
     # ---------------- per-layer pass for the roofline (same K steps, events between launches)
+    if args.graph:
+        step = eager_step
     eng.set_option("profile", 1)
     step()
     acc = None
