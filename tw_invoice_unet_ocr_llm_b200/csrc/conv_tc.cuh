@@ -189,6 +189,10 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(
         smem_gen + (s_tmem_ptr - smem_base));
+    // Programmatic dependent launch: the next layer's CTAs may start as soon as SMs free up; they
+    // set up, prefetch their (constant) weights and then block in pdl_wait() -- executed by the roles
+    // that read the previous layer's output -- until this grid has completed.
+    pdl_launch_dependents();
 
     const int n_cs = (p.C0 + p.C1) >> 6;            // 64-channel slices along K
     const int tiles_per_img = p.tiles_x * p.tiles_y;
@@ -256,6 +260,7 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
             }
         };
         float regs[NL];
+        pdl_wait();
         const int stride = 2 * static_cast<int>(gridDim.x);
         int it = 0;                                              // this group's tile counter
         int t = static_cast<int>(blockIdx.x) + grp * static_cast<int>(gridDim.x);
@@ -344,6 +349,7 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
             };
             const CUtensorMap* tm;
             int ca, bx, by, n;
+            pdl_wait();
             const int pf = p.pf_items;
             for (int i = 0; i < pf && i < n_items; ++i) {
                 locate(i, tm, ca, bx, by, n);

@@ -287,6 +287,12 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
         ::"r"(bar), "h"(static_cast<uint16_t>(3)) : "memory");
 }
 
+// ------------------ programmatic dependent launch (PDL) ---------------------
+// wait: blocks until every prerequisite grid has completed and its memory is visible.
+// launch_dependents: lets the next grid in the stream start launching CTAs as SMs free up.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------- misc helpers ---------------------------------
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");

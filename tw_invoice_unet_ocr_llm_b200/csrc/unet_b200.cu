@@ -291,6 +291,7 @@ struct Step {
     ub::ConvParams cp;
     ub::StemParams sp;
     int stem_cin = 0;
+    int pdl = 0;               // launch with programmatic stream serialization
     dim3 grid, block;
 };
 
@@ -486,24 +487,29 @@ int launch_step(Step& st, cudaStream_t stream) {
                 configured[reinterpret_cast<const void*>(st.conv.fn)] |= (1 << dev);
             }
         }
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof cfg);
+        cfg.gridDim = st.grid;
+        cfg.blockDim = st.block;
+        cfg.dynamicSmemBytes = st.conv.smem;
+        cfg.stream = stream;
+        cudaLaunchAttribute attrs[2];
+        int na = 0;
         if (st.conv.pair) {
-            cudaLaunchConfig_t cfg;
-            memset(&cfg, 0, sizeof cfg);
-            cfg.gridDim = st.grid;
-            cfg.blockDim = st.block;
-            cfg.dynamicSmemBytes = st.conv.smem;
-            cfg.stream = stream;
-            cudaLaunchAttribute attr;
-            attr.id = cudaLaunchAttributeClusterDimension;
-            attr.val.clusterDim.x = 2;
-            attr.val.clusterDim.y = 1;
-            attr.val.clusterDim.z = 1;
-            cfg.attrs = &attr;
-            cfg.numAttrs = 1;
-            UB_CUDA(cudaLaunchKernelEx(&cfg, st.conv.fn, st.cp));
-        } else {
-            st.conv.fn<<<st.grid, st.block, st.conv.smem, stream>>>(st.cp);
+            attrs[na].id = cudaLaunchAttributeClusterDimension;
+            attrs[na].val.clusterDim.x = 2;
+            attrs[na].val.clusterDim.y = 1;
+            attrs[na].val.clusterDim.z = 1;
+            ++na;
         }
+        if (st.pdl) {
+            attrs[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attrs[na].val.programmaticStreamSerializationAllowed = 1;
+            ++na;
+        }
+        cfg.attrs = attrs;
+        cfg.numAttrs = na;
+        UB_CUDA(cudaLaunchKernelEx(&cfg, st.conv.fn, st.cp));
     } else {
         switch (st.stem_cin) {
             case 1: ub::stem_conv_kernel<1><<<st.grid, st.block, 0, stream>>>(st.sp); break;
@@ -590,6 +596,7 @@ struct unetb200_handle_s {
     int pf_items = 0;           // L2 prefetch distance of the activation producer, in ring items (measured: no gain)
     int n_out_max = 4;          // store staging slots for weight-stationary launches
     int pair = 2;               // CTA pairs (cta_group::2): 0 = never, 1 = wherever instantiated, 2 = where measured faster
+    int pdl = 1;                // programmatic dependent launch between the layers of one forward
     int profile = 0;
     int* dbg = nullptr;         // pinned, device-visible watchdog record
     std::map<PlanKey, Plan> plans;
@@ -831,6 +838,8 @@ int unetb200_create(const unetb200_arch_t* arch, const void* blob_dev, uint64_t 
     if (env) h->bn_max = atoi(env);
     env = getenv("UNETB200_WSTAT");
     if (env) h->wstat = atoi(env) ? 1 : 0;
+    env = getenv("UNETB200_PDL");
+    if (env) h->pdl = atoi(env) ? 1 : 0;
     env = getenv("UNETB200_PAIR");
     if (env) h->pair = atoi(env);
     env = getenv("UNETB200_N_OUT_MAX");
@@ -865,6 +874,8 @@ int unetb200_set_option(unetb200_handle_t h, const char* key, int value) {
         h->wstat = value ? 1 : 0;
     } else if (k == "stem_tc") {
         h->stem_tc = value ? 1 : 0;
+    } else if (k == "pdl") {
+        h->pdl = value ? 1 : 0;
     } else if (k == "pair") {
         if (value < 0 || value > 2) return fail(UNETB200_EINVAL, "pair must be 0, 1 or 2");
         h->pair = value;
@@ -893,6 +904,7 @@ int unetb200_get_option(unetb200_handle_t h, const char* key, int* value) {
     else if (k == "pf_items") *value = h->pf_items;
     else if (k == "n_out_max") *value = h->n_out_max;
     else if (k == "pair") *value = h->pair;
+    else if (k == "pdl") *value = h->pdl;
     else if (k == "profile") *value = h->profile;
     else if (k == "num_sms") *value = h->num_sms;
     else return fail(UNETB200_EINVAL, "unknown option " + k);
@@ -951,6 +963,8 @@ int unetb200_forward(unetb200_handle_t h, const void* x, int x_fmt, int n, int h
     }
     int launches = 0;
     for (size_t i = 0; i < plan.steps.size(); ++i) {
+        // the first launch of a forward keeps normal stream order (its predecessor is foreign work)
+        plan.steps[i].pdl = (h->pdl && !prof && i > 0 && plan.steps[i].kind == 1) ? 1 : 0;
         int rc = launch_step(plan.steps[i], s);
         if (rc) return rc;
         ++launches;
