@@ -425,7 +425,9 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
         // 32-64 cycles, so the issue path itself is kept to a couple of integer ops per MMA:
         // descriptor high words are constants, low words are (base + constant) in 16-byte
         // units, and mbarrier probes for the next stage are issued ahead of the MMAs.
-        if (lane == 0 && rank == 0) {
+        // The whole warp walks the loops converged (uniform addresses live in uniform registers);
+        // one elected lane issues the MMAs and commits.
+        if (rank == 0) {
             constexpr uint32_t idesc = umma_idesc_bf16(BN, PAIR ? 256 : 128);
             constexpr uint32_t a_sbo = (TAPS == 9 && AMODE == A_HALO) ? 10 * 128 : 1024;
             constexpr uint32_t a_hi = umma_desc_hi_sw128(a_sbo);
@@ -448,64 +450,72 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
                         mbar_wait(bar_a_full + 8 * sa, pa, 5, p.dbg);
                         tc_fence_after();
                         const uint32_t a_lo0 = umma_desc_lo(sA + sa * Cfg::A_STAGE);
+                        const bool last_item = (cs == n_cs - 1) && (item == ITEMS - 1);
+                        auto mma = [&](uint32_t a_lo, uint32_t b_lo, uint32_t acc_flag) {
+                            if (PAIR) umma_bf16_pair(d_tmem, umma_desc(a_lo, a_hi), umma_desc(b_lo, b_hi), idesc, acc_flag);
+                            else umma_bf16(d_tmem, umma_desc(a_lo, a_hi), umma_desc(b_lo, b_hi), idesc, acc_flag);
+                        };
+                        auto commit = [&](uint32_t bar) {
+                            if (PAIR) umma_commit_pair(bar); else umma_commit(bar);
+                        };
+                        // activation view of tap tt inside the staged item, in 16-byte units
+                        auto a_view = [&](int tt) -> uint32_t {
+                            return TAPS == 1 ? 0u
+                                 : (AMODE == A_COL3 ? static_cast<uint32_t>(tt) * (1024 >> 4)
+                                 : (AMODE == A_HALO ? static_cast<uint32_t>((tt / 3) * 10 + (tt % 3)) * (128 >> 4) : 0u));
+                        };
                         if (p.wstat) {
-                            // resident weights: slot = cs * TAPS + tap, no barrier traffic
+                            // resident weights (slot = cs * TAPS + tap): every MMA of the item back to back
                             const uint32_t b_cs = b_lo0 + (cs * TAPS) * (Cfg::B_TAP >> 4);
+                            if (elect_one()) {
 #pragma unroll
-                            for (int tt = 0; tt < TPA; ++tt) {
-                                const int tap_c = TAPS == 1 ? 0 : (AMODE == A_COL3 ? tt * 3 : tt);
-                                const uint32_t tap_r = (TAPS == 9 && AMODE != A_HALO) ? item * (AMODE == A_COL3 ? 1 : TPA) : 0;
-                                const uint32_t a_off = TAPS == 1 ? 0
-                                                     : (AMODE == A_COL3 ? tt * (1024 >> 4)
-                                                     : (AMODE == A_HALO ? ((tt / 3) * 10 + (tt % 3)) * (128 >> 4) : 0));
-                                const uint32_t b_lo = b_cs + (tap_c + tap_r) * (Cfg::B_TAP >> 4);
+                                for (int tt = 0; tt < TPA; ++tt) {
+                                    const int tap_c = TAPS == 1 ? 0 : (AMODE == A_COL3 ? tt * 3 : tt);
+                                    const uint32_t tap_r = (TAPS == 9 && AMODE != A_HALO) ? item * (AMODE == A_COL3 ? 1 : TPA) : 0;
+                                    const uint32_t b_lo = b_cs + (tap_c + tap_r) * (Cfg::B_TAP >> 4);
 #pragma unroll
-                                for (int k = 0; k < 4; ++k) {
-                                    if (AMODE == A_STEM && cs == 1 && k >= 2) break;   // slice 1 holds 32 taps only
-                                    if (PAIR) umma_bf16_pair(d_tmem, umma_desc(a_lo0 + a_off + 2 * k, a_hi),
-                                                             umma_desc(b_lo + 2 * k, b_hi), idesc, accumulate);
-                                    else umma_bf16(d_tmem, umma_desc(a_lo0 + a_off + 2 * k, a_hi),
-                                                   umma_desc(b_lo + 2 * k, b_hi), idesc, accumulate);
-                                    accumulate = 1;
+                                    for (int k = 0; k < 4; ++k) {
+                                        if (AMODE == A_STEM && cs == 1 && k >= 2) break;   // slice 1 holds 32 taps only
+                                        mma(a_lo0 + a_view(tt) + 2 * k, b_lo + 2 * k, (tt | k) ? 1u : accumulate);
+                                    }
                                 }
+                                commit(bar_a_empty + 8 * sa);
+                                if (last_item) commit(bar_t_full + 8 * acc);
                             }
+                            accumulate = 1;
                         } else {
                             constexpr int TPB = Cfg::TPB;
                             bool ready = mbar_try_wait(bar_b_full + 8 * sb, pb);
-                            uint32_t cur = sb, b_stage_lo = 0;
 #pragma unroll
-                            for (int tt = 0; tt < TPA; ++tt) {
-                                if (tt % TPB == 0) {
-                                    if (!ready) mbar_wait(bar_b_full + 8 * sb, pb, 6, p.dbg);
-                                    tc_fence_after();
-                                    b_stage_lo = b_lo0 + sb * (Cfg::B_STAGE >> 4);
-                                    cur = sb;
-                                    if (++sb == static_cast<uint32_t>(p.nb)) { sb = 0; pb ^= 1; }
-                                    // probe the next weight stage now; the answer is needed after these MMAs
-                                    ready = mbar_try_wait(bar_b_full + 8 * sb, pb);
-                                }
-                                const uint32_t b_lo = b_stage_lo + (tt % TPB) * (Cfg::B_TAP >> 4);
-                                const uint32_t a_off = TAPS == 1 ? 0
-                                                     : (AMODE == A_COL3 ? tt * (1024 >> 4)
-                                                     : (AMODE == A_HALO ? ((tt / 3) * 10 + (tt % 3)) * (128 >> 4) : 0));
+                            for (int st = 0; st < TPA / TPB; ++st) {
+                                if (!ready) mbar_wait(bar_b_full + 8 * sb, pb, 6, p.dbg);
+                                tc_fence_after();
+                                const uint32_t b_stage_lo = b_lo0 + sb * (Cfg::B_STAGE >> 4);
+                                const uint32_t cur = sb;
+                                if (++sb == static_cast<uint32_t>(p.nb)) { sb = 0; pb ^= 1; }
+                                // probe the next weight stage now; the answer is needed after these MMAs
+                                ready = mbar_try_wait(bar_b_full + 8 * sb, pb);
+                                if (elect_one()) {
 #pragma unroll
-                                for (int k = 0; k < 4; ++k) {
-                                    if (PAIR) umma_bf16_pair(d_tmem, umma_desc(a_lo0 + a_off + 2 * k, a_hi),
-                                                             umma_desc(b_lo + 2 * k, b_hi), idesc, accumulate);
-                                    else umma_bf16(d_tmem, umma_desc(a_lo0 + a_off + 2 * k, a_hi),
-                                                   umma_desc(b_lo + 2 * k, b_hi), idesc, accumulate);
-                                    accumulate = 1;
+                                    for (int j = 0; j < TPB; ++j) {
+                                        const int tt = st * TPB + j;
+#pragma unroll
+                                        for (int k = 0; k < 4; ++k)
+                                            mma(a_lo0 + a_view(tt) + 2 * k, b_stage_lo + j * (Cfg::B_TAP >> 4) + 2 * k,
+                                                (j | k) ? 1u : accumulate);
+                                    }
+                                    commit(bar_b_empty + 8 * cur);
+                                    if (st == TPA / TPB - 1) {
+                                        commit(bar_a_empty + 8 * sa);
+                                        if (last_item) commit(bar_t_full + 8 * acc);
+                                    }
                                 }
-                                if (tt % TPB == TPB - 1) {
-                                    if (PAIR) umma_commit_pair(bar_b_empty + 8 * cur); else umma_commit(bar_b_empty + 8 * cur);
-                                }
+                                accumulate = 1;
                             }
                         }
-                        if (PAIR) umma_commit_pair(bar_a_empty + 8 * sa); else umma_commit(bar_a_empty + 8 * sa);
                         if (++sa == static_cast<uint32_t>(p.na)) { sa = 0; pa ^= 1; }
                     }
                 }
-                if (PAIR) umma_commit_pair(bar_t_full + 8 * acc); else umma_commit(bar_t_full + 8 * acc);
             }
         }
     } else if (warp >= 4) {
