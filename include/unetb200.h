@@ -90,7 +90,7 @@ int unetb200_create(const unetb200_arch_t* arch, const void* blob_dev, uint64_t 
 int unetb200_destroy(unetb200_handle_t h);
 
 /* options: "amode" (UNETB200_A_*), "bn_max" (64/128/256), "wstat" (0/1), "stem_tc" (0/1), "pair" (0 never / 1 everywhere / 2 auto),
- * "pdl" (0/1 programmatic dependent launch), "n_out_max" (1..4), "pf_items" (0..64), "profile" (0/1) */
+ * "pdl" (0/1 programmatic dependent launch), "epi2" (two epilogue groups: 0 never / 1 weight-stationary launches / 2 always), "pf_items" (0..64), "profile" (0/1) */
 int unetb200_set_option(unetb200_handle_t h, const char* key, int value);
 int unetb200_get_option(unetb200_handle_t h, const char* key, int* value);
 

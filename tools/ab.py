@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--rounds", type=int, default=6)
+    ap.add_argument("--layers", action="store_true", help="also print per-layer times (profiled pass)")
     a = ap.parse_args()
     key, vals = a.spec.split("=")
     vals = [int(v) for v in vals.split(",")]
@@ -54,6 +55,22 @@ def main():
             torch.cuda.synchronize()
             if rnd > 0:
                 res[v].append(e0.elapsed_time(e1) / a.steps)
+    if a.layers:
+        per = {}
+        for v in vals:
+            eng.set_option(key, v)
+            eng.set_option("profile", 1)
+            acc = None
+            for _ in range(4):
+                eng.run(x, thresholds=thr, logits_out=logits, mask_out=mask)
+                t = eng.layer_times_ms()
+                acc = t if acc is None else [p + q for p, q in zip(acc, t)]
+            eng.set_option("profile", 0)
+            per[v] = [q / 4 for q in acc]
+        print("layer".ljust(20) + "".join(f"{key}={v}".rjust(12) for v in vals))
+        for i, l in enumerate(eng.layers[:-1]):
+            print(l.name.decode().ljust(20) + "".join(f"{per[v][i]:12.3f}" for v in vals))
+        print("sum".ljust(20) + "".join(f"{sum(per[v]):12.3f}" for v in vals))
     for v in vals:
         t = res[v]
         print(f"{key}={v}: median {statistics.median(t):.3f} ms  min {min(t):.3f}  max {max(t):.3f}  "

@@ -35,10 +35,12 @@
 //             fp32-class accuracy from bf16 MMAs.  The layer is HBM-bound (it writes 64 bf16
 //             channels per pixel), the extra MMAs are free.
 //
-// Warp roles (256 threads, 1 CTA / SM, persistent over tiles):
-//   warp 0 : TMA producer, activations      warp 1 : MMA issuer (one lane)
+// Warp roles (384 threads, 1 CTA / SM, persistent over tiles):
+//   warp 0 : TMA producer, activations      warp 1 : MMA issuer (one elected lane)
 //   warp 2 : TMEM allocator                 warp 3 : TMA producer, weights
-//   warps 4-7 : epilogue (TMEM -> regs -> smem -> TMA store)
+//   warps 4-7, 8-11 : two epilogue groups (TMEM -> regs -> smem -> TMA store) taking alternate
+//                     tiles, so one tile's TMEM-load / convert / store latency chain overlaps the next's
+//   warps 12-19 (stem only) : two im2col producer groups
 // Activations and weights have separate producers and separate mbarrier rings, so the
 // activation prefetch distance (HBM latency) does not depend on the weight ring depth.
 // Weight-stationary mode (`wstat`): when the whole [taps x Cin x BN] weight slab of the
@@ -88,7 +90,8 @@ struct ConvParams {
     int ncls;
     int na, nb;              // ring depths: activation items / weight tiles (wstat: nb = all tiles)
     int wstat;               // 1 = weight-stationary (see header)
-    int n_out;               // output (and pool) staging buffers, 1..4
+    int n_out;               // output (and pool) staging slots PER EPILOGUE GROUP (1 or 2)
+    int n_epi;               // active epilogue groups: 2 = alternate tiles, 1 = group 0 takes every tile
     int pf_items;            // activation items prefetched into L2 ahead of the smem ring (0 = off)
     int off_b, off_out, off_pool, off_bar;   // smem carve-up, bytes from the 1024-aligned base
     int off_patch;           // A_STEM: 2 x [Cin][18][10] fp32 input halo patches
@@ -119,7 +122,7 @@ constexpr int kSmemLimit = 232448;    // 227 KB per CTA on sm_100
 
 // X: A_STEM -> n_channels of the network input; EPI_HEAD -> n_classes (0 = generic, up to 8).
 template <int BN, int TAPS, int AMODE, int EPI, int X = 0, bool PAIR = false>
-__global__ void __launch_bounds__(AMODE == A_STEM ? 512 : 256, 1)
+__global__ void __launch_bounds__(AMODE == A_STEM ? 640 : 384, 1)
 conv_tc_kernel(const __grid_constant__ ConvParams p) {
     constexpr int CIN = X;
     static_assert(!(PAIR && AMODE == A_STEM), "the stem runs unpaired");
@@ -214,7 +217,7 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
         return valid;
     };
 
-    if (AMODE == A_STEM && warp >= 8) {
+    if (AMODE == A_STEM && warp >= 12) {
         // ================== im2col producer (first conv only) =================
         // thread r builds A row r = output pixel (y0 + r/8, x0 + r%8) of the tile:
         //   slice 0 (ring item 0): k in [0,32) = bf16 hi of the 9*CIN taps, [32,64) = bf16 lo
@@ -223,8 +226,8 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
         constexpr int KS = 9 * CI;
         constexpr int PE = CI * 180;                             // patch elements: [CIN][18][10]
         constexpr int NL = (PE + 127) / 128;
-        const int grp = (threadIdx.x - 256) >> 7;                // producer group: takes tiles it % 2 == grp
-        const int r = (threadIdx.x - 256) & 127;
+        const int grp = (threadIdx.x - 384) >> 7;                // producer group: takes tiles it % 2 == grp
+        const int r = (threadIdx.x - 384) & 127;
         float* s_patch = reinterpret_cast<float*>(smem_gen + p.off_patch) + grp * 2 * PE;
         const int hh = r >> 3, ww = r & 7;
         auto fetch = [&](int t, float (&regs)[NL]) {
@@ -268,7 +271,7 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
             fetch(t, regs);
             publish(0, regs);
         }
-        named_bar_sync(3 + grp, 128);
+        named_bar_sync(9 + grp, 128);
         for (; t < p.total_tiles; t += stride, ++it) {
             const int tn = t + stride;
             if (tn < p.total_tiles) fetch(tn, regs);             // global loads in flight during the build
@@ -320,7 +323,7 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
                 mbar_arrive(bar_a_full + 8 * sa);
             }
             if (tn < p.total_tiles) publish((it + 1) & 1, regs);
-            named_bar_sync(3 + grp, 128);
+            named_bar_sync(9 + grp, 128);
         }
     } else if (warp == 0) {
         // ===================== TMA producer: activations ======================
@@ -518,18 +521,22 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
                 }
             }
         }
-    } else if (warp >= 4) {
+    } else if (warp >= 4 && warp < 12) {
         // ============================= epilogue ===============================
-        const int q = warp - 4;                 // TMEM lane quarter
+        const int eg = (warp - 4) >> 2;         // epilogue group: takes tiles tile_it % 2 == eg
+        const int q = warp & 3;                 // TMEM lane quarter this warp may access (warp id % 4)
         const int row = q * 32 + lane;          // pixel row of the tile: h = row/8, w = row%8
-        const int et = threadIdx.x - 128;       // 0..127
-        uint32_t tile_it = 0, chunk_it = 0;
+        const int et = (threadIdx.x - 128) & 127;   // 0..127 inside the group
+        const int bar0 = 1 + 4 * eg;            // named barriers of this group: bar0, bar0 + 1
+        const int estep = p.n_epi;              // tiles between two tiles of this group
+        uint32_t tile_it = eg, chunk_it = 0;
         // hand-back of an accumulator: arrive on the (leader's) barrier the MMA issuer waits on
         auto release_acc = [&](uint32_t acc) {
             if (PAIR) mbar_arrive_cluster(mapa_shared(bar_t_empty + 8 * acc, 0));
             else mbar_arrive(bar_t_empty + 8 * acc);
         };
-        for (int u = first_unit; u < n_units; u += unit_stride, ++tile_it) {
+        for (int u = eg < estep ? first_unit + eg * unit_stride : n_units; u < n_units;
+             u += estep * unit_stride, tile_it += estep) {
             int mt, nb;
             const bool valid = decode(u, mt, nb);
             const int n = mt / tiles_per_img;
@@ -598,19 +605,15 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
                 const int gcol = nb * BN + j * 64;            // global column of this 64-wide chunk
                 const int tapo = EPI == EPI_UPSAMPLE ? gcol / p.Cout : 0;
                 const int ch0 = EPI == EPI_UPSAMPLE ? gcol - tapo * p.Cout : gcol;
-                const uint32_t buf = chunk_it % static_cast<uint32_t>(p.n_out);
+                // each group owns n_out staging slots; a slot was last read by this group's store
+                // issued n_out chunks ago (bulk groups are per thread: et == 0 of the group)
+                const uint32_t buf = eg * p.n_out + chunk_it % static_cast<uint32_t>(p.n_out);
                 const uint32_t obuf = sOut + buf * kOutStage;
                 const uint32_t pbuf = sPool + buf * kPoolStage;
-                // the staging buffer was last read by the store issued n_out chunks ago
                 if (et == 0) {
-                    switch (p.n_out) {
-                        case 4: tma_store_wait_read<3>(); break;
-                        case 3: tma_store_wait_read<2>(); break;
-                        case 2: tma_store_wait_read<1>(); break;
-                        default: tma_store_wait_read<0>(); break;
-                    }
+                    if (p.n_out == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
                 }
-                named_bar_sync(1, 128);
+                named_bar_sync(bar0, 128);
                 uint32_t pk[32];
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
@@ -660,7 +663,7 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
                     }
                 }
                 fence_proxy_async_smem();
-                named_bar_sync(2, 128);
+                named_bar_sync(bar0 + 1, 128);
                 if (et == 0 && valid) {
                     if (EPI == EPI_UPSAMPLE)
                         tma_store_4d(&p.tmOut[tapo], obuf, ch0, x0, y0, n);

@@ -316,7 +316,7 @@ struct ConvDesc {
     int bn = 128, amode = ub::A_COL3;
     int wstat = 1;              // allow weight-stationary mode when it fits
     int pf_items = 0;           // L2 prefetch distance (activation ring items)
-    int n_out_max = 4;          // store staging slots for weight-stationary launches
+    int epi2 = 1;               // two epilogue groups: 0 never, 1 weight-stationary launches, 2 always
     int pair = 0;               // CTA pairs (cta_group::2) where an instantiation exists
     const void* stem_x = nullptr;   // A_STEM: network input, its format and channel count
     int stem_fmt = 0, stem_cin = 0;
@@ -327,23 +327,25 @@ struct ConvDesc {
 // staging][barriers].  Weight-stationary when the layer has one column block and its whole
 // weight slab fits beside at least two activation stages.
 int plan_smem(ConvLaunch* cl, ub::ConvParams* p, int taps, int n_cs, int n_blocks, int bn, bool pool,
-              bool has_out, int allow_wstat, int patch_bytes, int n_out_max) {
+              bool has_out, int allow_wstat, int patch_bytes, int epi2) {
     const int budget = ub::kSmemLimit - ub::kStaticSmem - 1024 /*alignment slack*/ - patch_bytes;
     const int slab = taps * n_cs * cl->b_tap;
-    const int per_out = ub::kOutStage + (pool ? ub::kPoolStage : 0);   // one staging slot (+ its pool slot)
-    int n_out = has_out ? 2 : 0, na = 0, nb = 0, wstat = 0;
+    // Epilogue groups: thin-K launches with resident weights are epilogue-bound -> two groups on
+    // alternate tiles, two staging slots each; everything else keeps one group with two slots.
+    const int slot = ub::kOutStage + (pool ? ub::kPoolStage : 0);
+    int n_out = has_out ? 2 : 0, n_epi = 1, na = 0, nb = 0, wstat = 0;
     if (allow_wstat && n_blocks == 1) {
-        // resident weights: as many store staging slots as fit beside >= 3 (else >= 2) activation stages;
-        // TMA stores of the thin-K layers drain slowly, deep staging keeps the epilogue warps busy
-        const int lo = has_out ? 1 : 0, hi = has_out ? n_out_max : 0;
         for (int want_na = 3; want_na >= 2 && !wstat; --want_na) {
-            for (int no = hi; no >= lo && !wstat; --no) {
-                const int rest = budget - ub::kBarBytes - no * per_out - slab;
-                if (rest >= want_na * cl->a_stage) {
-                    wstat = 1;
-                    n_out = no;
-                    nb = taps * n_cs;        // (in units of one tap's tile)
-                    na = rest / cl->a_stage;
+            for (int ne = (epi2 >= 1 ? 2 : 1); ne >= 1 && !wstat; --ne) {
+                for (int no = has_out ? 2 : 0; no >= (has_out ? 1 : 0) && !wstat; --no) {
+                    const int rest = budget - ub::kBarBytes - ne * no * slot - slab;
+                    if (rest >= want_na * cl->a_stage) {
+                        wstat = 1;
+                        n_out = no;
+                        n_epi = ne;
+                        nb = taps * n_cs;        // (in units of one tap's tile)
+                        na = rest / cl->a_stage;
+                    }
                 }
             }
         }
@@ -352,7 +354,9 @@ int plan_smem(ConvLaunch* cl, ub::ConvParams* p, int taps, int n_cs, int n_block
         // weight ring: ~96 / 80 / 64 KB for BN = 256 / 128 / 64 (a CTA pair stages half rows -> twice the depth)
         nb = (bn == 256 ? 3 * 32768 : (bn == 128 ? 5 * 16384 : 8 * 8192)) / cl->b_stage;
         if (nb > ub::kMaxRing) nb = ub::kMaxRing;
-        const int rest = budget - ub::kBarBytes - n_out * per_out - nb * cl->b_stage;
+        n_epi = epi2 >= 2 ? 2 : 1;
+        n_out = has_out ? (n_epi == 2 ? 1 : 2) : 0;
+        const int rest = budget - ub::kBarBytes - n_epi * n_out * slot - nb * cl->b_stage;
         na = rest / cl->a_stage;
     }
     if (na > ub::kMaxRing) na = ub::kMaxRing;
@@ -364,8 +368,9 @@ int plan_smem(ConvLaunch* cl, ub::ConvParams* p, int taps, int n_cs, int n_block
     p->n_out = n_out ? n_out : 1;
     p->off_b = na * cl->a_stage;
     p->off_out = p->off_b + (wstat ? slab : nb * cl->b_stage);
-    p->off_pool = p->off_out + n_out * ub::kOutStage;
-    p->off_bar = p->off_pool + (pool ? n_out * ub::kPoolStage : 0);
+    p->n_epi = n_epi;
+    p->off_pool = p->off_out + n_epi * n_out * ub::kOutStage;
+    p->off_bar = p->off_pool + (pool ? n_epi * n_out * ub::kPoolStage : 0);
     p->off_patch = p->off_bar + ub::kBarBytes;
     cl->smem = p->off_patch + patch_bytes + 1024;
     return 0;
@@ -457,7 +462,7 @@ int build_conv_step(const ConvDesc& d, int num_sms, Step* st) {
     p.pf_items = d.pf_items;
     if ((rc = plan_smem(&st->conv, &p, d.taps == 9 ? 9 : 1, cin / 64, p.n_blocks, bn,
                         d.epi == ub::EPI_STORE_POOL, d.epi != ub::EPI_HEAD, stem ? 1 : d.wstat,
-                        stem ? 4 * d.stem_cin * 180 * 4 : 0, d.n_out_max)))
+                        stem ? 4 * d.stem_cin * 180 * 4 : 0, d.epi2)))
         return rc;
     if (st->conv.pair) {
         const long long m_tiles = 1LL * p.tiles_x * p.tiles_y * d.n;
@@ -467,7 +472,7 @@ int build_conv_step(const ConvDesc& d, int num_sms, Step* st) {
     } else {
         st->grid = dim3(static_cast<unsigned>(total < num_sms ? total : num_sms));
     }
-    st->block = dim3(stem ? 512 : 256);
+    st->block = dim3(stem ? 640 : 384);
     return 0;
 }
 
@@ -594,7 +599,7 @@ struct unetb200_handle_s {
     int wstat = 1;
     int stem_tc = 1;            // first conv on the tensor cores (n_channels <= 3)
     int pf_items = 0;           // L2 prefetch distance of the activation producer, in ring items (measured: no gain)
-    int n_out_max = 4;          // store staging slots for weight-stationary launches
+    int epi2 = 1;               // two epilogue groups: 0 never, 1 weight-stationary launches, 2 always
     int pair = 2;               // CTA pairs (cta_group::2): 0 = never, 1 = wherever instantiated, 2 = where measured faster
     int pdl = 1;                // programmatic dependent launch between the layers of one forward
     int profile = 0;
@@ -652,7 +657,7 @@ int build_plan(unetb200_handle_t h, const void* x, int x_fmt, int n, int H, int 
         d.n = n; d.h = H >> lvl; d.wd = W >> lvl; d.cout = h->layers[li].cout;
         d.relu = 1; d.taps = 9; d.epi = pool ? ub::EPI_STORE_POOL : ub::EPI_STORE;
         d.out = out; d.pool = pool;
-        d.bn = h->bn_max; d.amode = h->amode; d.wstat = h->wstat; d.pf_items = h->pf_items; d.n_out_max = h->n_out_max; d.dbg = h->dbg;
+        d.bn = h->bn_max; d.amode = h->amode; d.wstat = h->wstat; d.pf_items = h->pf_items; d.epi2 = h->epi2; d.dbg = h->dbg;
         // measured on B200 (profiles/): CTA pairs win or tie on every 3x3 conv, lose slightly on the up-convs
         d.pair = h->pair >= 1;
         Step st;
@@ -667,7 +672,7 @@ int build_plan(unetb200_handle_t h, const void* x, int x_fmt, int n, int H, int 
         d.w = Wp(li); d.bias = Bp(li);
         d.n = n; d.h = H >> lvl; d.wd = W >> lvl; d.cout = h->layers[li].cout;
         d.relu = 0; d.taps = 1; d.epi = ub::EPI_UPSAMPLE; d.out = out;
-        d.bn = h->bn_max; d.amode = ub::A_TAP; d.wstat = h->wstat; d.pf_items = h->pf_items; d.n_out_max = h->n_out_max; d.pair = h->pair == 1; d.dbg = h->dbg;
+        d.bn = h->bn_max; d.amode = ub::A_TAP; d.wstat = h->wstat; d.pf_items = h->pf_items; d.epi2 = h->epi2; d.pair = h->pair == 1; d.dbg = h->dbg;
         Step st;
         if ((rc = build_conv_step(d, h->num_sms, &st))) return rc;
         st.layer = li;
@@ -716,7 +721,7 @@ int build_plan(unetb200_handle_t h, const void* x, int x_fmt, int n, int H, int 
             d.n = n; d.h = H; d.wd = W; d.cout = bw; d.relu = 1; d.taps = 9; d.epi = ub::EPI_HEAD;
             d.head_w = reinterpret_cast<const float*>(Wp(22)); d.head_b = Bp(22);
             d.ncls = h->arch.n_classes; d.logits = logits; d.mask = mask;
-            d.bn = 64; d.amode = h->amode; d.wstat = h->wstat; d.pf_items = h->pf_items; d.n_out_max = h->n_out_max; d.pair = h->pair >= 1; d.dbg = h->dbg;
+            d.bn = 64; d.amode = h->amode; d.wstat = h->wstat; d.pf_items = h->pf_items; d.epi2 = h->epi2; d.pair = h->pair >= 1; d.dbg = h->dbg;
             Step st;
             if ((rc = build_conv_step(d, h->num_sms, &st))) return rc;
             st.layer = 21;
@@ -842,8 +847,8 @@ int unetb200_create(const unetb200_arch_t* arch, const void* blob_dev, uint64_t 
     if (env) h->pdl = atoi(env) ? 1 : 0;
     env = getenv("UNETB200_PAIR");
     if (env) h->pair = atoi(env);
-    env = getenv("UNETB200_N_OUT_MAX");
-    if (env) h->n_out_max = atoi(env);
+    env = getenv("UNETB200_EPI2");
+    if (env) h->epi2 = atoi(env);
     env = getenv("UNETB200_PF_ITEMS");
     if (env) h->pf_items = atoi(env);
     env = getenv("UNETB200_STEM_TC");
@@ -879,9 +884,9 @@ int unetb200_set_option(unetb200_handle_t h, const char* key, int value) {
     } else if (k == "pair") {
         if (value < 0 || value > 2) return fail(UNETB200_EINVAL, "pair must be 0, 1 or 2");
         h->pair = value;
-    } else if (k == "n_out_max") {
-        if (value < 1 || value > 4) return fail(UNETB200_EINVAL, "n_out_max must be in 1..4");
-        h->n_out_max = value;
+    } else if (k == "epi2") {
+        if (value < 0 || value > 2) return fail(UNETB200_EINVAL, "epi2 must be 0, 1 or 2");
+        h->epi2 = value;
     } else if (k == "pf_items") {
         if (value < 0 || value > 64) return fail(UNETB200_EINVAL, "pf_items must be in 0..64");
         h->pf_items = value;
@@ -902,7 +907,7 @@ int unetb200_get_option(unetb200_handle_t h, const char* key, int* value) {
     else if (k == "wstat") *value = h->wstat;
     else if (k == "stem_tc") *value = h->stem_tc;
     else if (k == "pf_items") *value = h->pf_items;
-    else if (k == "n_out_max") *value = h->n_out_max;
+    else if (k == "epi2") *value = h->epi2;
     else if (k == "pair") *value = h->pair;
     else if (k == "pdl") *value = h->pdl;
     else if (k == "profile") *value = h->profile;
