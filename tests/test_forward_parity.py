@@ -66,6 +66,39 @@ def test_logits_512(model, fixture_state, cuda_dev):
 import os
 
 
+def test_logits_1024_nonsquare(model, fixture_state, cuda_dev):
+    """BASELINE.json configs[3] class: a high-resolution scan, here 1024 x 768 (non-square, /16)."""
+    from oracle.unet_oracle import oracle_forward, parity_report
+    from tw_invoice_unet_ocr_llm_b200.synthetic import synthetic_invoices
+    x = synthetic_invoices(1, 1024, 768, seed=51)
+    with torch.no_grad():
+        z = model(x.to(cuda_dev))
+    rep = parity_report(oracle_forward(fixture_state, x), z)
+    print(f"parity 1x1024x768: {rep}")
+    _check(rep, 0.999)
+
+
+def test_batch64_properties(model, cuda_dev):
+    """BASELINE.json configs[1] at full size (64 x 3 x 512 x 512), through size-independent
+    properties: eight distinct frames tiled 8x must give eight identical groups of logits (images
+    are independent and every tile/CTA assignment must produce the same bits), and the masks must
+    equal logits > threshold."""
+    from tw_invoice_unet_ocr_llm_b200.synthetic import synthetic_invoices
+    base = synthetic_invoices(8, 512, 512, seed=52)
+    x = torch.cat([base] * 8).to(cuda_dev)
+    eng = model.engine(cuda_dev)
+    thr = [0.25, 0.40, 0.30]
+    z, m = eng.run(x, thresholds=thr)
+    torch.cuda.synchronize()
+    assert z.shape == (64, 3, 512, 512)
+    for g in range(1, 8):
+        assert torch.equal(z[:8], z[8 * g:8 * g + 8]), f"group {g} differs"
+    from tw_invoice_unet_ocr_llm_b200.engine import logit_thresholds
+    t = torch.tensor(logit_thresholds(thr), dtype=torch.float32, device=cuda_dev).view(1, 3, 1, 1)
+    assert torch.equal(m, (z > t).to(torch.uint8))
+    assert torch.isfinite(z).all()
+
+
 @pytest.mark.parametrize("amode", [int(v) for v in os.environ.get("UNETB200_TEST_AMODES", "0,1,2").split(",")])
 def test_amodes_agree(model, cuda_dev, amode):
     """The three activation-staging strategies feed the same tiles to the same MMAs.  A_TAP

@@ -1,0 +1,87 @@
+"""The reference-facing entry points on the GPU: inference.run_unet / run_unet_batch / load_model
+(reference inference.py:17-129) against the oracle's restatement of the same pipeline."""
+import os
+
+import numpy as np
+import pytest
+import torch
+from PIL import Image
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def checkpoint(tmp_path_factory, fixture_state):
+    d = tmp_path_factory.mktemp("ckpt")
+    path = os.path.join(d, "best_unet_model.pth")
+    torch.save(fixture_state, path)          # same format as train.py:159
+    return path
+
+
+def _oracle_masks(fixture_state, pil):
+    from oracle.unet_oracle import IMG_SIZE, oracle_forward, oracle_masks
+    arr = np.array(pil.resize((IMG_SIZE, IMG_SIZE)).convert("RGB").resize((IMG_SIZE, IMG_SIZE))).astype(np.float32) / 255.0
+    x = torch.from_numpy(arr.transpose(2, 0, 1)).unsqueeze(0)
+    z = oracle_forward(fixture_state, x)
+    return oracle_masks(z)[0], z[0]
+
+
+def test_run_unet_matches_oracle(checkpoint, fixture_state, cuda_dev):
+    from oracle.unet_oracle import oracle_crop_boxes
+    from tw_invoice_unet_ocr_llm_b200 import inference as inf
+    from tw_invoice_unet_ocr_llm_b200.synthetic import synthetic_invoices_u8
+    assert inf.DEVICE == "cuda"
+    pil = Image.fromarray(synthetic_invoices_u8(1, 720, 1280, seed=77)[0])
+    masks, crops = inf.run_unet(pil, checkpoint)
+    assert list(masks) == inf.FIELDS and list(crops) == inf.FIELDS
+    ref, z = _oracle_masks(fixture_state, pil)
+    total = agree = 0
+    for c, k in enumerate(inf.FIELDS):
+        assert masks[k].dtype == np.bool_ and masks[k].shape == (512, 512)
+        total += masks[k].size
+        agree += int((masks[k] == ref[c]).sum())
+    assert agree / total >= 0.999, agree / total
+    # crops follow from the product's own masks exactly as the reference computes them
+    boxes = oracle_crop_boxes(masks, *pil.size)
+    for k in inf.FIELDS:
+        if boxes[k] is None:
+            assert crops[k] is None
+        else:
+            x1, y1, x2, y2 = boxes[k]
+            assert crops[k] is not None and crops[k].size == (x2 - x1, y2 - y1)
+
+
+def test_load_model_is_cached_and_strict(checkpoint, cuda_dev):
+    from tw_invoice_unet_ocr_llm_b200 import inference as inf
+    m1 = inf.load_model(checkpoint)
+    m2 = inf.load_model(checkpoint)
+    assert m1 is m2 and not m1.training
+    assert next(m1.parameters()).is_cuda
+
+
+def test_run_unet_batch_equals_single(checkpoint, cuda_dev):
+    from tw_invoice_unet_ocr_llm_b200 import inference as inf
+    from tw_invoice_unet_ocr_llm_b200.synthetic import synthetic_invoices_u8
+    frames = synthetic_invoices_u8(3, 300, 400, seed=78)
+    pils = [Image.fromarray(f) for f in frames]
+    batch = inf.run_unet_batch(pils, checkpoint)
+    assert len(batch) == 3
+    for pil, (bm, bc) in zip(pils, batch):
+        sm, sc = inf.run_unet(pil, checkpoint)
+        for k in inf.FIELDS:
+            assert np.array_equal(bm[k], sm[k])
+            assert (bc[k] is None) == (sc[k] is None)
+    assert inf.run_unet_batch([], checkpoint) == []
+
+
+def test_launcher_single_gpu_matches_engine(fixture_state, cuda_dev):
+    """MultiGpuSegmenter on one device (chunked, double-buffered) == one direct engine call."""
+    from tw_invoice_unet_ocr_llm_b200.engine import Engine
+    from tw_invoice_unet_ocr_llm_b200.launcher import MultiGpuSegmenter
+    from tw_invoice_unet_ocr_llm_b200.synthetic import synthetic_invoices_u8
+    frames = synthetic_invoices_u8(5, 64, 96, seed=79)
+    seg = MultiGpuSegmenter(fixture_state, devices=["cuda:0"], chunk=2)
+    out = seg.segment(frames)
+    eng = Engine(fixture_state, cuda_dev)
+    _, m = eng.run(torch.from_numpy(frames).to(cuda_dev), want_logits=False, thresholds=[0.25, 0.40, 0.30])
+    assert torch.equal(out, m.cpu())

@@ -61,7 +61,7 @@ def load_model(checkpoint_path: str):
 def _resized_rgb_u8(pil_img: Image.Image) -> np.ndarray:
     """``convert("RGB").resize((512, 512))`` -> uint8 (512, 512, 3)  (reference :35)."""
     img = pil_img.convert("RGB").resize((IMG_SIZE, IMG_SIZE))
-    arr = np.asarray(img)
+    arr = np.array(img)              # writable copy, uint8 HWC
     if arr.ndim != 3 or arr.shape[2] != 3:
         raise ValueError(f"Invalid image shape: {arr.shape}")
     return arr
