@@ -50,6 +50,28 @@ def read_peaks():
                 "source": "fallback of B200_PROFILING.md (MEASURED_PEAKS.json absent)"}
 
 
+def ncu_traffic_bytes():
+    """DRAM bytes (read + write) of the 21 tensor-core launches of one step, from the newest committed
+    `ncu --set full` capture (profiles/*_ncu_raw.csv, batch 64 @ 512x512); None if absent."""
+    import csv
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_raw.csv")))
+    if not files:
+        return None, None
+    try:
+        rows = list(csv.reader(open(files[-1])))
+        h, unit, data = rows[0], rows[1], rows[2:]
+        ir, iw, ik = h.index("dram__bytes_read.sum"), h.index("dram__bytes_write.sum"), h.index("Kernel Name")
+        scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[unit[ir]]
+        tc = [r for r in data if "conv_tc_kernel" in r[ik] and "conv_tc_kernel<64, 1, 3," not in r[ik]
+              and "(int)64, (int)1, (int)3" not in r[ik]]            # all launches but the stem (A_STEM)
+        if len(tc) != 21:
+            return None, None
+        return sum(float(r[ir]) + float(r[iw]) for r in tc) * scale, os.path.basename(files[-1])
+    except Exception:
+        return None, None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -272,10 +294,13 @@ def main():
                       "ms": round(ms, 4), "gflop": round(fl / 1e9, 2), "tflops": round(tf, 1),
                       "frac_of_peak": round(tf / peaks["tflops"], 3)})
     achieved = tc_flops / (tc_ms * 1e-3) / 1e12
+    traffic, traffic_src = ncu_traffic_bytes() if (B == 64 and S == 512) else (None, None)
     roofline = {
         "bound": "tensor", "kernel": "conv_tc_kernel<BN,TAPS,AMODE,EPI> (21 launches per step: 17 conv3x3 + 4 convT)",
         "achieved": round(achieved, 1), "peak": peaks["tflops"], "unit": "TFLOP/s",
-        "frac": round(achieved / peaks["tflops"], 4), "traffic": None,
+        "frac": round(achieved / peaks["tflops"], 4), "traffic": traffic,
+        "traffic_note": (f"DRAM read+write bytes of the same 21 launches of one step, ncu --set full ({traffic_src}); "
+                         "algorithmic bytes of those layers: 64 x 571.7 MB = 36.6 GB") if traffic else None,
         "peak_source": peaks["source"],
         "how": "sum of algorithmic conv FLOPs of the 21 tcgen05 launches / sum of their CUDA-event durations "
                "(events recorded between launches on the launching stream, averaged over the K steps)",

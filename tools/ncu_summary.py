@@ -37,7 +37,9 @@ def main():
     print("|---|---|---|" + "---|" * len(cols))
     # the capture window may start mid-forward: anchor the labels on the stem kernel
     names = [r[idx["Kernel Name"]] for r in data]
-    stem = next((i for i, n in enumerate(names) if "stem" in n), 0)
+    # stem = the A_STEM instantiation conv_tc_kernel<64, 1, 3, ...> (or the CUDA-core stem_conv_kernel)
+    stem = next((i for i, n in enumerate(names)
+                 if "stem" in n or "conv_tc_kernel<(int)64, (int)1, (int)3" in n or "conv_tc_kernel<64, 1, 3" in n), 0)
     for i, r in enumerate(data):
         name = names[i]
         short = name.split("(")[0].replace("ub::", "").replace("void ", "")[:60]

@@ -19,9 +19,9 @@ ncu -i /tmp/ncu/all.ncu-rep --page raw --csv > $out/prof_${tag}_raw.csv 2> /dev/
 ncu -i /tmp/ncu/all.ncu-rep --page details --csv > $out/prof_${tag}_details.csv 2> /dev/null
 # source-level capture of two tensor-core kernels: conv launches #19 (conv1.net.0, Cout=64,
 # weight-stationary) and #13 (conv3.net.0, Cout=256) of the 4th forward
-ncu --set full --clock-control none --import-source on -k regex:conv_tc -s 76 -c 1 \
+ncu --set full --clock-control none --import-source on -k regex:conv_tc -s 80 -c 1 \
     -o $out/prof_${tag}_conv3_0 -f $CMD > $out/ncu_src1_$tag.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:conv_tc -s 82 -c 1 \
+ncu --set full --clock-control none --import-source on -k regex:conv_tc -s 86 -c 1 \
     -o $out/prof_${tag}_conv1_0 -f $CMD > $out/ncu_src2_$tag.log 2>&1
 echo "source rc=$?"
 ls -la $out/ | tail -n 20
