@@ -39,6 +39,27 @@ def layer_flops(layer, h, w) -> float:
     return 2.0 * hh * ww * layer.cin * layer.cout      # 1x1 head
 
 
+def layer_bytes(layer, h, w, n_classes=3) -> float:
+    """Algorithmic HBM bytes per image of one layer in the fused plan: bf16 NHWC
+    activations read once per consumer and written once, pool as a second output, concat virtual,
+    out_conv + threshold fused into conv1.net.3 (fp32 logits + u8 mask out); weights excluded."""
+    px = (h >> layer.level) * (w >> layer.level)
+    name = layer.name.decode()
+    if layer.kind == 0:                                   # stem: fp32 NCHW in, bf16 out
+        return px * (layer.cin * 4 + layer.cout * 2)
+    if layer.kind == 2:                                   # convT: 4 output pixels per input pixel
+        return px * layer.cin * 2 + 4 * px * layer.cout * 2
+    if layer.kind == 3:
+        return 0.0
+    b = px * layer.cin * 2
+    if name == "conv1.net.3":
+        return b + px * n_classes * (4 + 1)
+    b += px * layer.cout * 2
+    if name.startswith("down") and name.endswith(".3"):
+        b += px // 4 * layer.cout * 2                     # fused 2x2 max-pool output
+    return b
+
+
 def read_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -277,7 +298,7 @@ def main():
     layer_ms = [a / args.steps for a in acc]
     layers = eng.layers
     peaks = read_peaks()
-    table, tc_flops, tc_ms = [], 0.0, 0.0
+    table, tc_flops, tc_ms, tc_bytes = [], 0.0, 0.0, 0.0
     for i, l in enumerate(layers):
         if l.kind == nat.HEAD:
             continue                                  # fused into conv1.net.3
@@ -287,11 +308,14 @@ def main():
         ms = layer_ms[i]
         tf = fl / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
         tensor = l.kind in (nat.CONV3X3, nat.CONVT2X2)
+        by = layer_bytes(l, S, S) * B + l.w_bytes
         if tensor:
             tc_flops += fl
             tc_ms += ms
+            tc_bytes += by
         table.append({"layer": l.name.decode(), "kernel": "conv_tc_kernel (tcgen05)" if tensor else "stem_conv_kernel",
                       "ms": round(ms, 4), "gflop": round(fl / 1e9, 2), "tflops": round(tf, 1),
+                      "algorithmic_gb": round(by / 1e9, 3), "gb_per_s": round(by / 1e9 / (ms * 1e-3), 1) if ms > 0 else 0.0,
                       "frac_of_peak": round(tf / peaks["tflops"], 3)})
     achieved = tc_flops / (tc_ms * 1e-3) / 1e12
     traffic, traffic_src = ncu_traffic_bytes() if (B == 64 and S == 512) else (None, None)
@@ -300,7 +324,7 @@ def main():
         "achieved": round(achieved, 1), "peak": peaks["tflops"], "unit": "TFLOP/s",
         "frac": round(achieved / peaks["tflops"], 4), "traffic": traffic,
         "traffic_note": (f"DRAM read+write bytes of the same 21 launches of one step, ncu --set full ({traffic_src}); "
-                         "algorithmic bytes of those layers: 64 x 571.7 MB = 36.6 GB") if traffic else None,
+                         f"algorithmic bytes of those launches: {tc_bytes / 1e9:.2f} GB per step") if traffic else None,
         "peak_source": peaks["source"],
         "how": "sum of algorithmic conv FLOPs of the 21 tcgen05 launches / sum of their CUDA-event durations "
                "(events recorded between launches on the launching stream, averaged over the K steps)",

@@ -526,8 +526,6 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
         const int eg = (warp - 4) >> 2;         // epilogue group: takes tiles tile_it % 2 == eg
         const int q = warp & 3;                 // TMEM lane quarter this warp may access (warp id % 4)
         const int row = q * 32 + lane;          // pixel row of the tile: h = row/8, w = row%8
-        const int et = (threadIdx.x - 128) & 127;   // 0..127 inside the group
-        const int bar0 = 1 + 4 * eg;            // named barriers of this group: bar0, bar0 + 1
         const int estep = p.n_epi;              // tiles between two tiles of this group
         uint32_t tile_it = eg, chunk_it = 0;
         // hand-back of an accumulator: arrive on the (leader's) barrier the MMA issuer waits on
@@ -605,15 +603,16 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
                 const int gcol = nb * BN + j * 64;            // global column of this 64-wide chunk
                 const int tapo = EPI == EPI_UPSAMPLE ? gcol / p.Cout : 0;
                 const int ch0 = EPI == EPI_UPSAMPLE ? gcol - tapo * p.Cout : gcol;
-                // each group owns n_out staging slots; a slot was last read by this group's store
-                // issued n_out chunks ago (bulk groups are per thread: et == 0 of the group)
+                // Each warp owns a quarter of the tile (4 pixel rows): its own 4 KB slab of the staging
+                // slot, its own TMA stores, its own bulk groups -- no barrier between the four warps.
+                // Each group owns n_out slots; a slab was last read by this warp's store n_out chunks ago.
                 const uint32_t buf = eg * p.n_out + chunk_it % static_cast<uint32_t>(p.n_out);
                 const uint32_t obuf = sOut + buf * kOutStage;
                 const uint32_t pbuf = sPool + buf * kPoolStage;
-                if (et == 0) {
+                if (lane == 0) {
                     if (p.n_out == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
                 }
-                named_bar_sync(bar0, 128);
+                __syncwarp();
                 uint32_t pk[32];
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
@@ -663,19 +662,22 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
                     }
                 }
                 fence_proxy_async_smem();
-                named_bar_sync(bar0 + 1, 128);
-                if (et == 0 && valid) {
-                    if (EPI == EPI_UPSAMPLE)
-                        tma_store_4d(&p.tmOut[tapo], obuf, ch0, x0, y0, n);
-                    else
-                        tma_store_4d(&p.tmOut[0], obuf, ch0, x0, y0, n);
-                    if (EPI == EPI_STORE_POOL)
-                        tma_store_4d(&p.tmPool, pbuf, ch0, x0 >> 1, y0 >> 1, n);
+                __syncwarp();
+                if (lane == 0) {
+                    if (valid) {
+                        // this warp's rows y0 + 4q .. +3 (pooled: (y0 >> 1) + 2q, +1)
+                        if (EPI == EPI_UPSAMPLE)
+                            tma_store_4d(&p.tmOut[tapo], obuf + q * 4096, ch0, x0, y0 + 4 * q, n);
+                        else
+                            tma_store_4d(&p.tmOut[0], obuf + q * 4096, ch0, x0, y0 + 4 * q, n);
+                        if (EPI == EPI_STORE_POOL)
+                            tma_store_4d(&p.tmPool, pbuf + q * 1024, ch0, x0 >> 1, (y0 >> 1) + 2 * q, n);
+                    }
                     tma_store_commit();
                 }
             }
         }
-        if (et == 0) tma_store_wait_all<0>();
+        if (lane == 0) tma_store_wait_all<0>();
     }
 
     tc_fence_before();

@@ -426,16 +426,17 @@ int build_conv_step(const ConvDesc& d, int num_sms, Step* st) {
             const int a = tap >> 1, b = tap & 1;
             const char* base = static_cast<const char*>(d.out) + (uint64_t(a) * wo + b) * d.cout * 2;
             if ((rc = make_map4(&p.tmOut[tap], base, d.cout, d.wd, d.h, d.n, uint64_t(2) * d.cout * 2,
-                                uint64_t(2) * wo * d.cout * 2, uint64_t(ho) * wo * d.cout * 2, 8, 16)))
+                                uint64_t(2) * wo * d.cout * 2, uint64_t(ho) * wo * d.cout * 2, 8, 4)))
                 return rc;
         }
     } else if (d.epi != ub::EPI_HEAD) {
-        if ((rc = make_act_map(&p.tmOut[0], d.out, d.cout, d.wd, d.h, d.n, 8, 16))) return rc;
+        // store boxes: one epilogue warp's quarter tile (8 x 4 pixels), pooled 4 x 2
+        if ((rc = make_act_map(&p.tmOut[0], d.out, d.cout, d.wd, d.h, d.n, 8, 4))) return rc;
         for (int i = 1; i < 4; ++i) p.tmOut[i] = p.tmOut[0];
     }
     if (d.epi == ub::EPI_STORE_POOL) {
         if (!d.pool) return fail(UNETB200_EINVAL, "pool output missing");
-        if ((rc = make_act_map(&p.tmPool, d.pool, d.cout, d.wd / 2, d.h / 2, d.n, 4, 8))) return rc;
+        if ((rc = make_act_map(&p.tmPool, d.pool, d.cout, d.wd / 2, d.h / 2, d.n, 4, 2))) return rc;
     } else {
         p.tmPool = p.tmA0;
     }
