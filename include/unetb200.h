@@ -142,6 +142,22 @@ uint64_t unetb200_stem_tc_offset(int cin);
 int unetb200_stem(const void* x, int x_fmt, int cin, const float* w, const float* bias, int n,
                   int height, int width, void* out, void* stream);
 
+/* ---- pre / post processing: bit-exact integer work around the forward ---- */
+/* Pillow's 8-bit bicubic resample, i.e. PIL.Image.resize of inference.py:35,63 (the reference
+ * delegates to Pillow==10.2.0, requirements.txt:3).  unetb200_resize_coeffs is host-only: it fills
+ * kk[out_size * ksize] (22-bit fixed point) and bounds[out_size * 2] ({first tap, tap count}) for
+ * one axis, ksize = unetb200_resize_ksize(in_size, out_size); upload both to the device.
+ * unetb200_resize_bicubic_u8: src uint8 [n,h,w,c] -> dst uint8 [n,oh,ow,c]; tmp holds n*h*ow*c
+ * bytes (horizontal pass output; may be NULL if only one axis changes). */
+int unetb200_resize_ksize(int in_size, int out_size);
+int unetb200_resize_coeffs(int in_size, int out_size, int32_t* kk, int32_t* bounds);
+int unetb200_resize_bicubic_u8(const uint8_t* src, int n, int h, int w, int c, const int32_t* kx_dev,
+                               const int32_t* bx_dev, int ksx, const int32_t* ky_dev, const int32_t* by_dev,
+                               int ksy, uint8_t* tmp_dev, uint8_t* dst_dev, int oh, int ow, void* stream);
+/* np.where(mask) min/max of inference.py:85-93: mask uint8 [n_planes,h,w] ->
+ * out int32 [n_planes,5] = {xmin, xmax, ymin, ymax, count}; an empty plane gives {w, -1, h, -1, 0}. */
+int unetb200_mask_bbox(const uint8_t* mask, int n_planes, int h, int w, int32_t* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

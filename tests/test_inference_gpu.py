@@ -51,6 +51,24 @@ def test_run_unet_matches_oracle(checkpoint, fixture_state, cuda_dev):
             assert crops[k] is not None and crops[k].size == (x2 - x1, y2 - y1)
 
 
+def test_gpu_preprocess_equals_host_preprocess(checkpoint, cuda_dev):
+    """RGB frames take the GPU resize; any other mode takes the reference's PIL calls on the host.
+    Same pixels either way -> identical masks and crops."""
+    from tw_invoice_unet_ocr_llm_b200 import inference as inf
+    from tw_invoice_unet_ocr_llm_b200.synthetic import synthetic_invoices_u8
+    frame = synthetic_invoices_u8(1, 600, 900, seed=80)[0]
+    rgb = Image.fromarray(frame)
+    rgba = rgb.convert("RGBA")                  # alpha = 255: resize + convert("RGB") gives the same RGB bytes
+    assert inf._gpu_resizable(rgb) and not inf._gpu_resizable(rgba)
+    m1, c1 = inf.run_unet(rgb, checkpoint)
+    m2, c2 = inf.run_unet(rgba, checkpoint)
+    for k in inf.FIELDS:
+        assert np.array_equal(m1[k], m2[k])
+        assert (c1[k] is None) == (c2[k] is None)
+        if c1[k] is not None:
+            assert c1[k].size == c2[k].size
+
+
 def test_load_model_is_cached_and_strict(checkpoint, cuda_dev):
     from tw_invoice_unet_ocr_llm_b200 import inference as inf
     m1 = inf.load_model(checkpoint)

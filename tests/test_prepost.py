@@ -1,0 +1,82 @@
+"""Pre/post-processing: Pillow-exact bicubic resize and mask -> bbox reduction.
+Integer / byte work: the bar is bit-exact."""
+import numpy as np
+import pytest
+import torch
+from PIL import Image
+
+SIZES = [(1080, 1920), (300, 420), (512, 512), (513, 700), (64, 1500), (900, 64), (512, 300), (100, 512)]
+
+
+@pytest.mark.parametrize("h,w", SIZES[:6])
+def test_resample_oracle_equals_pillow(h, w):
+    """The numpy restatement is pinned against Pillow itself, run in this process."""
+    from oracle.pillow_resample import resize_u8
+    img = np.random.default_rng(h * 7 + w).integers(0, 256, (h, w, 3), dtype=np.uint8)
+    ref = np.asarray(Image.fromarray(img).resize((512, 512)))
+    assert np.array_equal(resize_u8(img, 512, 512), ref)
+
+
+@pytest.mark.parametrize("a,o", [(1920, 512), (1080, 512), (300, 512), (512, 512), (7, 512), (5000, 512), (513, 64)])
+def test_resize_coeffs_c_abi_equals_oracle(a, o):
+    """unetb200_resize_coeffs (host double-precision math in the library) == the oracle's tables."""
+    from oracle.pillow_resample import coeffs
+    from tw_invoice_unet_ocr_llm_b200 import prepost
+    kk, b = prepost.resize_tables_host(a, o)
+    k2, b2 = coeffs(a, o)
+    assert np.array_equal(kk, k2) and np.array_equal(b, b2)
+
+
+def test_mask_bbox_oracle():
+    from oracle.pillow_resample import mask_bbox
+    m = np.zeros((512, 512), bool)
+    assert mask_bbox(m) == (512, -1, 512, -1, 0)
+    m[10:20, 30:45] = True
+    m[400, 7] = True
+    assert mask_bbox(m) == (7, 44, 10, 400, 151)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("h,w", SIZES)
+def test_gpu_resize_bit_exact_vs_pillow(cuda_dev, h, w):
+    from tw_invoice_unet_ocr_llm_b200 import prepost
+    rng = np.random.default_rng(h + 3 * w)
+    imgs = rng.integers(0, 256, (2, h, w, 3), dtype=np.uint8)
+    out = prepost.resize_u8(torch.from_numpy(imgs).to(cuda_dev), 512, 512).cpu().numpy()
+    for i in range(2):
+        ref = np.asarray(Image.fromarray(imgs[i]).resize((512, 512)))
+        assert np.array_equal(out[i], ref), f"{int((out[i] != ref).sum())} bytes differ"
+
+
+@pytest.mark.gpu
+def test_gpu_resize_other_targets_and_channels(cuda_dev):
+    from oracle.pillow_resample import resize_u8
+    from tw_invoice_unet_ocr_llm_b200 import prepost
+    rng = np.random.default_rng(5)
+    g = rng.integers(0, 256, (1, 37, 91, 1), dtype=np.uint8)
+    out = prepost.resize_u8(torch.from_numpy(g).to(cuda_dev), 64, 48).cpu().numpy()
+    assert np.array_equal(out[0], resize_u8(g[0], 64, 48))
+    rgba = rng.integers(0, 256, (1, 200, 100, 4), dtype=np.uint8)
+    out = prepost.resize_u8(torch.from_numpy(rgba).to(cuda_dev), 200, 60).cpu().numpy()      # one axis only
+    assert np.array_equal(out[0], resize_u8(rgba[0], 200, 60))
+
+
+@pytest.mark.gpu
+def test_gpu_mask_bbox_bit_exact(cuda_dev):
+    from oracle.pillow_resample import mask_bbox
+    from tw_invoice_unet_ocr_llm_b200 import prepost
+    rng = np.random.default_rng(9)
+    m = np.zeros((3, 3, 512, 512), np.uint8)
+    m[0, 0, 100:130, 200:260] = 1
+    m[0, 1] = (rng.random((512, 512)) < 0.001)
+    m[1, 2, 511, 511] = 1
+    m[2, 0, 0, 0] = 1
+    m[2, 1] = 1
+    got = prepost.mask_bbox(torch.from_numpy(m).to(cuda_dev)).cpu().numpy()
+    for n in range(3):
+        for c in range(3):
+            assert tuple(int(v) for v in got[n, c]) == mask_bbox(m[n, c].astype(bool)), (n, c)
+    odd = np.zeros((1, 1, 33, 50), np.uint8)           # width not a multiple of 16: scalar path
+    odd[0, 0, 5:9, 17:23] = 255
+    got = prepost.mask_bbox(torch.from_numpy(odd).to(cuda_dev)).cpu().numpy()
+    assert tuple(int(v) for v in got[0, 0]) == mask_bbox(odd[0, 0].astype(bool))

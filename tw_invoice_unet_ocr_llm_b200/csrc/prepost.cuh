@@ -1,0 +1,123 @@
+// Pre- and post-processing around the forward, integer / byte work,
+// HBM-bound, bit-exact by construction:
+//
+//  * resize_*_kernel : PIL.Image.resize((512, 512)) of inference.py:35,63 for uint8 RGB frames.
+//    The reference delegates to Pillow (pinned Pillow==10.2.0, requirements.txt:3), whose
+//    ImagingResample for 8-bit images is: bicubic (a = -0.5) kernel stretched by the scale factor
+//    (antialiasing), coefficients normalised in double precision and rounded to 22-bit fixed point,
+//    a horizontal pass into a uint8 intermediate, then a vertical pass; each output is
+//    clip8((2^21 + sum(pixel * k)) >> 22).  The coefficient tables are computed on the host in
+//    double precision (unet_b200.cu: resize_coeffs) exactly as Pillow's precompute_coeffs does.
+//  * mask_bbox_kernel : the np.where(mask) min/max of inference.py:85-93 as one block reduction per
+//    (image, class) plane: {xmin, xmax, ymin, ymax, count}.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ub {
+
+constexpr int kResizePrecisionBits = 32 - 8 - 2;   // Pillow: PRECISION_BITS
+
+__device__ __forceinline__ uint8_t clip8(int v) {
+    v >>= kResizePrecisionBits;                      // arithmetic shift, like Pillow's lookup table
+    return static_cast<uint8_t>(v < 0 ? 0 : (v > 255 ? 255 : v));
+}
+
+// src [n][h][w][c] -> dst [n][h][ow][c]; one thread per (row, output column), all channels
+template <int C>
+__global__ void resize_horizontal_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
+                                         const int32_t* __restrict__ kk, const int32_t* __restrict__ bounds,
+                                         int ksize, int rows /* n*h */, int w, int ow) {
+    const int xx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int row = blockIdx.y;
+    if (xx >= ow || row >= rows) return;
+    const int xmin = bounds[2 * xx], xn = bounds[2 * xx + 1];
+    const int32_t* k = kk + static_cast<size_t>(xx) * ksize;
+    const uint8_t* in = src + (static_cast<size_t>(row) * w + xmin) * C;
+    int acc[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc[c] = 1 << (kResizePrecisionBits - 1);
+    for (int x = 0; x < xn; ++x) {
+        const int kv = __ldg(k + x);
+#pragma unroll
+        for (int c = 0; c < C; ++c) acc[c] += static_cast<int>(__ldg(in + x * C + c)) * kv;
+    }
+    uint8_t* out = dst + (static_cast<size_t>(row) * ow + xx) * C;
+#pragma unroll
+    for (int c = 0; c < C; ++c) out[c] = clip8(acc[c]);
+}
+
+// src [n][h][w*c] -> dst [n][oh][w*c]; one thread per (output row, byte column)
+__global__ void resize_vertical_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
+                                       const int32_t* __restrict__ kk, const int32_t* __restrict__ bounds,
+                                       int ksize, int h, int oh, int wc) {
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    const int yy = blockIdx.y;
+    const int n = blockIdx.z;
+    if (col >= wc) return;
+    const int ymin = bounds[2 * yy], yn = bounds[2 * yy + 1];
+    const int32_t* k = kk + static_cast<size_t>(yy) * ksize;
+    const uint8_t* in = src + (static_cast<size_t>(n) * h + ymin) * wc + col;
+    int acc = 1 << (kResizePrecisionBits - 1);
+    for (int y = 0; y < yn; ++y) acc += static_cast<int>(__ldg(in + static_cast<size_t>(y) * wc)) * __ldg(k + y);
+    dst[(static_cast<size_t>(n) * oh + yy) * wc + col] = clip8(acc);
+}
+
+// one block per plane [h][w] of uint8 (non-zero = set): out[plane] = {xmin, xmax, ymin, ymax, count};
+// empty plane -> {w, -1, h, -1, 0}
+__global__ void __launch_bounds__(256) mask_bbox_kernel(const uint8_t* __restrict__ mask, int h, int w,
+                                                        int32_t* __restrict__ out) {
+    const uint8_t* m = mask + static_cast<size_t>(blockIdx.x) * h * w;
+    int xmin = w, xmax = -1, ymin = h, ymax = -1, cnt = 0;
+    const int total = h * w;
+    if ((w & 15) == 0 && (reinterpret_cast<uintptr_t>(m) & 15) == 0) {
+        const uint4* m4 = reinterpret_cast<const uint4*>(m);
+        for (int i = threadIdx.x; i < total / 16; i += blockDim.x) {
+            const uint4 v = __ldg(m4 + i);
+            const uint32_t words[4] = {v.x, v.y, v.z, v.w};
+            if ((v.x | v.y | v.z | v.w) == 0) continue;
+            const int base = i * 16, y = base / w, x0 = base - y * w;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                if ((words[j >> 2] >> ((j & 3) * 8)) & 0xffu) {
+                    const int x = x0 + j;
+                    xmin = min(xmin, x); xmax = max(xmax, x);
+                    ymin = min(ymin, y); ymax = max(ymax, y);
+                    ++cnt;
+                }
+            }
+        }
+    } else {
+        for (int i = threadIdx.x; i < total; i += blockDim.x) {
+            if (m[i]) {
+                const int y = i / w, x = i - y * w;
+                xmin = min(xmin, x); xmax = max(xmax, x);
+                ymin = min(ymin, y); ymax = max(ymax, y);
+                ++cnt;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        xmin = min(xmin, __shfl_xor_sync(0xffffffffu, xmin, o));
+        xmax = max(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
+        ymin = min(ymin, __shfl_xor_sync(0xffffffffu, ymin, o));
+        ymax = max(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    }
+    __shared__ int s[8][5];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { s[warp][0] = xmin; s[warp][1] = xmax; s[warp][2] = ymin; s[warp][3] = ymax; s[warp][4] = cnt; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < 8; ++i) {
+            xmin = min(xmin, s[i][0]); xmax = max(xmax, s[i][1]);
+            ymin = min(ymin, s[i][2]); ymax = max(ymax, s[i][3]);
+            cnt += s[i][4];
+        }
+        int32_t* o = out + static_cast<size_t>(blockIdx.x) * 5;
+        o[0] = xmin; o[1] = xmax; o[2] = ymin; o[3] = ymax; o[4] = cnt;
+    }
+}
+
+}  // namespace ub

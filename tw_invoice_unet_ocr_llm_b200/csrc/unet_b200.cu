@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cmath>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -16,6 +17,7 @@
 
 #include "conv_tc.cuh"
 #include "pack.cuh"
+#include "prepost.cuh"
 #include "stem.cuh"
 
 namespace {
@@ -1092,6 +1094,120 @@ int unetb200_stem(const void* x, int x_fmt, int cin, const float* w, const float
     int rc = build_stem_step(x, x_fmt, cin, w, bias, n, height, width, out, &st);
     if (rc) return rc;
     return launch_step(st, static_cast<cudaStream_t>(stream));
+}
+
+// ------------------------------------------------------------------ pre / post processing
+namespace {
+// Pillow's bicubic kernel (Resample.c bicubic_filter, a = -0.5), evaluated exactly as written there.
+inline double pil_bicubic(double x) {
+    const double a = -0.5;
+    if (x < 0.0) x = -x;
+    if (x < 1.0) return ((a + 2.0) * x - (a + 3.0)) * x * x + 1;
+    if (x < 2.0) return (((x - 5) * x + 8) * x - 4) * a;
+    return 0.0;
+}
+inline int pil_ksize(int in_size, int out_size) {
+    double filterscale = static_cast<double>(in_size) / out_size;
+    if (filterscale < 1.0) filterscale = 1.0;
+    return static_cast<int>(std::ceil(2.0 * filterscale)) * 2 + 1;
+}
+}  // namespace
+
+int unetb200_resize_ksize(int in_size, int out_size) {
+    if (in_size <= 0 || out_size <= 0) return -1;
+    return pil_ksize(in_size, out_size);
+}
+
+// precompute_coeffs + normalize_coeffs_8bpc of Pillow's Resample.c for box = (0, in_size)
+int unetb200_resize_coeffs(int in_size, int out_size, int32_t* kk, int32_t* bounds) {
+    if (in_size <= 0 || out_size <= 0 || !kk || !bounds) return fail(UNETB200_EINVAL, "resize_coeffs: bad argument");
+    const double in0 = 0.0, in1 = static_cast<double>(in_size);
+    const double scale = (in1 - in0) / out_size;
+    double filterscale = scale;
+    if (filterscale < 1.0) filterscale = 1.0;
+    const double support = 2.0 * filterscale;
+    const int ksize = static_cast<int>(std::ceil(support)) * 2 + 1;
+    std::vector<double> k(ksize);
+    for (int xx = 0; xx < out_size; ++xx) {
+        const double center = in0 + (xx + 0.5) * scale;
+        double ww = 0.0;
+        const double ss = 1.0 / filterscale;
+        int xmin = static_cast<int>(center - support + 0.5);
+        if (xmin < 0) xmin = 0;
+        int xmax = static_cast<int>(center + support + 0.5);
+        if (xmax > in_size) xmax = in_size;
+        xmax -= xmin;
+        int x = 0;
+        for (; x < xmax; ++x) {
+            const double w = pil_bicubic((x + xmin - center + 0.5) * ss);
+            k[x] = w;
+            ww += w;
+        }
+        for (x = 0; x < xmax; ++x)
+            if (ww != 0.0) k[x] /= ww;
+        for (; x < ksize; ++x) k[x] = 0;
+        for (x = 0; x < ksize; ++x) {
+            const double v = k[x] * (1 << ub::kResizePrecisionBits);
+            kk[static_cast<size_t>(xx) * ksize + x] = k[x] < 0 ? static_cast<int>(-0.5 + v) : static_cast<int>(0.5 + v);
+        }
+        bounds[2 * xx] = xmin;
+        bounds[2 * xx + 1] = xmax;
+    }
+    return 0;
+}
+
+int unetb200_resize_bicubic_u8(const uint8_t* src, int n, int h, int w, int c, const int32_t* kx_dev,
+                               const int32_t* bx_dev, int ksx, const int32_t* ky_dev, const int32_t* by_dev,
+                               int ksy, uint8_t* tmp_dev, uint8_t* dst_dev, int oh, int ow, void* stream) {
+    if (!src || !dst_dev || n <= 0 || h <= 0 || w <= 0 || oh <= 0 || ow <= 0)
+        return fail(UNETB200_EINVAL, "resize: bad argument");
+    if (!(c == 1 || c == 3 || c == 4)) return fail(UNETB200_EINVAL, "resize: channels must be 1, 3 or 4");
+    const bool need_h = ow != w, need_v = oh != h;
+    if (need_h && (!kx_dev || !bx_dev)) return fail(UNETB200_EINVAL, "resize: horizontal tables missing");
+    if (need_v && (!ky_dev || !by_dev)) return fail(UNETB200_EINVAL, "resize: vertical tables missing");
+    if (need_h && need_v && !tmp_dev) return fail(UNETB200_EINVAL, "resize: intermediate buffer missing");
+    if (static_cast<long long>(n) * h > 2147483647LL || oh > 65535 || n > 65535)
+        return fail(UNETB200_EINVAL, "resize: image too large");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const uint8_t* cur = src;
+    if (need_h) {
+        uint8_t* out = need_v ? tmp_dev : dst_dev;
+        dim3 grid((ow + 127) / 128, n * h);
+        if (n * h > 65535) {
+            // rows beyond the grid.y limit: one launch per image
+            for (int i = 0; i < n; ++i) {
+                dim3 g((ow + 127) / 128, h);
+                const uint8_t* si = src + static_cast<size_t>(i) * h * w * c;
+                uint8_t* oi = out + static_cast<size_t>(i) * h * ow * c;
+                if (c == 1) ub::resize_horizontal_kernel<1><<<g, 128, 0, s>>>(si, oi, kx_dev, bx_dev, ksx, h, w, ow);
+                else if (c == 3) ub::resize_horizontal_kernel<3><<<g, 128, 0, s>>>(si, oi, kx_dev, bx_dev, ksx, h, w, ow);
+                else ub::resize_horizontal_kernel<4><<<g, 128, 0, s>>>(si, oi, kx_dev, bx_dev, ksx, h, w, ow);
+            }
+        } else if (c == 1) {
+            ub::resize_horizontal_kernel<1><<<grid, 128, 0, s>>>(src, out, kx_dev, bx_dev, ksx, n * h, w, ow);
+        } else if (c == 3) {
+            ub::resize_horizontal_kernel<3><<<grid, 128, 0, s>>>(src, out, kx_dev, bx_dev, ksx, n * h, w, ow);
+        } else {
+            ub::resize_horizontal_kernel<4><<<grid, 128, 0, s>>>(src, out, kx_dev, bx_dev, ksx, n * h, w, ow);
+        }
+        cur = out;
+    }
+    if (need_v) {
+        const int wc = ow * c;
+        dim3 grid((wc + 255) / 256, oh, n);
+        ub::resize_vertical_kernel<<<grid, 256, 0, s>>>(cur, dst_dev, ky_dev, by_dev, ksy, h, oh, wc);
+    } else if (!need_h) {
+        UB_CUDA(cudaMemcpyAsync(dst_dev, src, static_cast<size_t>(n) * h * w * c, cudaMemcpyDeviceToDevice, s));
+    }
+    UB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int unetb200_mask_bbox(const uint8_t* mask, int n_planes, int h, int w, int32_t* out, void* stream) {
+    if (!mask || !out || n_planes <= 0 || h <= 0 || w <= 0) return fail(UNETB200_EINVAL, "mask_bbox: bad argument");
+    ub::mask_bbox_kernel<<<n_planes, 256, 0, static_cast<cudaStream_t>(stream)>>>(mask, h, w, out);
+    UB_CUDA(cudaGetLastError());
+    return 0;
 }
 
 }  // extern "C"

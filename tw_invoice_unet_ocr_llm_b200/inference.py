@@ -11,6 +11,9 @@ keeps working unmodified.  Differences, all internal:
   of float32); the ``/255`` of ``preprocess`` happens in the first CUDA kernel and
   the sigmoid + per-class threshold (reference :72-79) in the last one, in logit
   space, so only three uint8 masks come back.
+* For plain RGB inputs the 512x512 resize itself runs on the GPU (``prepost.resize_u8``,
+  bit-identical to Pillow's bicubic resample) and the mask -> bounding box reduction of :85-93
+  too (``prepost.mask_bbox``); other PIL modes take the reference's PIL calls on the host.
 * ``run_unet_batch`` (new, additive) does the same for a list of images in one
   batched forward.
 """
@@ -74,49 +77,88 @@ def preprocess(pil_img: Image.Image):
     return torch.from_numpy(np.ascontiguousarray(arr)).unsqueeze(0).to(DEVICE)
 
 
-def masks_to_crops(pil_img: Image.Image, masks: Dict[str, np.ndarray]) -> Dict[str, Optional[Image.Image]]:
-    """Mask -> bounding box -> crop of the ORIGINAL image (reference :84-127).
-
-    Box = min/max of the mask's pixel coordinates, scaled by (orig / 512) with ``int()``
-    truncation, grown by 15 % of its size, clamped to the image; an empty box, an empty
-    mask or a near-black crop (mean < 3) gives ``None``.
-    """
+def _crop_from_extent(pil_img: Image.Image, extent) -> Optional[Image.Image]:
+    """Mask extent (xmin, xmax, ymin, ymax in 512-space, or None) -> crop of the ORIGINAL image
+    (reference :95-127): scale by (orig / 512) with ``int()`` truncation, grow by 15 % of the box
+    size, clamp to the image; an empty box or a near-black crop (mean < 3) gives ``None``."""
+    if extent is None:
+        return None
     ow, oh = pil_img.size
     sx, sy = ow / IMG_SIZE, oh / IMG_SIZE
+    mx1, mx2, my1, my2 = extent
+    x1, x2 = int(mx1 * sx), int(mx2 * sx)
+    y1, y2 = int(my1 * sy), int(my2 * sy)
+    px, py = int((x2 - x1) * 0.15), int((y2 - y1) * 0.15)
+    x1, y1 = max(0, x1 - px), max(0, y1 - py)
+    x2, y2 = min(ow, x2 + px), min(oh, y2 + py)
+    if x2 <= x1 or y2 <= y1:
+        return None
+    crop = pil_img.crop((x1, y1, x2, y2))
+    arr = np.array(crop)
+    return None if (arr.size == 0 or arr.mean() < 3) else crop
+
+
+def masks_to_crops(pil_img: Image.Image, masks: Dict[str, np.ndarray]) -> Dict[str, Optional[Image.Image]]:
+    """Mask -> bounding box (min/max of the set pixels, reference :85-93) -> crop (reference :95-127)."""
     crops: Dict[str, Optional[Image.Image]] = {}
     for key, mask in masks.items():
         rows = np.flatnonzero(mask.any(axis=1))
         cols = np.flatnonzero(mask.any(axis=0))
-        if rows.size == 0 or cols.size == 0:
-            crops[key] = None
-            continue
-        x1, x2 = int(cols[0] * sx), int(cols[-1] * sx)
-        y1, y2 = int(rows[0] * sy), int(rows[-1] * sy)
-        px, py = int((x2 - x1) * 0.15), int((y2 - y1) * 0.15)
-        x1, y1 = max(0, x1 - px), max(0, y1 - py)
-        x2, y2 = min(ow, x2 + px), min(oh, y2 + py)
-        if x2 <= x1 or y2 <= y1:
-            crops[key] = None
-            continue
-        crop = pil_img.crop((x1, y1, x2, y2))
-        arr = np.array(crop)
-        crops[key] = None if (arr.size == 0 or arr.mean() < 3) else crop
+        extent = None if (rows.size == 0 or cols.size == 0) else (int(cols[0]), int(cols[-1]), int(rows[0]), int(rows[-1]))
+        crops[key] = _crop_from_extent(pil_img, extent)
     return crops
 
 
-def _segment_u8(model: UNet, frames: np.ndarray) -> np.ndarray:
-    """uint8 frames (B, 512, 512, 3) -> uint8 masks (B, 3, 512, 512) through the CUDA engine."""
+def boxes_to_crops(pil_img: Image.Image, boxes: np.ndarray) -> Dict[str, Optional[Image.Image]]:
+    """Same, from the GPU reduction ``prepost.mask_bbox``: ``boxes`` int32 [3, 5] = xmin, xmax, ymin,
+    ymax, count per field."""
+    crops: Dict[str, Optional[Image.Image]] = {}
+    for i, key in enumerate(FIELDS):
+        xmin, xmax, ymin, ymax, count = (int(v) for v in boxes[i])
+        crops[key] = _crop_from_extent(pil_img, None if count == 0 else (xmin, xmax, ymin, ymax))
+    return crops
+
+
+def _require_cuda():
     if DEVICE != "cuda":
         raise RuntimeError("run_unet needs a CUDA (B200, sm_100a) device: there is no CPU path "
                            "(the CPU oracle lives in oracle/ and is test-only)")
+
+
+def _segment_u8(model: UNet, frames: np.ndarray):
+    """uint8 frames (B, 512, 512, 3) -> (uint8 masks (B, 3, 512, 512), int32 boxes (B, 3, 5))."""
+    from . import prepost
+    _require_cuda()
     eng = model.engine(DEVICE)
     thr = [THRESHOLDS[f] for f in FIELDS]
-    out = np.empty((frames.shape[0], len(FIELDS), IMG_SIZE, IMG_SIZE), dtype=np.uint8)
+    masks = np.empty((frames.shape[0], len(FIELDS), IMG_SIZE, IMG_SIZE), dtype=np.uint8)
+    boxes = np.empty((frames.shape[0], len(FIELDS), 5), dtype=np.int32)
     for lo in range(0, frames.shape[0], MAX_CHUNK):
         chunk = torch.from_numpy(np.ascontiguousarray(frames[lo:lo + MAX_CHUNK])).pin_memory()
         x = chunk.to(eng.device, non_blocking=True)
         _, mask = eng.run(x, want_logits=False, thresholds=thr)
-        out[lo:lo + MAX_CHUNK] = mask.cpu().numpy()
+        box = prepost.mask_bbox(mask)
+        masks[lo:lo + MAX_CHUNK] = mask.cpu().numpy()
+        boxes[lo:lo + MAX_CHUNK] = box.cpu().numpy()
+    return masks, boxes
+
+
+def _gpu_resizable(pil_img: Image.Image) -> bool:
+    """Plain 8-bit RGB: the two PIL calls of the reference (:63 resize, :35 convert + resize) reduce
+    to one bicubic resample of the uint8 HWC frame, which prepost.resize_u8 reproduces bit for bit."""
+    return pil_img.mode == "RGB" and pil_img.size[0] > 0 and pil_img.size[1] > 0
+
+
+def _frames_512(pil_imgs: Sequence[Image.Image]) -> np.ndarray:
+    """Resized uint8 frames (B, 512, 512, 3): on the GPU for plain RGB inputs, PIL otherwise."""
+    from . import prepost
+    out = np.empty((len(pil_imgs), IMG_SIZE, IMG_SIZE, 3), dtype=np.uint8)
+    for i, im in enumerate(pil_imgs):
+        if DEVICE == "cuda" and _gpu_resizable(im):
+            raw = torch.from_numpy(np.array(im)).pin_memory().to(DEVICE, non_blocking=True)
+            out[i] = prepost.resize_u8(raw[None], IMG_SIZE, IMG_SIZE)[0].cpu().numpy()
+        else:
+            out[i] = _resized_rgb_u8(im.resize((IMG_SIZE, IMG_SIZE)))
     return out
 
 
@@ -126,12 +168,22 @@ def run_unet(pil_img: Image.Image, checkpoint_path: str):
     ``masks``: dict field -> ``np.bool_`` (512, 512); ``crops``: dict field -> ``PIL.Image`` or
     ``None``; key order = ``FIELDS``.
     """
+    from . import prepost
+    _require_cuda()
     model = load_model(checkpoint_path)
+    eng = model.engine(DEVICE)
+    thr = [THRESHOLDS[f] for f in FIELDS]
     # the reference resizes twice (:63 then :35); the second resize is the identity
-    frame = _resized_rgb_u8(pil_img.resize((IMG_SIZE, IMG_SIZE)))
-    m = _segment_u8(model, frame[None])[0]
+    if _gpu_resizable(pil_img):
+        raw = torch.from_numpy(np.array(pil_img)).pin_memory().to(DEVICE, non_blocking=True)
+        x = prepost.resize_u8(raw[None], IMG_SIZE, IMG_SIZE)        # frame never leaves the GPU
+    else:
+        x = torch.from_numpy(_resized_rgb_u8(pil_img.resize((IMG_SIZE, IMG_SIZE)))[None]).to(DEVICE)
+    _, mask = eng.run(x, want_logits=False, thresholds=thr)
+    boxes = prepost.mask_bbox(mask)
+    m = mask[0].cpu().numpy()
     masks = {f: m[i].astype(bool) for i, f in enumerate(FIELDS)}
-    return masks, masks_to_crops(pil_img, masks)
+    return masks, boxes_to_crops(pil_img, boxes[0].cpu().numpy())
 
 
 def run_unet_batch(pil_imgs: Sequence[Image.Image], checkpoint_path: str
@@ -139,11 +191,11 @@ def run_unet_batch(pil_imgs: Sequence[Image.Image], checkpoint_path: str
     """``run_unet`` for many images with one batched forward per 64 images (new entry point)."""
     if len(pil_imgs) == 0:
         return []
+    _require_cuda()
     model = load_model(checkpoint_path)
-    frames = np.stack([_resized_rgb_u8(im.resize((IMG_SIZE, IMG_SIZE))) for im in pil_imgs])
-    m = _segment_u8(model, frames)
+    m, boxes = _segment_u8(model, _frames_512(pil_imgs))
     out = []
     for b, im in enumerate(pil_imgs):
         masks = {f: m[b, i].astype(bool) for i, f in enumerate(FIELDS)}
-        out.append((masks, masks_to_crops(im, masks)))
+        out.append((masks, boxes_to_crops(im, boxes[b])))
     return out

@@ -1,0 +1,84 @@
+"""GPU pre/post-processing around the forward, via ``libunetb200.so``:
+
+* ``resize_u8``  -- ``PIL.Image.resize((512, 512))`` of reference inference.py:35,63 for uint8
+  frames already on the device, bit-identical to Pillow's 8-bit bicubic resample;
+* ``mask_bbox``  -- the ``np.where(mask)`` min/max of reference inference.py:85-93 as 5 ints per
+  (image, class) instead of a 512x512 mask.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+from typing import Dict, Tuple
+
+import numpy as np
+import torch
+
+from . import _native as nat
+
+_table_cache: Dict[Tuple[int, int, str], Tuple[torch.Tensor, torch.Tensor, int]] = {}
+_lock = threading.Lock()
+
+
+def resize_tables_host(in_size: int, out_size: int):
+    """Pillow's fixed-point coefficient table of one axis: (kk int32 [out, ksize], bounds int32 [out, 2])."""
+    lib = nat.lib()
+    ks = lib.unetb200_resize_ksize(in_size, out_size)
+    if ks <= 0:
+        raise ValueError(f"bad resize {in_size} -> {out_size}")
+    kk = np.zeros((out_size, ks), dtype=np.int32)
+    bounds = np.zeros((out_size, 2), dtype=np.int32)
+    nat.check(lib.unetb200_resize_coeffs(in_size, out_size, kk.ctypes.data, bounds.ctypes.data))
+    return kk, bounds
+
+
+def _tables(in_size: int, out_size: int, device: torch.device):
+    key = (in_size, out_size, str(device))
+    with _lock:
+        t = _table_cache.get(key)
+        if t is None:
+            kk, bounds = resize_tables_host(in_size, out_size)
+            t = (torch.from_numpy(kk).to(device), torch.from_numpy(bounds).to(device), kk.shape[1])
+            if len(_table_cache) > 64:
+                _table_cache.clear()
+            _table_cache[key] = t
+    return t
+
+
+def resize_u8(frames: torch.Tensor, oh: int, ow: int) -> torch.Tensor:
+    """uint8 ``[N, H, W, C]`` on a CUDA device -> uint8 ``[N, oh, ow, C]``, bit-identical to
+    ``PIL.Image.resize((ow, oh))`` (default BICUBIC) of each frame.  Enqueued on the current stream."""
+    if frames.dtype != torch.uint8 or frames.dim() != 4 or not frames.is_cuda:
+        raise RuntimeError("resize_u8 expects a CUDA uint8 [N,H,W,C] tensor")
+    frames = frames.contiguous()
+    n, h, w, c = frames.shape
+    dev = frames.device
+    out = torch.empty((n, oh, ow, c), dtype=torch.uint8, device=dev)
+    kx = bx = ky = by = tmp = None
+    ksx = ksy = 0
+    if ow != w:
+        kx, bx, ksx = _tables(w, ow, dev)
+    if oh != h:
+        ky, by, ksy = _tables(h, oh, dev)
+    if ow != w and oh != h:
+        tmp = torch.empty((n, h, ow, c), dtype=torch.uint8, device=dev)
+    p = lambda t: None if t is None else t.data_ptr()
+    with torch.cuda.device(dev):
+        nat.check(nat.lib().unetb200_resize_bicubic_u8(
+            frames.data_ptr(), n, h, w, c, p(kx), p(bx), ksx, p(ky), p(by), ksy, p(tmp), out.data_ptr(),
+            oh, ow, torch.cuda.current_stream(dev).cuda_stream))
+    return out
+
+
+def mask_bbox(mask: torch.Tensor) -> torch.Tensor:
+    """uint8 ``[N, C, H, W]`` (non-zero = set) -> int32 ``[N, C, 5]`` = xmin, xmax, ymin, ymax, count
+    (empty plane: W, -1, H, -1, 0).  Enqueued on the current stream."""
+    if mask.dtype != torch.uint8 or mask.dim() != 4 or not mask.is_cuda:
+        raise RuntimeError("mask_bbox expects a CUDA uint8 [N,C,H,W] tensor")
+    mask = mask.contiguous()
+    n, c, h, w = mask.shape
+    out = torch.empty((n, c, 5), dtype=torch.int32, device=mask.device)
+    with torch.cuda.device(mask.device):
+        nat.check(nat.lib().unetb200_mask_bbox(mask.data_ptr(), n * c, h, w, out.data_ptr(),
+                                               torch.cuda.current_stream(mask.device).cuda_stream))
+    return out
