@@ -367,6 +367,34 @@ def main():
         lat = {"p50_ms": ts[len(ts) // 2], "p95_ms": ts[int(len(ts) * 0.95)], "calls": len(ts),
                "what": "engine.run on one resident 3x512x512 frame, host-synchronised per call"}
 
+    # ---------------- run_unet end to end (BASELINE.json configs[4]b): 1920x1080 RGB frame -> masks + crops
+    # through the reference-facing entry point with the model cached; GPU resize vs host PIL resize
+    if rank == 0:
+        try:
+            import tempfile
+            from PIL import Image
+            from tw_invoice_unet_ocr_llm_b200 import inference as inf
+            with tempfile.TemporaryDirectory() as d:
+                ckpt = os.path.join(d, "best_unet_model.pth")
+                torch.save(state, ckpt)
+                rgb = Image.fromarray(synthetic_invoices_u8(1, 1080, 1920, seed=11)[0])
+                rgba = rgb.convert("RGBA")
+                res = {}
+                for tag, im in (("gpu_resize", rgb), ("host_pil_resize", rgba)):
+                    ts = []
+                    for i in range(60):
+                        t0 = time.perf_counter()
+                        inf.run_unet(im, ckpt)
+                        if i >= 10:
+                            ts.append((time.perf_counter() - t0) * 1e3)
+                    ts.sort()
+                    res[tag] = {"p50_ms": ts[len(ts) // 2], "p95_ms": ts[int(len(ts) * 0.95)]}
+            if lat is not None:
+                lat["run_unet_1080p"] = res
+        except Exception as e:          # informational only
+            if lat is not None:
+                lat["run_unet_1080p"] = {"error": repr(e)}
+
     # ---------------- CPU baseline (rank 0, N = 1 only): the oracle port on the host cores
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -143,6 +143,23 @@ def _segment_u8(model: UNet, frames: np.ndarray):
     return masks, boxes
 
 
+_staging: Dict[tuple, torch.Tensor] = {}
+
+
+def _upload_rgb(pil_img: Image.Image) -> torch.Tensor:
+    """RGB PIL image -> uint8 [1, H, W, 3] on DEVICE through a cached pinned staging buffer.
+    Callers synchronise (``.cpu()``) before the next call, so the buffer is free to reuse."""
+    arr = np.asarray(pil_img)
+    key = (threading.get_ident(), arr.shape)
+    buf = _staging.get(key)
+    if buf is None:
+        if len(_staging) > 8:
+            _staging.clear()
+        buf = _staging[key] = torch.empty(arr.shape, dtype=torch.uint8).pin_memory()
+    buf.numpy()[...] = arr
+    return buf.to(DEVICE, non_blocking=True)[None]
+
+
 def _gpu_resizable(pil_img: Image.Image) -> bool:
     """Plain 8-bit RGB: the two PIL calls of the reference (:63 resize, :35 convert + resize) reduce
     to one bicubic resample of the uint8 HWC frame, which prepost.resize_u8 reproduces bit for bit."""
@@ -155,8 +172,7 @@ def _frames_512(pil_imgs: Sequence[Image.Image]) -> np.ndarray:
     out = np.empty((len(pil_imgs), IMG_SIZE, IMG_SIZE, 3), dtype=np.uint8)
     for i, im in enumerate(pil_imgs):
         if DEVICE == "cuda" and _gpu_resizable(im):
-            raw = torch.from_numpy(np.array(im)).pin_memory().to(DEVICE, non_blocking=True)
-            out[i] = prepost.resize_u8(raw[None], IMG_SIZE, IMG_SIZE)[0].cpu().numpy()
+            out[i] = prepost.resize_u8(_upload_rgb(im), IMG_SIZE, IMG_SIZE)[0].cpu().numpy()
         else:
             out[i] = _resized_rgb_u8(im.resize((IMG_SIZE, IMG_SIZE)))
     return out
@@ -175,8 +191,7 @@ def run_unet(pil_img: Image.Image, checkpoint_path: str):
     thr = [THRESHOLDS[f] for f in FIELDS]
     # the reference resizes twice (:63 then :35); the second resize is the identity
     if _gpu_resizable(pil_img):
-        raw = torch.from_numpy(np.array(pil_img)).pin_memory().to(DEVICE, non_blocking=True)
-        x = prepost.resize_u8(raw[None], IMG_SIZE, IMG_SIZE)        # frame never leaves the GPU
+        x = prepost.resize_u8(_upload_rgb(pil_img), IMG_SIZE, IMG_SIZE)   # the resized frame never leaves the GPU
     else:
         x = torch.from_numpy(_resized_rgb_u8(pil_img.resize((IMG_SIZE, IMG_SIZE)))[None]).to(DEVICE)
     _, mask = eng.run(x, want_logits=False, thresholds=thr)
