@@ -41,7 +41,7 @@ def chunk_bounds(lo: int, hi: int, chunk: int = MAX_CHUNK) -> List[Tuple[int, in
 
 
 class GpuWorker:
-    """One GPU: engine + two streams + double-buffered device staging."""
+    """One GPU: engine + three streams (upload, compute, download) + double-buffered device staging."""
 
     def __init__(self, state, device, thresholds: Sequence[float] = DEFAULT_THRESHOLDS,
                  chunk: int = MAX_CHUNK):
@@ -51,9 +51,12 @@ class GpuWorker:
         self.chunk = chunk
         self.engine = Engine(state, self.device)
         with torch.cuda.device(self.device):
-            self.copy_stream = torch.cuda.Stream(self.device)
+            self.copy_stream = torch.cuda.Stream(self.device)       # host -> device
             self.compute_stream = torch.cuda.Stream(self.device)
+            self.down_stream = torch.cuda.Stream(self.device)       # device -> host
         self._bufs = {}
+        self._next_slot = 0
+        self._drained = [None, None]     # per staging slot: event of its last device->host copy
 
     def _staging(self, shape_in, shape_out):
         key = (tuple(shape_in[1:]), tuple(shape_out[1:]))
@@ -62,40 +65,55 @@ class GpuWorker:
             self._bufs[key] = [(mk(shape_in), mk(shape_out)) for _ in range(2)]
         return self._bufs[key]
 
-    def segment(self, frames: torch.Tensor, out: torch.Tensor) -> None:
-        """``frames`` uint8 [B,H,W,3] (pinned host) -> ``out`` uint8 [B,3,H,W] (pinned host).
-
-        Per chunk: H2D on the copy stream, forward on the compute stream, D2H on the copy
-        stream; chunk i+1's upload overlaps chunk i's forward."""
-        b, h, w, _ = frames.shape
+    def segment_async(self, frames: torch.Tensor, out: torch.Tensor) -> None:
+        """Enqueue ``frames`` uint8 [B,H,W,3] (pinned host) -> ``out`` uint8 [B,3,H,W] (pinned host)
+        and return without waiting.  Per chunk: H2D on the upload stream, forward on the compute
+        stream, D2H on the download stream; the upload of the next chunk (or of the next call) and
+        the download of the previous one overlap the forward of the current one.  ``out`` is valid
+        after :meth:`synchronize`."""
+        b = frames.shape[0]
         bufs = self._staging(frames.shape, out.shape)
-        cs, ks = self.copy_stream, self.compute_stream
+        cs, ks, ds = self.copy_stream, self.compute_stream, self.down_stream
         with torch.cuda.device(self.device):
-            ready = [torch.cuda.Event() for _ in range(2)]     # upload of slot done
-            done = [torch.cuda.Event() for _ in range(2)]      # forward of slot done
-            drained = [None, None]                             # download of slot done
-            for i, (lo, hi) in enumerate(chunk_bounds(0, b, self.chunk)):
-                slot = i & 1
+            for lo, hi in chunk_bounds(0, b, self.chunk):
+                slot = self._next_slot
+                self._next_slot ^= 1
                 xin, mout = bufs[slot]
                 n = hi - lo
+                ready, done, drained = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
                 with torch.cuda.stream(cs):
-                    if drained[slot] is not None:
-                        cs.wait_event(drained[slot])
+                    if self._drained[slot] is not None:        # slot's previous masks have left the device
+                        cs.wait_event(self._drained[slot])
                     xin[:n].copy_(frames[lo:hi], non_blocking=True)
-                    ready[slot].record(cs)
+                    ready.record(cs)
                 with torch.cuda.stream(ks):
-                    ks.wait_event(ready[slot])
+                    ks.wait_event(ready)
                     self.engine.run(xin[:n], want_logits=False, thresholds=self.thresholds,
                                     mask_out=mout[:n])
-                    done[slot].record(ks)
-                with torch.cuda.stream(cs):
-                    cs.wait_event(done[slot])
+                    done.record(ks)
+                with torch.cuda.stream(ds):
+                    ds.wait_event(done)
                     out[lo:hi].copy_(mout[:n], non_blocking=True)
-                    ev = torch.cuda.Event()
-                    ev.record(cs)
-                    drained[slot] = ev
-            cs.synchronize()
-            ks.synchronize()
+                    drained.record(ds)
+                    self._drained[slot] = drained
+
+    def synchronize(self) -> None:
+        """Block until everything enqueued by :meth:`segment_async` has landed in host memory."""
+        self.copy_stream.synchronize()
+        self.compute_stream.synchronize()
+        self.down_stream.synchronize()
+
+    def join_current_stream(self) -> None:
+        """Make the caller's current stream wait for all enqueued work (for CUDA-event timing)."""
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_stream(self.copy_stream)
+        cur.wait_stream(self.compute_stream)
+        cur.wait_stream(self.down_stream)
+
+    def segment(self, frames: torch.Tensor, out: torch.Tensor) -> None:
+        """Synchronous form: enqueue, then wait until ``out`` is complete."""
+        self.segment_async(frames, out)
+        self.synchronize()
 
 
 class MultiGpuSegmenter:
