@@ -527,6 +527,19 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
         const int q = warp & 3;                 // TMEM lane quarter this warp may access (warp id % 4)
         const int row = q * 32 + lane;          // pixel row of the tile: h = row/8, w = row%8
         const int estep = p.n_epi;              // tiles between two tiles of this group
+        // BN == 64 launches (one 64-column chunk per tile, in production a single column block): the
+        // chunk's 64 bias values live in registers and are reloaded only when the channel offset
+        // changes (the thin-K epilogues stalled on their shared-memory loads)
+        constexpr bool kBiasRegs = BN == 64 && AMODE != A_STEM;   // (the 640-thread stem has 102 registers per thread)
+        float bias_r[kBiasRegs ? 64 : 1];
+        int bias_ch0 = -1;
+        auto load_bias = [&](int ch0) {
+            if (kBiasRegs && ch0 != bias_ch0) {
+#pragma unroll
+                for (int i = 0; i < (kBiasRegs ? 64 : 1); ++i) bias_r[i] = s_bias[ch0 + i];
+                bias_ch0 = ch0;
+            }
+        };
         uint32_t tile_it = eg, chunk_it = 0;
         // hand-back of an accumulator: arrive on the (leader's) barrier the MMA issuer waits on
         auto release_acc = [&](uint32_t acc) {
@@ -547,6 +560,7 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
             const uint32_t t_addr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
 
             if (EPI == EPI_HEAD) {
+                load_bias(0);
                 // out_conv 1x1 (unet_model.py:86) from the fp32 accumulators, NC classes at once;
                 // s_head_w rows past n_classes are zero so the generic variant needs no predicates
                 constexpr int NC = X > 0 ? X : kMaxClasses;
@@ -560,7 +574,8 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
                     tmem_ld_wait();
 #pragma unroll
                     for (int i = 0; i < 32; i += 4) {
-                        const float4 b4 = *reinterpret_cast<const float4*>(s_bias + half * 32 + i);
+                        const float4 b4 = make_float4(bias_r[half * 32 + i], bias_r[half * 32 + i + 1],
+                                                      bias_r[half * 32 + i + 2], bias_r[half * 32 + i + 3]);
                         float f0 = __uint_as_float(v[i + 0]) + b4.x;
                         float f1 = __uint_as_float(v[i + 1]) + b4.y;
                         float f2 = __uint_as_float(v[i + 2]) + b4.z;
@@ -603,6 +618,7 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
                 const int gcol = nb * BN + j * 64;            // global column of this 64-wide chunk
                 const int tapo = EPI == EPI_UPSAMPLE ? gcol / p.Cout : 0;
                 const int ch0 = EPI == EPI_UPSAMPLE ? gcol - tapo * p.Cout : gcol;
+                load_bias(ch0);
                 // Each warp owns a quarter of the tile (4 pixel rows): its own 4 KB slab of the staging
                 // slot, its own TMA stores, its own bulk groups -- no barrier between the four warps.
                 // Each group owns n_out slots; a slab was last read by this warp's store n_out chunks ago.
@@ -621,7 +637,14 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
                     tmem_ld_wait();
 #pragma unroll
                     for (int i = 0; i < 32; i += 4) {
-                        const float4 b4 = *reinterpret_cast<const float4*>(s_bias + ch0 + half * 32 + i);
+                        float4 b4;
+                        if (kBiasRegs) {
+                            constexpr int o = kBiasRegs ? 1 : 0;     // (keeps the indices in range otherwise)
+                            b4 = make_float4(bias_r[o * (half * 32 + i)], bias_r[o * (half * 32 + i + 1)],
+                                             bias_r[o * (half * 32 + i + 2)], bias_r[o * (half * 32 + i + 3)]);
+                        } else {
+                            b4 = *reinterpret_cast<const float4*>(s_bias + ch0 + half * 32 + i);
+                        }
                         float f0 = __uint_as_float(v[i + 0]) + b4.x;
                         float f1 = __uint_as_float(v[i + 1]) + b4.y;
                         float f2 = __uint_as_float(v[i + 2]) + b4.z;
