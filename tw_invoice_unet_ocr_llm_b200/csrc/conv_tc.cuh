@@ -219,9 +219,9 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
 
     if (AMODE == A_STEM && warp >= 12) {
         // ================== im2col producer (first conv only) =================
-        // thread r builds A row r = output pixel (y0 + r/8, x0 + r%8) of the tile:
-        //   slice 0 (ring item 0): k in [0,32) = bf16 hi of the 9*CIN taps, [32,64) = bf16 lo
-        //   slice 1 (ring item 1): k in [0,32) = hi again (multiplies w_lo); upper half unused
+        // thread r builds A row r = output pixel (y0 + r/8, x0 + r%8) of the tile, one ring item:
+        //   k in [0,32) = bf16 hi of the 9*CIN taps, k in [32,64) = bf16 lo.
+        // The MMA warp multiplies the whole row by [w_hi | w_hi] and the hi half again by w_lo.
         constexpr int CI = CIN > 0 ? CIN : 1;                    // (CIN == 0 only in dead instantiations)
         constexpr int KS = 9 * CI;
         constexpr int PE = CI * 180;                             // patch elements: [CIN][18][10]
@@ -230,17 +230,24 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
         const int r = (threadIdx.x - 384) & 127;
         float* s_patch = reinterpret_cast<float*>(smem_gen + p.off_patch) + grp * 2 * PE;
         const int hh = r >> 3, ww = r & 7;
+        // patch elements this thread fetches, fixed for the whole kernel: (ci, dy, dx) packed
+        int ecode[NL];
+#pragma unroll
+        for (int i = 0; i < NL; ++i) {
+            const int e = r + i * 128;
+            const int ci = e / 180, rem = e - ci * 180;
+            ecode[i] = e < PE ? ((ci << 16) | ((rem / 10) << 8) | (rem % 10)) : -1;
+        }
         auto fetch = [&](int t, float (&regs)[NL]) {
             const int n = t / tiles_per_img;
             const int rr = t - n * tiles_per_img;
             const int y0 = (rr / p.tiles_x) * 16 - 1, x0 = (rr % p.tiles_x) * 8 - 1;
 #pragma unroll
             for (int i = 0; i < NL; ++i) {
-                const int e = r + i * 128;
                 float v = 0.f;
-                if (e < PE) {
-                    const int ci = e / 180, rem = e - ci * 180;
-                    const int y = y0 + rem / 10, x = x0 + rem % 10;
+                if (ecode[i] >= 0) {
+                    const int ci = ecode[i] >> 16;
+                    const int y = y0 + ((ecode[i] >> 8) & 0xff), x = x0 + (ecode[i] & 0xff);
                     if (y >= 0 && y < p.H && x >= 0 && x < p.W) {
                         if (p.stem_fmt == 0) {
                             v = __ldg(static_cast<const float*>(p.stem_x) +
@@ -295,12 +302,11 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
                 h[1] = __uint_as_float(hi[k2] & 0xffff0000u);
                 lo[k2] = pack_bf16x2(v[0] - h[0], v[1] - h[1]);
             }
-            // ring items of this CTA-local tile (2 * it + grp): slice 0 then slice 1
-            const uint32_t item0 = 2u * (2u * static_cast<uint32_t>(it) + grp);
-            const uint32_t na = static_cast<uint32_t>(p.na);
-            // ---- slice 0: [hi | lo]
+            // ring item of this CTA-local tile (2 * it + grp)
             {
-                const uint32_t sa = item0 % na, pa = (item0 / na) & 1;
+                const uint32_t item = 2u * static_cast<uint32_t>(it) + grp;
+                const uint32_t na = static_cast<uint32_t>(p.na);
+                const uint32_t sa = item % na, pa = (item / na) & 1;
                 mbar_wait(bar_a_empty + 8 * sa, pa ^ 1, 1, p.dbg);
                 const uint32_t row = sA + sa * Cfg::A_STAGE + r * 128;
 #pragma unroll
@@ -308,17 +314,6 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
                     st_shared_v4(row + ((c ^ (r & 7)) << 4), hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
                     st_shared_v4(row + (((c + 4) ^ (r & 7)) << 4), lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
                 }
-                fence_proxy_async_smem();
-                mbar_arrive(bar_a_full + 8 * sa);
-            }
-            // ---- slice 1: [hi | (unused)]
-            {
-                const uint32_t sa = (item0 + 1) % na, pa = ((item0 + 1) / na) & 1;
-                mbar_wait(bar_a_empty + 8 * sa, pa ^ 1, 2, p.dbg);
-                const uint32_t row = sA + sa * Cfg::A_STAGE + r * 128;
-#pragma unroll
-                for (int c = 0; c < 4; ++c)
-                    st_shared_v4(row + ((c ^ (r & 7)) << 4), hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
                 fence_proxy_async_smem();
                 mbar_arrive(bar_a_full + 8 * sa);
             }
@@ -384,12 +379,14 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
             const int row_off = PAIR ? static_cast<int>(rank) * (BN / 2) : 0;   // this CTA's half of the weight rows
             if (p.wstat) {
                 // whole weight slab of this layer, once: slot = cs * TAPS + tap
-                const uint32_t bytes = static_cast<uint32_t>(n_cs * TAPS) * Cfg::B_TAP;
+                // (stem: two K slices of weights, [w_hi | w_hi] and [w_lo | 0], for its single activation slice)
+                const int n_wcs = AMODE == A_STEM ? 2 : n_cs;
+                const uint32_t bytes = static_cast<uint32_t>(n_wcs * TAPS) * Cfg::B_TAP;
                 const uint32_t fb = PAIR ? mapa_shared(bar_b_full, 0) : bar_b_full;
                 if (!PAIR) mbar_expect_tx(bar_b_full, bytes);
                 else if (rank == 0) mbar_expect_tx(bar_b_full, 2 * bytes);
                 else mbar_arrive_cluster(fb);
-                for (int cs = 0; cs < n_cs; ++cs)
+                for (int cs = 0; cs < n_wcs; ++cs)
                     for (int tap = 0; tap < TAPS; tap += Cfg::TPB) {      // one box = TPB consecutive taps
                         const uint32_t dst = sB + (cs * TAPS + tap) * Cfg::B_TAP;
                         if (PAIR) tma_load_3d_pair(dst, &p.tmB, fb, cs << 6, row_off, tap);
@@ -477,10 +474,14 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
                                     const uint32_t tap_r = (TAPS == 9 && AMODE != A_HALO) ? item * (AMODE == A_COL3 ? 1 : TPA) : 0;
                                     const uint32_t b_lo = b_cs + (tap_c + tap_r) * (Cfg::B_TAP >> 4);
 #pragma unroll
-                                    for (int k = 0; k < 4; ++k) {
-                                        if (AMODE == A_STEM && cs == 1 && k >= 2) break;   // slice 1 holds 32 taps only
+                                    for (int k = 0; k < 4; ++k)
                                         mma(a_lo0 + a_view(tt) + 2 * k, b_lo + 2 * k, (tt | k) ? 1u : accumulate);
-                                    }
+                                }
+                                if (AMODE == A_STEM) {
+                                    // x_hi * w_lo: the hi half of the row (K = 32) against the second weight slice
+#pragma unroll
+                                    for (int k = 0; k < 2; ++k)
+                                        mma(a_lo0 + 2 * k, b_lo0 + (Cfg::B_TAP >> 4) + 2 * k, 1u);
                                 }
                                 commit(bar_a_empty + 8 * sa);
                                 if (last_item) commit(bar_t_full + 8 * acc);

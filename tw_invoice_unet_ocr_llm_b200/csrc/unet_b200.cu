@@ -382,7 +382,7 @@ int build_conv_step(const ConvDesc& d, int num_sms, Step* st) {
     const bool stem = d.amode == ub::A_STEM;
     if (d.c0 <= 0 || d.c0 % 64 || d.c1 % 64 || d.c1 < 0)
         return fail(UNETB200_EINVAL, "conv: source channels must be multiples of 64");
-    if (stem && (d.taps != 1 || d.cout != 64 || d.c0 != 128 || d.c1 != 0 || !d.stem_x ||
+    if (stem && (d.taps != 1 || d.cout != 64 || d.c0 != 64 || d.c1 != 0 || !d.stem_x ||
                  d.epi != ub::EPI_STORE))
         return fail(UNETB200_EINVAL, "stem: bad configuration");
     if (d.cout % 64) return fail(UNETB200_EINVAL, "conv: cout must be a multiple of 64");
@@ -419,7 +419,7 @@ int build_conv_step(const ConvDesc& d, int num_sms, Step* st) {
             p.tmA1 = p.tmA0;
         }
     }
-    const int cin = d.c0 + d.c1;
+    const int cin = stem ? 128 : d.c0 + d.c1;      // K extent of the packed weights (stem: hi/lo layout)
     if ((rc = make_w_map(&p.tmB, d.w, cin, cols, d.taps == 9 ? 9 : 1, st->conv.pair ? bn / 2 : bn, st->conv.tpb)))
         return rc;
     if (d.epi == ub::EPI_UPSAMPLE) {
@@ -558,7 +558,7 @@ int build_stem_tc_step(const void* x, int x_fmt, int cin, const void* w_tc, cons
         return fail(UNETB200_EINVAL, "unknown x_fmt");
     if (!(cin == 1 || cin == 3)) return fail(UNETB200_EINVAL, "tensor-core stem: n_channels must be 1 or 3");
     ConvDesc d;
-    d.c0 = 128; d.w = w_tc; d.bias = bias; d.n = n; d.h = h; d.wd = wd; d.cout = 64; d.relu = 1;
+    d.c0 = 64; d.w = w_tc; d.bias = bias; d.n = n; d.h = h; d.wd = wd; d.cout = 64; d.relu = 1;
     d.taps = 1; d.epi = ub::EPI_STORE; d.out = out; d.bn = 64; d.amode = ub::A_STEM;
     d.stem_x = x; d.stem_fmt = x_fmt; d.stem_cin = cin; d.dbg = dbg;
     return build_conv_step(d, num_sms, st);
