@@ -185,6 +185,32 @@ def test_batch_independence(model, cuda_dev):
     assert torch.equal(zb, zs)
 
 
+@pytest.mark.parametrize("n_channels,n_classes", [(1, 2), (4, 5), (3, 8), (3, 1)])
+def test_other_channel_and_class_counts(cuda_dev, n_channels, n_classes):
+    """UNet(n_channels, n_classes) other than the reference's (3, 3): the generic head epilogue,
+    the 1-channel tensor-core stem and the 4-channel CUDA-core stem, against the oracle."""
+    from oracle.unet_oracle import oracle_forward
+    from tw_invoice_unet_ocr_llm_b200.unet_model import UNet
+    torch.manual_seed(7 + n_channels + n_classes)
+    m = UNet(n_channels=n_channels, n_classes=n_classes)
+    with torch.no_grad():
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.BatchNorm2d):
+                mod.running_mean.normal_(0, 0.1)
+                mod.running_var.uniform_(0.5, 1.5)
+                mod.weight.uniform_(0.8, 1.6)
+                mod.bias.normal_(0, 0.1)
+        m.out_conv.weight.mul_(8.0)
+    m = m.to(cuda_dev).eval()
+    x = torch.rand(2, n_channels, 32, 48)
+    with torch.no_grad():
+        z = m(x.to(cuda_dev))
+    ref = oracle_forward({k: v.cpu() for k, v in m.state_dict().items()}, x)
+    assert z.shape == ref.shape == (2, n_classes, 32, 48)
+    err = (z.cpu() - ref).abs()
+    assert float(err.max()) <= 0.05 * float(ref.std()) + 0.02, (float(err.max()), float(ref.std()))
+
+
 def test_errors(model, cuda_dev):
     with pytest.raises(RuntimeError):
         model(torch.zeros(1, 3, 500, 500, device=cuda_dev))     # not divisible by 16 (reference raises too)

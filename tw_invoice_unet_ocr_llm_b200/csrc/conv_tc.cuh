@@ -611,11 +611,10 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
                         }
                     }
                 }
-                continue;
             }
 
 #pragma unroll 1
-            for (int j = 0; j < BN / 64; ++j, ++chunk_it) {
+            for (int j = 0; j < (EPI == EPI_HEAD ? 0 : BN / 64); ++j, ++chunk_it) {
                 const int gcol = nb * BN + j * 64;            // global column of this 64-wide chunk
                 const int tapo = EPI == EPI_UPSAMPLE ? gcol / p.Cout : 0;
                 const int ch0 = EPI == EPI_UPSAMPLE ? gcol - tapo * p.Cout : gcol;

@@ -97,12 +97,14 @@ class Engine:
     def workspace_bytes(self, n: int, h: int, w: int) -> int:
         return int(self._lib.unetb200_workspace_bytes(self._handle, n, h, w))
 
-    def _workspace(self, n: int, h: int, w: int) -> torch.Tensor:
+    def _workspace(self, n: int, h: int, w: int):
+        """(pointer, bytes) of a 1024-byte aligned scratch region big enough for this shape."""
         need = self.workspace_bytes(n, h, w)
-        if self._ws is None or self._ws.numel() < need:
+        if self._ws is None or self._ws.numel() < need + 1024:
             self._ws = None
-            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
-        return self._ws
+            self._ws = torch.empty(need + 1024, dtype=torch.uint8, device=self.device)
+        ptr = (self._ws.data_ptr() + 1023) & ~1023          # small torch blocks are only 512-byte aligned
+        return ptr, self._ws.numel() - (ptr - self._ws.data_ptr())
 
     # ------------------------------------------------------------------ forward
     def run(self, x: torch.Tensor, *, want_logits: bool = True,
@@ -134,7 +136,7 @@ class Engine:
         x = x.contiguous()
         thr = None
         with self._lock, torch.cuda.device(self.device):
-            ws = self._workspace(n, h, w)
+            ws_ptr, ws_bytes = self._workspace(n, h, w)
             logits = None
             if want_logits:
                 logits = logits_out if logits_out is not None else torch.empty(
@@ -148,7 +150,7 @@ class Engine:
                     (n, self.n_classes, h, w), dtype=torch.uint8, device=self.device)
             stream = torch.cuda.current_stream(self.device).cuda_stream
             nat.check(self._lib.unetb200_forward(
-                self._handle, x.data_ptr(), fmt, n, h, w, ws.data_ptr(), ws.numel(),
+                self._handle, x.data_ptr(), fmt, n, h, w, ws_ptr, ws_bytes,
                 _ptr(logits), _ptr(mask), thr, stream))
         return logits, mask
 
