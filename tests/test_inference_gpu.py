@@ -103,3 +103,44 @@ def test_launcher_single_gpu_matches_engine(fixture_state, cuda_dev):
     eng = Engine(fixture_state, cuda_dev)
     _, m = eng.run(torch.from_numpy(frames).to(cuda_dev), want_logits=False, thresholds=[0.25, 0.40, 0.30])
     assert torch.equal(out, m.cpu())
+
+
+def test_concurrent_run_unet_threads(checkpoint, cuda_dev):
+    """Streamlit runs each session in its own thread of one process and they share the cached model
+    (SURVEY.md 8b "Threading"): concurrent run_unet calls must give the single-threaded answers."""
+    import threading
+    from tw_invoice_unet_ocr_llm_b200 import inference as inf
+    from tw_invoice_unet_ocr_llm_b200.synthetic import synthetic_invoices_u8
+    pils = [Image.fromarray(f) for f in synthetic_invoices_u8(4, 480, 640, seed=81)]
+    ref = [inf.run_unet(p, checkpoint)[0] for p in pils]
+    got = [None] * len(pils)
+    errs = []
+
+    def work(i):
+        try:
+            for _ in range(3):
+                got[i] = inf.run_unet(pils[i], checkpoint)[0]
+        except BaseException as e:
+            errs.append(e)
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(len(pils))]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errs, errs
+    for r, g in zip(ref, got):
+        for k in inf.FIELDS:
+            assert np.array_equal(r[k], g[k])
+
+
+def test_multi_gpu_segmenter_all_devices(fixture_state, cuda_dev):
+    """Batch sharded over every visible GPU == the single-GPU result, bit for bit.
+    With one GPU visible this still exercises the threaded launcher path."""
+    from tw_invoice_unet_ocr_llm_b200.launcher import MultiGpuSegmenter
+    from tw_invoice_unet_ocr_llm_b200.synthetic import synthetic_invoices_u8
+    frames = synthetic_invoices_u8(9, 64, 64, seed=82)
+    one = MultiGpuSegmenter(fixture_state, devices=["cuda:0"], chunk=4).segment(frames)
+    n = torch.cuda.device_count()
+    every = MultiGpuSegmenter(fixture_state, devices=[f"cuda:{i}" for i in range(n)], chunk=4).segment(frames)
+    assert torch.equal(one, every)
