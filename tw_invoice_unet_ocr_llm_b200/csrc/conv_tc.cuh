@@ -29,11 +29,11 @@
 //             address (validated on hardware by tests/test_conv_kernels.py).
 // TMA zero-fills out-of-bounds box elements, which is the conv zero padding.
 //   A_STEM  : first conv of the network (Cin = n_channels <= 3, K = 9*Cin <= 27): eight extra
-//             warps (two groups of 128 threads taking alternate tiles) build the im2col rows themselves, straight from the user's fp32 NCHW /
-//             uint8 NHWC tensor, as bf16 hi + lo pairs (x = hi + lo to 16 significand bits);
-//             the GEMM is x_hi*w_hi + x_lo*w_hi + x_hi*w_lo over two 64-wide K slices, i.e.
-//             fp32-class accuracy from bf16 MMAs.  The layer is HBM-bound (it writes 64 bf16
-//             channels per pixel), the extra MMAs are free.
+//             warps (two groups of 128 threads taking alternate tiles) build the im2col rows
+//             themselves, straight from the user's fp32 NCHW / uint8 NHWC tensor, as bf16
+//             hi | lo halves of one 64-wide K slice (x = hi + lo to 16 significand bits); the GEMM
+//             is [x_hi | x_lo] * [w_hi | w_hi] + x_hi * w_lo, i.e. fp32-class accuracy from bf16
+//             MMAs.  The layer is HBM-bound (64 bf16 channels out per pixel); the MMAs are free.
 //
 // Warp roles (384 threads, 1 CTA / SM, persistent over tiles):
 //   warp 0 : TMA producer, activations      warp 1 : MMA issuer (one elected lane)
