@@ -128,3 +128,27 @@ def test_package_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+
+
+def test_shims_expose_the_reference_module_names():
+    """shims/ first on sys.path makes `from inference import run_unet` / `from unet_model import UNet`
+    (reference app_camera.py:16, inference.py:4, train.py:12) resolve to this package."""
+    import importlib
+    import sys
+    shim_dir = os.path.join(ROOT, "shims")
+    saved = {k: sys.modules.pop(k, None) for k in ("inference", "unet_model")}
+    sys.path.insert(0, shim_dir)
+    try:
+        inf = importlib.import_module("inference")
+        um = importlib.import_module("unet_model")
+        from tw_invoice_unet_ocr_llm_b200 import inference as pkg_inf
+        from tw_invoice_unet_ocr_llm_b200 import unet_model as pkg_um
+        assert inf.run_unet is pkg_inf.run_unet and inf.load_model is pkg_inf.load_model
+        assert inf.preprocess is pkg_inf.preprocess and inf.IMG_SIZE == 512
+        assert um.UNet is pkg_um.UNet and um.DoubleConv is pkg_um.DoubleConv
+    finally:
+        sys.path.remove(shim_dir)
+        for k, v in saved.items():
+            sys.modules.pop(k, None)
+            if v is not None:
+                sys.modules[k] = v
