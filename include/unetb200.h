@@ -89,7 +89,7 @@ int unetb200_create(const unetb200_arch_t* arch, const void* blob_dev, uint64_t 
                     int device, unetb200_handle_t* out);
 int unetb200_destroy(unetb200_handle_t h);
 
-/* options: "amode" (UNETB200_A_*), "bn_max" (64/128/256), "wstat" (0/1), "stem_tc" (0/1), "pair" (0 never / 1 everywhere / 2 auto),
+/* options: "amode" (UNETB200_A_*), "bn_max" (64/128/256), "wstat" (0/1), "stem_tc" (first conv: 0 CUDA cores / 1 tensor cores + im2col / 2 tensor cores, implicit GEMM), "pair" (0 never / 1 everywhere / 2 auto),
  * "pdl" (0/1 programmatic dependent launch), "epi2" (two epilogue groups: 0 never / 1 weight-stationary launches / 2 always), "pf_items" (0..64), "profile" (0/1) */
 int unetb200_set_option(unetb200_handle_t h, const char* key, int value);
 int unetb200_get_option(unetb200_handle_t h, const char* key, int* value);
@@ -137,6 +137,11 @@ int unetb200_convt2x2(const void* src, int cin, const void* w_packed, const floa
 int unetb200_stem_tc(const void* x, int x_fmt, int cin, const void* w_tc, const float* bias, int n,
                      int height, int width, void* out, void* stream);
 uint64_t unetb200_stem_tc_offset(int cin);
+/* First conv on the tensor cores as an implicit GEMM over a shared-memory input patch (n_channels 1, 3
+ * or 4; an alternative to unetb200_stem_tc, measured slower): w_patch = blob + w_off + unetb200_stem_patch_offset(cin). */
+int unetb200_stem_patch(const void* x, int x_fmt, int cin, const void* w_patch, const float* bias, int n,
+                        int height, int width, void* out, void* stream);
+uint64_t unetb200_stem_patch_offset(int cin);
 /* First conv (n_channels -> 64) + ReLU on the CUDA cores (any n_channels in {1,3,4}):
  * x (format x_fmt) -> out [N,H,W,64] bf16. w fp32 [9*cin][64] (start of the stem's blob region). */
 int unetb200_stem(const void* x, int x_fmt, int cin, const float* w, const float* bias, int n,

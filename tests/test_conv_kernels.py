@@ -140,9 +140,10 @@ def test_stem(cuda_dev, fmt):
     _close(_to_nchw_f32(out), ref, f"stem {fmt}")
 
 
+@pytest.mark.parametrize("variant", ["im2col", "patch"])
 @pytest.mark.parametrize("fmt", ["f32", "u8"])
 @pytest.mark.parametrize("n,h,w", [(2, 40, 48), (1, 16, 16), (3, 4, 6)])
-def test_stem_tensor_core(cuda_dev, fmt, n, h, w):
+def test_stem_tensor_core(cuda_dev, fmt, n, h, w, variant):
     """First conv on the tensor cores: in-kernel im2col, bf16 hi/lo split GEMM.  Must be as
     accurate as the fp32 CUDA-core stem (error dominated by the single bf16 output rounding),
     and exercises unetb200_pack_layer's BatchNorm fold for layer 0."""
@@ -164,12 +165,17 @@ def test_stem_tensor_core(cuda_dev, fmt, n, h, w):
                                             beta.data_ptr(), mean.data_ptr(), var.data_ptr(), 1e-5,
                                             blob.data_ptr(), None))
     l0 = layers[0]
-    w_tc = blob.data_ptr() + l0.w_off + int(nat.lib().unetb200_stem_tc_offset(3))
     bias = blob.data_ptr() + l0.b_off
     out = torch.full((n, h, w, 64), float("nan"), dtype=torch.bfloat16, device=cuda_dev)
     src = xf if fmt == "f32" else u8.to(cuda_dev)
-    nat.check(nat.lib().unetb200_stem_tc(src.data_ptr(), 0 if fmt == "f32" else 1, 3, w_tc, bias,
-                                         n, h, w, out.data_ptr(), None))
+    if variant == "im2col":
+        w_tc = blob.data_ptr() + l0.w_off + int(nat.lib().unetb200_stem_tc_offset(3))
+        nat.check(nat.lib().unetb200_stem_tc(src.data_ptr(), 0 if fmt == "f32" else 1, 3, w_tc, bias,
+                                             n, h, w, out.data_ptr(), None))
+    else:
+        w_p = blob.data_ptr() + l0.w_off + int(nat.lib().unetb200_stem_patch_offset(3))
+        nat.check(nat.lib().unetb200_stem_patch(src.data_ptr(), 0 if fmt == "f32" else 1, 3, w_p, bias,
+                                                n, h, w, out.data_ptr(), None))
     torch.cuda.synchronize()
     ref = F.relu(F.batch_norm(F.conv2d(xf, wt, b, padding=1), mean, var, gamma, beta, False, 0.0, 1e-5))
     got = _to_nchw_f32(out)

@@ -158,6 +158,26 @@ def test_cta_pairs_identical(model, cuda_dev):
     assert torch.equal(z0, z1)
 
 
+def test_stem_variants_agree(model, cuda_dev):
+    """The three first-conv implementations (CUDA cores fp32, tensor cores + im2col, tensor cores
+    implicit GEMM; the last two with the bf16 hi/lo split) agree to the accuracy of one bf16 rounding
+    of the 64-channel stem output, so the logits stay within a small fraction of the tolerance."""
+    from tw_invoice_unet_ocr_llm_b200.synthetic import synthetic_invoices
+    x = synthetic_invoices(2, 64, 96, seed=53).to(cuda_dev)
+    eng = model.engine(cuda_dev)
+    keep = eng.get_option("stem_tc")
+    z = {}
+    try:
+        for v in (0, 1, 2):
+            eng.set_option("stem_tc", v)
+            z[v], _ = eng.run(x)
+        torch.cuda.synchronize()
+    finally:
+        eng.set_option("stem_tc", keep)
+    assert (z[1] - z[2]).abs().max().item() < 0.15  # same products, different fp32 summation order
+    assert (z[0] - z[2]).abs().max().item() < 0.15
+
+
 def test_u8_input_and_masks(model, fixture_state, cuda_dev):
     """uint8 NHWC ingest (/255 in-kernel, inference.py:36) == float path, bit for bit; fused
     logit-space threshold == sigmoid(z) > t on the returned logits (inference.py:72-79)."""

@@ -62,6 +62,8 @@ SYMBOLS = {
     "unetb200_stem": (_I, [_VP, _I, _I, _VP, _VP, _I, _I, _I, _VP, _VP]),
     "unetb200_stem_tc": (_I, [_VP, _I, _I, _VP, _VP, _I, _I, _I, _VP, _VP]),
     "unetb200_stem_tc_offset": (_U64, [_I]),
+    "unetb200_stem_patch": (_I, [_VP, _I, _I, _VP, _VP, _I, _I, _I, _VP, _VP]),
+    "unetb200_stem_patch_offset": (_U64, [_I]),
     "unetb200_resize_ksize": (_I, [_I, _I]),
     "unetb200_resize_coeffs": (_I, [_I, _I, _VP, _VP]),
     "unetb200_resize_bicubic_u8": (_I, [_VP, _I, _I, _I, _I, _VP, _VP, _I, _VP, _VP, _I, _VP, _VP, _I, _I, _VP]),

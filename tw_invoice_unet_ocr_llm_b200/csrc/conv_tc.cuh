@@ -34,6 +34,11 @@
 //             hi | lo halves of one 64-wide K slice (x = hi + lo to 16 significand bits); the GEMM
 //             is [x_hi | x_lo] * [w_hi | w_hi] + x_hi * w_lo, i.e. fp32-class accuracy from bf16
 //             MMAs.  The layer is HBM-bound (64 bf16 channels out per pixel); the MMAs are free.
+//   A_STEMP : the same first conv as an implicit GEMM like A_HALO, without im2col: four extra warps
+//             write the 18x10 input halo patch of the tile ONCE as 32-byte pixels (16 B of bf16 hi
+//             of the <= 8 channels | 16 B of bf16 lo), SWIZZLE_32B K-major layout; each tap is a
+//             pair of K = 16 UMMAs on the patch shifted by (ky*10+kx) pixels (8-row group stride =
+//             one patch row = 320 B), against [w_hi | w_hi] and [w_lo | 0].
 //
 // Warp roles (384 threads, 1 CTA / SM, persistent over tiles):
 //   warp 0 : TMA producer, activations      warp 1 : MMA issuer (one elected lane)
@@ -63,7 +68,7 @@
 namespace ub {
 
 enum : int { EPI_STORE = 0, EPI_STORE_POOL = 1, EPI_HEAD = 2, EPI_UPSAMPLE = 3 };
-enum : int { A_TAP = 0, A_COL3 = 1, A_HALO = 2, A_STEM = 3 };
+enum : int { A_TAP = 0, A_COL3 = 1, A_HALO = 2, A_STEM = 3, A_STEMP = 4 };
 
 constexpr int kMaxClasses = 8;
 
@@ -95,8 +100,9 @@ struct ConvParams {
     int pf_items;            // activation items prefetched into L2 ahead of the smem ring (0 = off)
     int off_b, off_out, off_pool, off_bar;   // smem carve-up, bytes from the 1024-aligned base
     int off_patch;           // A_STEM: 2 x [Cin][18][10] fp32 input halo patches
-    const void* stem_x;      // A_STEM: network input (format stem_fmt), see stem.cuh
+    const void* stem_x;      // A_STEM / A_STEMP: network input (format stem_fmt), see stem.cuh
     int stem_fmt;
+    const void* stem_w;      // A_STEMP: weights already in the smem tile layout (pack.cuh), 9 x 4096 B
 };
 
 template <int BN, int TAPS, int AMODE, bool PAIR = false>
@@ -104,8 +110,10 @@ struct ConvCfg {
     static constexpr int TPA = TAPS == 1 ? 1 : (AMODE == A_TAP ? 1 : (AMODE == A_COL3 ? 3 : 9));
     static constexpr int A_ROWS = TAPS == 1 ? 128 : (AMODE == A_TAP ? 128 : (AMODE == A_COL3 ? 144 : 180));
     static constexpr int A_TX = A_ROWS * 128;
-    static constexpr int A_STAGE = (A_TX + 1023) / 1024 * 1024;
-    static constexpr int B_TAP = (PAIR ? BN / 2 : BN) * 128;     // one tap's weight rows (a CTA pair splits them)
+    // A_STEMP: 180 pixels x 32 B
+    static constexpr int A_STAGE = AMODE == A_STEMP ? 6144 : (A_TX + 1023) / 1024 * 1024;
+    // one tap's weight rows (a CTA pair splits them); A_STEMP: two variants x 64 rows x 32 B
+    static constexpr int B_TAP = AMODE == A_STEMP ? 4096 : (PAIR ? BN / 2 : BN) * 128;
     // taps per weight ring stage / per TMA box: thin per-tap tiles (<= 8 KB, A_HALO) are grouped by three so a
     // stage covers 12 MMAs and the (cross-CTA) barrier traffic drops 3x
     static constexpr int TPB = (TAPS == 9 && AMODE == A_HALO && B_TAP <= 8192) ? 3 : 1;   // (all 9 taps of a slice are one A item only in A_HALO)
@@ -122,10 +130,12 @@ constexpr int kSmemLimit = 232448;    // 227 KB per CTA on sm_100
 
 // X: A_STEM -> n_channels of the network input; EPI_HEAD -> n_classes (0 = generic, up to 8).
 template <int BN, int TAPS, int AMODE, int EPI, int X = 0, bool PAIR = false>
-__global__ void __launch_bounds__(AMODE == A_STEM ? 640 : 384, 1)
+__global__ void __launch_bounds__(AMODE == A_STEM ? 640 : (AMODE == A_STEMP ? 512 : 384), 1)
 conv_tc_kernel(const __grid_constant__ ConvParams p) {
     constexpr int CIN = X;
-    static_assert(!(PAIR && AMODE == A_STEM), "the stem runs unpaired");
+    static_assert(!(PAIR && (AMODE == A_STEM || AMODE == A_STEMP)), "the stem runs unpaired");
+    static_assert(AMODE != A_STEMP || (TAPS == 9 && BN == 64 && CIN >= 1 && CIN <= 4 && EPI == EPI_STORE),
+                  "patch stem: <= 4 input channels, 64 output channels");
     static_assert(TAPS == 9 || TAPS == 1, "3x3 conv or per-tap GEMM");
     static_assert(AMODE != A_STEM || (TAPS == 1 && BN == 64 && CIN >= 1 && 9 * CIN <= 32),
                   "stem: im2col rows of <= 32 taps, 64 output channels");
@@ -167,7 +177,7 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < kMaxRing; ++i) {
             // full: one producer arrive per CTA of the pair (stem: every im2col thread arrives)
-            mbar_init(bar_a_full + 8 * i, AMODE == A_STEM ? 128 : (PAIR ? 2 : 1));
+            mbar_init(bar_a_full + 8 * i, (AMODE == A_STEM || AMODE == A_STEMP) ? 128 : (PAIR ? 2 : 1));
             mbar_init(bar_a_empty + 8 * i, 1);
             mbar_init(bar_b_full + 8 * i, PAIR ? 2 : 1);
             mbar_init(bar_b_empty + 8 * i, 1);
@@ -217,7 +227,83 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
         return valid;
     };
 
-    if (AMODE == A_STEM && warp >= 12) {
+    if (AMODE == A_STEMP && warp >= 12) {
+        // ============ input-patch producer (first conv, implicit GEMM) ============
+        // thread r writes patch pixels q = r and q = r + 128 (< 180): 16 bytes of bf16 hi and 16
+        // bytes of bf16 lo each.  No im2col: the nine taps are shifted views of this patch.
+        constexpr int CI = (CIN >= 1 && CIN <= 4) ? CIN : 1;
+        constexpr int D = 4;                                     // tiles of global-load prefetch (register ring)
+        const int r = threadIdx.x - 384;
+        const int py0 = r / 10, px0 = r % 10;                    // patch pixel q = r
+        const int py1 = (r + 128) / 10, px1 = (r + 128) % 10;    // patch pixel q = r + 128 (only r < 52)
+        const bool has1 = r + 128 < 180;
+        auto fetch = [&](int t, float (&v)[2][CI]) {
+            if (t >= p.total_tiles) return;
+            const int n = t / tiles_per_img;
+            const int rr = t - n * tiles_per_img;
+            const int y0 = (rr / p.tiles_x) * 16 - 1, x0 = (rr % p.tiles_x) * 8 - 1;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int y = y0 + (j ? py1 : py0), x = x0 + (j ? px1 : px0);
+                const bool in = (j == 0 || has1) && y >= 0 && y < p.H && x >= 0 && x < p.W;
+#pragma unroll
+                for (int ci = 0; ci < CI; ++ci) {
+                    float f = 0.f;
+                    if (in) {
+                        if (p.stem_fmt == 0) {
+                            f = __ldg(static_cast<const float*>(p.stem_x) +
+                                      ((static_cast<size_t>(n) * CI + ci) * p.H + y) * p.W + x);
+                        } else {
+                            const uint8_t u = __ldg(static_cast<const uint8_t*>(p.stem_x) +
+                                                    ((static_cast<size_t>(n) * p.H + y) * p.W + x) * CI + ci);
+                            f = __fdiv_rn(static_cast<float>(u), 255.0f);   // inference.py:36 (`/ 255.0`)
+                        }
+                    }
+                    v[j][ci] = f;
+                }
+            }
+        };
+        float ring[D][2][CI];
+        pdl_wait();
+        uint32_t sa = 0, pa = 0;
+        const int stride = static_cast<int>(gridDim.x);
+        const int t0 = static_cast<int>(blockIdx.x);
+#pragma unroll
+        for (int d = 0; d < D; ++d) fetch(t0 + d * stride, ring[d]);
+        for (int base = t0; base < p.total_tiles; base += D * stride) {
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                const int t = base + d * stride;
+                if (t < p.total_tiles) {
+                    mbar_wait(bar_a_empty + 8 * sa, pa ^ 1, 1, p.dbg);
+                    const uint32_t stage = sA + sa * Cfg::A_STAGE;
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        if (j == 0 || has1) {
+                            const int q = r + j * 128;
+                            float f[4], l[4];
+#pragma unroll
+                            for (int ci = 0; ci < 4; ++ci) f[ci] = ci < CI ? ring[d][j][ci < CI ? ci : 0] : 0.f;
+                            const uint32_t h01 = pack_bf16x2(f[0], f[1]), h23 = pack_bf16x2(f[2], f[3]);
+                            l[0] = f[0] - __uint_as_float(h01 << 16);
+                            l[1] = f[1] - __uint_as_float(h01 & 0xffff0000u);
+                            l[2] = f[2] - __uint_as_float(h23 << 16);
+                            l[3] = f[3] - __uint_as_float(h23 & 0xffff0000u);
+                            // 32-byte swizzle: 16-byte chunk index ^= address bit 7 (absolute smem address)
+                            const uint32_t row = stage + q * 32;
+                            const uint32_t x = ((row >> 7) & 1u) << 4;
+                            st_shared_v4(row + x, h01, h23, 0u, 0u);
+                            st_shared_v4(row + (x ^ 16u), pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]), 0u, 0u);
+                        }
+                    }
+                    fence_proxy_async_smem();
+                    mbar_arrive(bar_a_full + 8 * sa);
+                    if (++sa == static_cast<uint32_t>(p.na)) { sa = 0; pa ^= 1; }
+                    fetch(t + D * stride, ring[d]);              // lands D - 1 tiles of work later
+                }
+            }
+        }
+    } else if (AMODE == A_STEM && warp >= 12) {
         // ================== im2col producer (first conv only) =================
         // thread r builds A row r = output pixel (y0 + r/8, x0 + r%8) of the tile, one ring item:
         //   k in [0,32) = bf16 hi of the 9*CIN taps, k in [32,64) = bf16 lo.
@@ -322,7 +408,7 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
         }
     } else if (warp == 0) {
         // ===================== TMA producer: activations ======================
-        if (lane == 0 && AMODE != A_STEM) {
+        if (lane == 0 && AMODE != A_STEM && AMODE != A_STEMP) {
             // flat walk over this CTA's activation items: idx -> (tile, 64-channel slice, item)
             const int ipt = n_cs * ITEMS;
             const int my_units = first_unit < n_units ? (n_units - first_unit + unit_stride - 1) / unit_stride : 0;
@@ -375,7 +461,17 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
         }
     } else if (warp == 3) {
         // ======================= TMA producer: weights ========================
-        if (lane == 0) {
+        if (AMODE == A_STEMP) {
+            // 36 KB of first-conv weights, already in the smem tile layout: plain copy by the warp
+            const uint4* src = static_cast<const uint4*>(p.stem_w);
+            for (int i = lane; i < 9 * Cfg::B_TAP / 16; i += 32) {
+                const uint4 w4 = __ldg(src + i);
+                st_shared_v4(sB + i * 16, w4.x, w4.y, w4.z, w4.w);
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_b_full);
+        } else if (lane == 0) {
             const int row_off = PAIR ? static_cast<int>(rank) * (BN / 2) : 0;   // this CTA's half of the weight rows
             if (p.wstat) {
                 // whole weight slab of this layer, once: slot = cs * TAPS + tap
@@ -427,7 +523,38 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
         // units, and mbarrier probes for the next stage are issued ahead of the MMAs.
         // The whole warp walks the loops converged (uniform addresses live in uniform registers);
         // one elected lane issues the MMAs and commits.
-        if (rank == 0) {
+        if (AMODE == A_STEMP) {
+            // patch stem: per tile 9 taps x {[w_hi | w_hi], [w_lo | 0]} K = 16 UMMAs on shifted patch views.
+            // SWIZZLE_32B K-major descriptors: rows (pixels / output channels) are 32 B, the 8-row
+            // group stride is one patch row (320 B) for A and 256 B for B.
+            constexpr uint32_t idesc = umma_idesc_bf16(BN, 128);
+            constexpr uint32_t a_hi = umma_desc_hi_sw32(320), b_hi = umma_desc_hi_sw32(256);
+            uint32_t sa = 0, pa = 0, tile_it = 0;
+            mbar_wait(bar_b_full, 0, 8, p.dbg);
+            tc_fence_after();
+            const uint32_t b_lo0 = umma_desc_lo(sB);
+            for (int u = first_unit; u < n_units; u += unit_stride, ++tile_it) {
+                const uint32_t acc = tile_it % Cfg::NACC, acc_ph = (tile_it / Cfg::NACC) & 1;
+                mbar_wait(bar_t_empty + 8 * acc, acc_ph ^ 1, 4, p.dbg);
+                mbar_wait(bar_a_full + 8 * sa, pa, 5, p.dbg);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                const uint32_t a_lo0 = umma_desc_lo(sA + sa * Cfg::A_STAGE);
+                if (elect_one()) {
+#pragma unroll
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const uint32_t a_lo = a_lo0 + 2 * ((tap / 3) * 10 + (tap % 3));   // one pixel = two 16-byte units
+#pragma unroll
+                        for (int v = 0; v < 2; ++v)
+                            umma_bf16(d_tmem, umma_desc(a_lo, a_hi),
+                                      umma_desc(b_lo0 + (tap * 2 + v) * (2048 >> 4), b_hi), idesc, (tap | v) ? 1u : 0u);
+                    }
+                    umma_commit(bar_a_empty + 8 * sa);
+                    umma_commit(bar_t_full + 8 * acc);
+                }
+                if (++sa == static_cast<uint32_t>(p.na)) { sa = 0; pa ^= 1; }
+            }
+        } else if (rank == 0) {
             constexpr uint32_t idesc = umma_idesc_bf16(BN, PAIR ? 256 : 128);
             constexpr uint32_t a_sbo = (TAPS == 9 && AMODE == A_HALO) ? 10 * 128 : 1024;
             constexpr uint32_t a_hi = umma_desc_hi_sw128(a_sbo);
@@ -531,7 +658,7 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
         // BN == 64 launches (one 64-column chunk per tile, in production a single column block): the
         // chunk's 64 bias values live in registers and are reloaded only when the channel offset
         // changes (the thin-K epilogues stalled on their shared-memory loads)
-        constexpr bool kBiasRegs = BN == 64 && AMODE != A_STEM;   // (the 640-thread stem has 102 registers per thread)
+        constexpr bool kBiasRegs = BN == 64 && AMODE != A_STEM && AMODE != A_STEMP;   // (the 640-thread stem has 102 registers per thread)
         float bias_r[kBiasRegs ? 64 : 1];
         int bias_ch0 = -1;
         auto load_bias = [&](int ch0) {

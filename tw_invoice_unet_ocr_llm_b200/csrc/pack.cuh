@@ -84,6 +84,31 @@ __global__ void pack_stem_tc_kernel(const float* __restrict__ w, const float* __
     }
 }
 
+// First conv for the patch stem (conv_tc.cuh, A_STEMP): [64][Cin][3][3] -> the exact shared-memory
+// image of its weight tiles, bf16 [tap 9][variant 2][row = co 64][16 k], SWIZZLE_32B applied
+// (the two 16-byte halves of row r are swapped when bit 2 of r is set; tiles are 2 KB aligned):
+//   variant 0: k 0..7 (multiplies x_hi) = w_hi, k 8..15 (multiplies x_lo) = w_hi
+//   variant 1: k 0..7                  = w_lo, k 8..15                  = 0
+// with k & 7 = input channel (>= Cin: 0) and w = w_hi + w_lo to 16 significand bits.
+__global__ void pack_stem_patch_kernel(const float* __restrict__ w, const float* __restrict__ gamma,
+                                       const float* __restrict__ var, float eps, int cout, int cin,
+                                       uint16_t* __restrict__ dst_w) {
+    const int total = 9 * 2 * cout * 16;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int k = i & 15, co = (i >> 4) % cout;
+        const int v = (i / (16 * cout)) & 1, tap = i / (32 * cout);
+        const int ci = k & 7, half = k >> 3;
+        uint16_t out = 0;
+        if (ci < cin && !(v == 1 && half == 1)) {
+            const float f = w[(static_cast<size_t>(co) * cin + ci) * 9 + tap] * bn_scale(gamma, var, eps, co);
+            const uint16_t hi = f32_to_bf16_bits(f);
+            out = v == 0 ? hi : f32_to_bf16_bits(f - __uint_as_float(static_cast<uint32_t>(hi) << 16));
+        }
+        const int phys_half = half ^ ((co >> 2) & 1);
+        dst_w[(i & ~15) + phys_half * 8 + ci] = out;
+    }
+}
+
 // ConvTranspose2d weight [Cin][Cout][2][2] -> [(a*2+b)*Cout + co][Cin] bf16 (unet_model.py:38-47).
 __global__ void pack_convt_kernel(const float* __restrict__ w, const float* __restrict__ b, int cin,
                                   int cout, uint16_t* __restrict__ dst_w, float* __restrict__ dst_b) {

@@ -204,6 +204,11 @@ __host__ __device__ constexpr uint32_t umma_desc_hi_sw128(uint32_t sbo_bytes) {
 __device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr) {
     return ((smem_addr & 0x3FFFF) >> 4) | (1u << 16);
 }
+// Same descriptor for 32-byte rows (K = 16 bf16 per row): SWIZZLE_32B = layout type 6, the XOR
+// (16-byte chunk index ^= address bit 7) again on absolute shared-memory address bits.
+__host__ __device__ constexpr uint32_t umma_desc_hi_sw32(uint32_t sbo_bytes) {
+    return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) | (6u << 29);
+}
 __device__ __forceinline__ uint64_t umma_desc(uint32_t lo, uint32_t hi) {
     return (static_cast<uint64_t>(hi) << 32) | lo;
 }

@@ -110,6 +110,8 @@ struct LayerSpec {
 // The stem's weight region holds two layouts: fp32 [9*cin][cout] for the CUDA-core kernel
 // (stem.cuh), then bf16 hi/lo [cout][128] for the tensor-core stem (conv_tc.cuh, A_STEM).
 uint64_t stem_tc_offset(int cin, int cout) { return (uint64_t(9) * cin * cout * 4 + 255) / 256 * 256; }
+// ... then the smem image of the patch stem's weight tiles (A_STEMP), 9 taps x 4096 B.
+uint64_t stem_patch_offset(int cin, int cout) { return stem_tc_offset(cin, cout) + uint64_t(cout) * 128 * 2; }
 
 std::vector<unetb200_layer_t> layer_table(const unetb200_arch_t& a) {
     const int w = a.base_width;
@@ -152,7 +154,7 @@ std::vector<unetb200_layer_t> layer_table(const unetb200_arch_t& a) {
         l.level = s.level;
         uint64_t wb = 0;
         switch (s.kind) {
-            case UNETB200_STEM: wb = stem_tc_offset(s.cin, s.cout) + uint64_t(s.cout) * 128 * 2; break;
+            case UNETB200_STEM: wb = stem_patch_offset(s.cin, s.cout) + 9 * 4096; break;
             case UNETB200_CONV3X3: wb = uint64_t(9) * s.cin * s.cout * 2; break;
             case UNETB200_CONVT2X2: wb = uint64_t(4) * s.cin * s.cout * 2; break;
             case UNETB200_HEAD: wb = uint64_t(s.cin) * s.cout * 4; break;
@@ -241,8 +243,26 @@ ConvLaunch stem_inst() {
     return l;
 }
 
+template <int CIN>
+ConvLaunch stemp_inst() {
+    ConvLaunch l;
+    l.fn = ub::conv_tc_kernel<64, 9, ub::A_STEMP, ub::EPI_STORE, CIN>;
+    l.a_stage = ub::ConvCfg<64, 9, ub::A_STEMP>::A_STAGE;
+    l.b_stage = ub::ConvCfg<64, 9, ub::A_STEMP>::B_STAGE;
+    l.b_tap = ub::ConvCfg<64, 9, ub::A_STEMP>::B_TAP;
+    return l;
+}
+
 ConvLaunch pick_conv(int taps, int bn, int amode, int epi, int stem_cin = 0, int ncls = 0, bool pair = false) {
-    if (pair && amode != ub::A_STEM && (taps == 1 || amode == ub::A_HALO)) {
+    if (amode == ub::A_STEMP) {
+        switch (stem_cin) {
+            case 1: return stemp_inst<1>();
+            case 3: return stemp_inst<3>();
+            case 4: return stemp_inst<4>();
+        }
+        return ConvLaunch();
+    }
+    if (pair && amode != ub::A_STEM && amode != ub::A_STEMP && (taps == 1 || amode == ub::A_HALO)) {
         if (epi == ub::EPI_HEAD)
             return ncls == 3 ? conv_inst<64, 9, ub::A_HALO, ub::EPI_HEAD, 3, true>()
                              : conv_inst<64, 9, ub::A_HALO, ub::EPI_HEAD, 0, true>();
@@ -379,10 +399,11 @@ int plan_smem(ConvLaunch* cl, ub::ConvParams* p, int taps, int n_cs, int n_block
 }
 
 int build_conv_step(const ConvDesc& d, int num_sms, Step* st) {
-    const bool stem = d.amode == ub::A_STEM;
+    const bool stemp = d.amode == ub::A_STEMP;
+    const bool stem = d.amode == ub::A_STEM || stemp;
     if (d.c0 <= 0 || d.c0 % 64 || d.c1 % 64 || d.c1 < 0)
         return fail(UNETB200_EINVAL, "conv: source channels must be multiples of 64");
-    if (stem && (d.taps != 1 || d.cout != 64 || d.c0 != 64 || d.c1 != 0 || !d.stem_x ||
+    if (stem && (d.taps != (stemp ? 9 : 1) || d.cout != 64 || d.c0 != 64 || d.c1 != 0 || !d.stem_x ||
                  d.epi != ub::EPI_STORE))
         return fail(UNETB200_EINVAL, "stem: bad configuration");
     if (d.cout % 64) return fail(UNETB200_EINVAL, "conv: cout must be a multiple of 64");
@@ -406,6 +427,7 @@ int build_conv_step(const ConvDesc& d, int num_sms, Step* st) {
     if (stem) {
         p.stem_x = d.stem_x;
         p.stem_fmt = d.stem_fmt;
+        p.stem_w = d.w;
         // tmA0/tmA1 are never used by the stem (its A rows are built in-kernel); keep them valid
         if ((rc = make_act_map(&p.tmA0, d.out, d.cout, d.wd, d.h, d.n, 8, 16))) return rc;
         p.tmA1 = p.tmA0;
@@ -419,9 +441,12 @@ int build_conv_step(const ConvDesc& d, int num_sms, Step* st) {
             p.tmA1 = p.tmA0;
         }
     }
-    const int cin = stem ? 128 : d.c0 + d.c1;      // K extent of the packed weights (stem: hi/lo layout)
-    if ((rc = make_w_map(&p.tmB, d.w, cin, cols, d.taps == 9 ? 9 : 1, st->conv.pair ? bn / 2 : bn, st->conv.tpb)))
+    const int cin = (stem && !stemp) ? 128 : d.c0 + d.c1;   // K extent of the packed weights (im2col stem: hi/lo layout)
+    if (stemp) {
+        p.tmB = p.tmA0;                 // unused: the kernel copies the weight tiles itself
+    } else if ((rc = make_w_map(&p.tmB, d.w, cin, cols, d.taps == 9 ? 9 : 1, st->conv.pair ? bn / 2 : bn, st->conv.tpb))) {
         return rc;
+    }
     if (d.epi == ub::EPI_UPSAMPLE) {
         const int ho = 2 * d.h, wo = 2 * d.wd;
         for (int tap = 0; tap < 4; ++tap) {
@@ -465,7 +490,7 @@ int build_conv_step(const ConvDesc& d, int num_sms, Step* st) {
     p.pf_items = d.pf_items;
     if ((rc = plan_smem(&st->conv, &p, d.taps == 9 ? 9 : 1, cin / 64, p.n_blocks, bn,
                         d.epi == ub::EPI_STORE_POOL, d.epi != ub::EPI_HEAD, stem ? 1 : d.wstat,
-                        stem ? 4 * d.stem_cin * 180 * 4 : 0, d.epi2)))
+                        (stem && !stemp) ? 4 * d.stem_cin * 180 * 4 : 0, d.epi2)))
         return rc;
     if (st->conv.pair) {
         const long long m_tiles = 1LL * p.tiles_x * p.tiles_y * d.n;
@@ -475,7 +500,7 @@ int build_conv_step(const ConvDesc& d, int num_sms, Step* st) {
     } else {
         st->grid = dim3(static_cast<unsigned>(total < num_sms ? total : num_sms));
     }
-    st->block = dim3(stem ? 640 : 384);
+    st->block = dim3(stemp ? 512 : (stem ? 640 : 384));
     return 0;
 }
 
@@ -553,13 +578,14 @@ int build_stem_step(const void* x, int x_fmt, int cin, const float* w, const flo
 // First conv on the tensor cores (conv_tc.cuh, A_STEM): im2col rows built in-kernel from the
 // user's tensor, hi/lo-split bf16 GEMM over two K slices against the [64][128] packed weights.
 int build_stem_tc_step(const void* x, int x_fmt, int cin, const void* w_tc, const float* bias, int n,
-                       int h, int wd, void* out, int num_sms, int* dbg, Step* st) {
+                       int h, int wd, void* out, int num_sms, int* dbg, Step* st, bool patch = false) {
     if (x_fmt != UNETB200_X_F32_NCHW && x_fmt != UNETB200_X_U8_NHWC)
         return fail(UNETB200_EINVAL, "unknown x_fmt");
-    if (!(cin == 1 || cin == 3)) return fail(UNETB200_EINVAL, "tensor-core stem: n_channels must be 1 or 3");
+    if (patch ? !(cin == 1 || cin == 3 || cin == 4) : !(cin == 1 || cin == 3))
+        return fail(UNETB200_EINVAL, "tensor-core stem: unsupported n_channels");
     ConvDesc d;
     d.c0 = 64; d.w = w_tc; d.bias = bias; d.n = n; d.h = h; d.wd = wd; d.cout = 64; d.relu = 1;
-    d.taps = 1; d.epi = ub::EPI_STORE; d.out = out; d.bn = 64; d.amode = ub::A_STEM;
+    d.taps = patch ? 9 : 1; d.epi = ub::EPI_STORE; d.out = out; d.bn = 64; d.amode = patch ? ub::A_STEMP : ub::A_STEM;
     d.stem_x = x; d.stem_fmt = x_fmt; d.stem_cin = cin; d.dbg = dbg;
     return build_conv_step(d, num_sms, st);
 }
@@ -600,7 +626,8 @@ struct unetb200_handle_s {
     int amode = ub::A_HALO;
     int bn_max = 256;
     int wstat = 1;
-    int stem_tc = 1;            // first conv on the tensor cores (n_channels <= 3)
+    int stem_tc = 1;            // first conv: 0 = CUDA cores, 1 = tensor cores + in-kernel im2col (fastest measured),
+                                // 2 = tensor cores, implicit GEMM over a shared-memory patch (validated, 1.6x slower)
     int pf_items = 0;           // L2 prefetch distance of the activation producer, in ring items (measured: no gain)
     int epi2 = 1;               // two epilogue groups: 0 never, 1 weight-stationary launches, 2 always
     int pair = 2;               // CTA pairs (cta_group::2): 0 = never, 1 = wherever instantiated, 2 = where measured faster
@@ -685,7 +712,12 @@ int build_plan(unetb200_handle_t h, const void* x, int x_fmt, int n, int H, int 
     // ---- encoder (unet_model.py:56-66)
     {
         Step st;
-        if (h->stem_tc && h->arch.n_channels <= 3) {
+        if (h->stem_tc == 2) {
+            if ((rc = build_stem_tc_step(x, x_fmt, h->arch.n_channels,
+                                         h->blob + h->layers[0].w_off + stem_patch_offset(h->arch.n_channels, bw),
+                                         Bp(0), n, H, W, P(L.a[0]), h->num_sms, h->dbg, &st, true)))
+                return rc;
+        } else if (h->stem_tc == 1 && h->arch.n_channels <= 3) {
             if ((rc = build_stem_tc_step(x, x_fmt, h->arch.n_channels,
                                          h->blob + h->layers[0].w_off + stem_tc_offset(h->arch.n_channels, bw),
                                          Bp(0), n, H, W, P(L.a[0]), h->num_sms, h->dbg, &st)))
@@ -789,6 +821,9 @@ int unetb200_pack_layer(const unetb200_arch_t* arch, int index, const float* wei
             ub::pack_stem_tc_kernel<<<(l.cout * 128 + threads - 1) / threads, threads, 0, s>>>(
                 weight, bn_gamma, bn_var, bn_eps, l.cout, l.cin,
                 reinterpret_cast<uint16_t*>(blob + l.w_off + stem_tc_offset(l.cin, l.cout)));
+            ub::pack_stem_patch_kernel<<<(9 * 32 * l.cout + threads - 1) / threads, threads, 0, s>>>(   // 9 x 2 x cout x 16
+                weight, bn_gamma, bn_var, bn_eps, l.cout, l.cin,
+                reinterpret_cast<uint16_t*>(blob + l.w_off + stem_patch_offset(l.cin, l.cout)));
             break;
         }
         case UNETB200_CONV3X3: {
@@ -855,7 +890,7 @@ int unetb200_create(const unetb200_arch_t* arch, const void* blob_dev, uint64_t 
     env = getenv("UNETB200_PF_ITEMS");
     if (env) h->pf_items = atoi(env);
     env = getenv("UNETB200_STEM_TC");
-    if (env) h->stem_tc = atoi(env) ? 1 : 0;
+    if (env) h->stem_tc = atoi(env);
     *out = h;
     return 0;
 }
@@ -881,7 +916,8 @@ int unetb200_set_option(unetb200_handle_t h, const char* key, int value) {
     } else if (k == "wstat") {
         h->wstat = value ? 1 : 0;
     } else if (k == "stem_tc") {
-        h->stem_tc = value ? 1 : 0;
+        if (value < 0 || value > 2) return fail(UNETB200_EINVAL, "stem_tc must be 0, 1 or 2");
+        h->stem_tc = value;
     } else if (k == "pdl") {
         h->pdl = value ? 1 : 0;
     } else if (k == "pair") {
@@ -1083,6 +1119,21 @@ int unetb200_stem_tc(const void* x, int x_fmt, int cin, const void* w_tc, const 
     if ((rc = device_num_sms(&sms))) return rc;
     Step st;
     if ((rc = build_stem_tc_step(x, x_fmt, cin, w_tc, bias, n, height, width, out, sms, g_hook_dbg(), &st)))
+        return rc;
+    return launch_step(st, static_cast<cudaStream_t>(stream));
+}
+
+uint64_t unetb200_stem_patch_offset(int cin) { return stem_patch_offset(cin, 64); }
+
+int unetb200_stem_patch(const void* x, int x_fmt, int cin, const void* w_patch, const float* bias, int n,
+                        int height, int width, void* out, void* stream) {
+    int rc;
+    if ((rc = check_sm100())) return rc;
+    if (!x || !w_patch || !bias || !out) return fail(UNETB200_EINVAL, "NULL pointer");
+    int sms = 0;
+    if ((rc = device_num_sms(&sms))) return rc;
+    Step st;
+    if ((rc = build_stem_tc_step(x, x_fmt, cin, w_patch, bias, n, height, width, out, sms, g_hook_dbg(), &st, true)))
         return rc;
     return launch_step(st, static_cast<cudaStream_t>(stream));
 }
