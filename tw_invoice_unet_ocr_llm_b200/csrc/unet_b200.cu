@@ -339,6 +339,7 @@ struct ConvDesc {
     int wstat = 1;              // allow weight-stationary mode when it fits
     int pf_items = 0;           // L2 prefetch distance (activation ring items)
     int epi2 = 1;               // two epilogue groups: 0 never, 1 weight-stationary launches, 2 always
+    int min_na = 3;             // weight-stationary launches: activation stages wanted before staging slots
     int pair = 0;               // CTA pairs (cta_group::2) where an instantiation exists
     const void* stem_x = nullptr;   // A_STEM: network input, its format and channel count
     int stem_fmt = 0, stem_cin = 0;
@@ -349,7 +350,7 @@ struct ConvDesc {
 // staging][barriers].  Weight-stationary when the layer has one column block and its whole
 // weight slab fits beside at least two activation stages.
 int plan_smem(ConvLaunch* cl, ub::ConvParams* p, int taps, int n_cs, int n_blocks, int bn, bool pool,
-              bool has_out, int allow_wstat, int patch_bytes, int epi2) {
+              bool has_out, int allow_wstat, int patch_bytes, int epi2, int min_na) {
     const int budget = ub::kSmemLimit - ub::kStaticSmem - 1024 /*alignment slack*/ - patch_bytes;
     const int slab = taps * n_cs * cl->b_tap;
     // Epilogue groups: thin-K launches with resident weights are epilogue-bound -> two groups on
@@ -357,7 +358,7 @@ int plan_smem(ConvLaunch* cl, ub::ConvParams* p, int taps, int n_cs, int n_block
     const int slot = ub::kOutStage + (pool ? ub::kPoolStage : 0);
     int n_out = has_out ? 2 : 0, n_epi = 1, na = 0, nb = 0, wstat = 0;
     if (allow_wstat && n_blocks == 1) {
-        for (int want_na = 3; want_na >= 2 && !wstat; --want_na) {
+        for (int want_na = (min_na > 2 ? min_na : 2); want_na >= 2 && !wstat; --want_na) {
             for (int ne = (epi2 >= 1 ? 2 : 1); ne >= 1 && !wstat; --ne) {
                 for (int no = has_out ? 2 : 0; no >= (has_out ? 1 : 0) && !wstat; --no) {
                     const int rest = budget - ub::kBarBytes - ne * no * slot - slab;
@@ -490,7 +491,7 @@ int build_conv_step(const ConvDesc& d, int num_sms, Step* st) {
     p.pf_items = d.pf_items;
     if ((rc = plan_smem(&st->conv, &p, d.taps == 9 ? 9 : 1, cin / 64, p.n_blocks, bn,
                         d.epi == ub::EPI_STORE_POOL, d.epi != ub::EPI_HEAD, stem ? 1 : d.wstat,
-                        (stem && !stemp) ? 4 * d.stem_cin * 180 * 4 : 0, d.epi2)))
+                        (stem && !stemp) ? 4 * d.stem_cin * 180 * 4 : 0, d.epi2, d.min_na)))
         return rc;
     if (st->conv.pair) {
         const long long m_tiles = 1LL * p.tiles_x * p.tiles_y * d.n;
@@ -630,6 +631,7 @@ struct unetb200_handle_s {
                                 // 2 = tensor cores, implicit GEMM over a shared-memory patch (validated, 1.6x slower)
     int pf_items = 0;           // L2 prefetch distance of the activation producer, in ring items (measured: no gain)
     int epi2 = 1;               // two epilogue groups: 0 never, 1 weight-stationary launches, 2 always
+    int min_na = 3;             // weight-stationary launches: activation stages wanted before staging slots
     int pair = 2;               // CTA pairs (cta_group::2): 0 = never, 1 = wherever instantiated, 2 = where measured faster
     int pdl = 1;                // programmatic dependent launch between the layers of one forward
     int profile = 0;
@@ -687,7 +689,7 @@ int build_plan(unetb200_handle_t h, const void* x, int x_fmt, int n, int H, int 
         d.n = n; d.h = H >> lvl; d.wd = W >> lvl; d.cout = h->layers[li].cout;
         d.relu = 1; d.taps = 9; d.epi = pool ? ub::EPI_STORE_POOL : ub::EPI_STORE;
         d.out = out; d.pool = pool;
-        d.bn = h->bn_max; d.amode = h->amode; d.wstat = h->wstat; d.pf_items = h->pf_items; d.epi2 = h->epi2; d.dbg = h->dbg;
+        d.bn = h->bn_max; d.amode = h->amode; d.wstat = h->wstat; d.pf_items = h->pf_items; d.epi2 = h->epi2; d.min_na = h->min_na; d.dbg = h->dbg;
         // measured on B200 (profiles/): CTA pairs win or tie on every 3x3 conv, lose slightly on the up-convs
         d.pair = h->pair >= 1;
         Step st;
@@ -702,7 +704,7 @@ int build_plan(unetb200_handle_t h, const void* x, int x_fmt, int n, int H, int 
         d.w = Wp(li); d.bias = Bp(li);
         d.n = n; d.h = H >> lvl; d.wd = W >> lvl; d.cout = h->layers[li].cout;
         d.relu = 0; d.taps = 1; d.epi = ub::EPI_UPSAMPLE; d.out = out;
-        d.bn = h->bn_max; d.amode = ub::A_TAP; d.wstat = h->wstat; d.pf_items = h->pf_items; d.epi2 = h->epi2; d.pair = h->pair == 1; d.dbg = h->dbg;
+        d.bn = h->bn_max; d.amode = ub::A_TAP; d.wstat = h->wstat; d.pf_items = h->pf_items; d.epi2 = h->epi2; d.min_na = h->min_na; d.pair = h->pair == 1; d.dbg = h->dbg;
         Step st;
         if ((rc = build_conv_step(d, h->num_sms, &st))) return rc;
         st.layer = li;
@@ -756,7 +758,7 @@ int build_plan(unetb200_handle_t h, const void* x, int x_fmt, int n, int H, int 
             d.n = n; d.h = H; d.wd = W; d.cout = bw; d.relu = 1; d.taps = 9; d.epi = ub::EPI_HEAD;
             d.head_w = reinterpret_cast<const float*>(Wp(22)); d.head_b = Bp(22);
             d.ncls = h->arch.n_classes; d.logits = logits; d.mask = mask;
-            d.bn = 64; d.amode = h->amode; d.wstat = h->wstat; d.pf_items = h->pf_items; d.epi2 = h->epi2; d.pair = h->pair >= 1; d.dbg = h->dbg;
+            d.bn = 64; d.amode = h->amode; d.wstat = h->wstat; d.pf_items = h->pf_items; d.epi2 = h->epi2; d.min_na = h->min_na; d.pair = h->pair >= 1; d.dbg = h->dbg;
             Step st;
             if ((rc = build_conv_step(d, h->num_sms, &st))) return rc;
             st.layer = 21;
@@ -923,6 +925,9 @@ int unetb200_set_option(unetb200_handle_t h, const char* key, int value) {
     } else if (k == "pair") {
         if (value < 0 || value > 2) return fail(UNETB200_EINVAL, "pair must be 0, 1 or 2");
         h->pair = value;
+    } else if (k == "min_na") {
+        if (value < 2 || value > 8) return fail(UNETB200_EINVAL, "min_na must be in 2..8");
+        h->min_na = value;
     } else if (k == "epi2") {
         if (value < 0 || value > 2) return fail(UNETB200_EINVAL, "epi2 must be 0, 1 or 2");
         h->epi2 = value;
@@ -947,6 +952,7 @@ int unetb200_get_option(unetb200_handle_t h, const char* key, int* value) {
     else if (k == "stem_tc") *value = h->stem_tc;
     else if (k == "pf_items") *value = h->pf_items;
     else if (k == "epi2") *value = h->epi2;
+    else if (k == "min_na") *value = h->min_na;
     else if (k == "pair") *value = h->pair;
     else if (k == "pdl") *value = h->pdl;
     else if (k == "profile") *value = h->profile;
