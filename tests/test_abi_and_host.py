@@ -152,3 +152,20 @@ def test_shims_expose_the_reference_module_names():
             sys.modules.pop(k, None)
             if v is not None:
                 sys.modules[k] = v
+
+
+def test_module_copies_and_pickles_without_the_engine(fixture_state):
+    """copy.deepcopy / pickle (torch.save(model)) must not try to serialise the packed GPU replica."""
+    import copy
+    import io
+    from tw_invoice_unet_ocr_llm_b200.unet_model import UNet
+    m = UNet()
+    m.load_state_dict(fixture_state)
+    object.__setattr__(m, "_engine", object())          # stand-in for a live engine
+    m2 = copy.deepcopy(m)
+    assert m2._engine is None and list(m2.state_dict()) == list(m.state_dict())
+    buf = io.BytesIO()
+    torch.save(m, buf)
+    buf.seek(0)
+    m3 = torch.load(buf, weights_only=False)
+    assert m3._engine is None and torch.equal(m3.down1.net[0].weight, m.down1.net[0].weight)

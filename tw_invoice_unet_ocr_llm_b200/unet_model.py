@@ -85,6 +85,13 @@ class UNet(nn.Module):
             self._drop_engine()
         return super().train(mode)
 
+    def __getstate__(self):
+        # the packed replica holds device pointers and a ctypes handle: never pickled / deep-copied
+        state = self.__dict__.copy()
+        state["_engine"] = None
+        state["_engine_key"] = None
+        return state
+
     def _weights_key(self):
         return tuple((t.data_ptr(), t._version) for t in itertools.chain(self.parameters(), self.buffers()))
 
