@@ -231,6 +231,29 @@ def test_other_channel_and_class_counts(cuda_dev, n_channels, n_classes):
     assert float(err.max()) <= 0.05 * float(ref.std()) + 0.02, (float(err.max()), float(ref.std()))
 
 
+def test_back_to_back_mixed_shapes(model, cuda_dev):
+    """Forwards of different shapes enqueued back to back on one stream share the workspace and run
+    with programmatic dependent launch between layers: every result must equal the result of the
+    same forward run alone."""
+    from tw_invoice_unet_ocr_llm_b200.synthetic import synthetic_invoices
+    shapes = [(1, 64, 64), (2, 96, 80), (1, 512, 512), (3, 32, 48), (1, 16, 16)]
+    xs = [synthetic_invoices(n, h, w, seed=60 + i).to(cuda_dev) for i, (n, h, w) in enumerate(shapes)]
+    eng = model.engine(cuda_dev)
+    alone = []
+    for x in xs:
+        z, _ = eng.run(x)
+        torch.cuda.synchronize()
+        alone.append(z.clone())
+    outs = []
+    for rep in range(3):
+        for x in xs:
+            z, _ = eng.run(x)          # no synchronisation in between
+            outs.append(z)
+    torch.cuda.synchronize()
+    for i, z in enumerate(outs):
+        assert torch.equal(z, alone[i % len(xs)]), f"forward {i} differs when run back to back"
+
+
 def test_errors(model, cuda_dev):
     with pytest.raises(RuntimeError):
         model(torch.zeros(1, 3, 500, 500, device=cuda_dev))     # not divisible by 16 (reference raises too)
