@@ -115,7 +115,9 @@ int unetb200_layer_times(unetb200_handle_t h, float* ms, int count);
 /* Number of kernels the last forward enqueued. */
 int unetb200_last_launch_count(unetb200_handle_t h);
 
-/* ---- single-kernel entry points (unit parity tests; same code paths as forward) ---- */
+/* ---- single-kernel entry points (unit parity tests; same code paths as forward).  Each is one layer
+ *      of the reference: Conv2d 3x3 + BatchNorm + ReLU (unet_model.py:10-16), the concat of :71-83,
+ *      MaxPool2d (:34), ConvTranspose2d (:38-47), out_conv (:50,86) ---- */
 /* 3x3 conv + bias + optional ReLU over NHWC bf16.  src1/c1 = second (skip) source or NULL/0.
  * w_packed: [9][cout][c0+c1] bf16, bias fp32[cout].  pool_out nullable (2x2 max-pool 2nd output).
  * bn in {64,128,256}, amode in UNETB200_A_*; `wstat` is a flag word: bit 0 allows the weight-stationary
