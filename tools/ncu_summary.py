@@ -4,7 +4,6 @@
 usage: tools/ncu_summary.py gpurun_out/prof_<tag>_raw.csv [layer names json] > profiles/<tag>_ncu_summary.md
 """
 import csv
-import json
 import sys
 
 COLS = [

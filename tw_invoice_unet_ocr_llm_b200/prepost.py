@@ -7,7 +7,6 @@
 """
 from __future__ import annotations
 
-import ctypes as C
 import threading
 from typing import Dict, Tuple
 
