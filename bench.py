@@ -403,6 +403,17 @@ def main():
             if lat is not None:
                 lat["run_unet_1080p"] = {"error": repr(e)}
 
+    # ---------------- OCR crop enhancement (rank 0, informational): 192 ragged crops
+    # through enhance_batch vs the reference's cv2 calls on the host cores
+    enh = None
+    if rank == 0 and world == 1:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import enhance_bench
+            enh = enhance_bench.measure(quick=True)
+        except Exception as e:          # informational only
+            enh = {"error": repr(e)}
+
     # ---------------- CPU baseline (rank 0, N = 1 only): the oracle port on the host cores
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -423,7 +434,7 @@ def main():
                        "l2": "no flush needed: per-step working set (~9 GB of activations, 201 MB input) exceeds the 126 MB L2",
                        "gflop_per_image": GFLOP_PER_IMAGE_512 * (S * S) / (512 * 512),
                        "achieved_tflops_whole_step": value / world * GFLOP_PER_IMAGE_512 * (S * S) / (512 * 512) / 1e3},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "latency_b1": lat, "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "latency_b1": lat, "enhance": enh, "clocks": clocks,
             "gpu_launches": launches_per_step * args.steps,
         }
         print(json.dumps(line), flush=True)

@@ -164,6 +164,44 @@ int unetb200_resize_bicubic_u8(const uint8_t* src, int n, int h, int w, int c, c
 /* np.where(mask) min/max of inference.py:85-93: mask uint8 [n_planes,h,w] ->
  * out int32 [n_planes,5] = {xmin, xmax, ymin, ymax, count}; an empty plane gives {w, -1, h, -1, 0}. */
 int unetb200_mask_bbox(const uint8_t* mask, int n_planes, int h, int w, int32_t* out, void* stream);
+/* Byte sums of n_boxes (<= 16) rectangles {x1, y1, x2, y2} (half-open, host array of 4*n_boxes ints) of one
+ * uint8 [h][w][c] device frame -> sums_dev uint64 [n_boxes] (zeroed here): the `np.array(crop).mean() < 3`
+ * rejection of inference.py:121-125 as the exact integer test sum < 3 * (x2-x1)*(y2-y1)*c. */
+int unetb200_box_sums(const uint8_t* img, int h, int w, int c, const int32_t* boxes_host, int n_boxes,
+                      uint64_t* sums_dev, void* stream);
+
+/* ---- OCR crop enhancement: app_camera.py:572-598 enhance_for_ocrspace and
+ * :685-705 enhance_for_date_ocr, i.e. cv2.cvtColor(RGB2GRAY) -> cv2.resize(fx=4, fy=4, INTER_CUBIC)
+ * -> [cv2.filter2D 3x3 sharpen] -> CLAHE(clip, 8x8) -> [cv2.GaussianBlur 3x3] -> [cv2.threshold OTSU],
+ * over a ragged batch of uint8 RGB crops, bit-exact with OpenCV's own code path. ---- */
+#define UNETB200_ENH_SHARPEN 1   /* filter2D [[-1,-1,-1],[-1,9,-1],[-1,-1,-1]] after the upscale */
+#define UNETB200_ENH_BLUR 2      /* GaussianBlur((3,3), 0) after CLAHE */
+#define UNETB200_ENH_OTSU 4      /* threshold(0, 255, THRESH_BINARY | THRESH_OTSU) at the end */
+/* enhance_for_ocrspace(mode="text") = SHARPEN|OTSU, clip 4.0; any other mode = SHARPEN, clip 4.0;
+ * enhance_for_date_ocr = BLUR|OTSU, clip 3.0 */
+typedef struct unetb200_enh_crop {
+    int32_t h, w;             /* in : crop size in pixels (output is 4h x 4w) */
+    int32_t flags;            /* in : UNETB200_ENH_* */
+    float clip;               /* in : CLAHE clipLimit (> 0) */
+    int32_t clip_count;       /* out: per-bin clip limit, max((int)(clip * tile_area / 256), 1) */
+    int32_t tile_h, tile_w;   /* out: CLAHE tile size of the (reflect-extended) upscaled image */
+    int32_t first_block;      /* out: index of this crop's first 32x32 output block in the batch */
+    int32_t blocks_x;         /* out: output blocks per row */
+    int32_t n_blocks;         /* out: output blocks of this crop */
+    int32_t reserved[2];
+    uint64_t src_off;         /* out: byte offset of the uint8 [h][w][3] crop in `src` */
+    uint64_t out_off;         /* out: byte offset of the uint8 [4h][4w] result in `out` */
+    uint64_t ws_off;          /* out: byte offset of this crop's scratch in `workspace` */
+} unetb200_enh_crop;
+/* Host only: fills the `out` fields of table[0..n) from the `in` fields and returns the sizes of the
+ * three device buffers (crops packed back to back at 16-byte aligned offsets). */
+int unetb200_enhance_plan(unetb200_enh_crop* table, int n, uint64_t* src_bytes, uint64_t* out_bytes,
+                          uint64_t* workspace_bytes);
+/* Enqueues the five kernels on `stream`.  table_host = the planned table (read for validation and grid
+ * sizes), table_dev = the same n structs in device memory; src/out/workspace are device buffers of at
+ * least the planned sizes.  Nothing is allocated; the workspace needs no initialisation. */
+int unetb200_enhance_run(const unetb200_enh_crop* table_host, const void* table_dev, int n,
+                         const uint8_t* src_dev, uint8_t* out_dev, void* workspace_dev, void* stream);
 
 #ifdef __cplusplus
 }

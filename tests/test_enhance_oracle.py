@@ -1,0 +1,143 @@
+"""CPU: pins oracle/opencv_enhance.py (the restatement of app_camera.py:572-598, 685-705) against
+(1) golden vectors produced by the reference's own two functions (tests/golden/make_golden_enhance.py)
+and (2) OpenCV executed in this process, step by step."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import opencv_enhance as oe
+from tw_invoice_unet_ocr_llm_b200.synthetic import synthetic_crops_u8
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = np.load(os.path.join(HERE, "golden", "golden_enhance.npz"))
+
+cv2 = pytest.importorskip("cv2")
+
+
+def _images(rng, n, lo=3, hi=160):
+    for t in range(n):
+        h, w = int(rng.integers(lo, hi)), int(rng.integers(lo, hi * 2))
+        if t % 3 == 0:
+            yield rng.integers(0, 256, (h, w), dtype=np.uint8)
+        elif t % 3 == 1:
+            yield np.clip(np.where(rng.random((h, w)) < 0.3, rng.normal(60, 20, (h, w)),
+                                   rng.normal(190, 25, (h, w))), 0, 255).astype(np.uint8)
+        else:
+            yield (rng.integers(0, 2, (h, w)) * 255).astype(np.uint8)
+
+
+def test_golden_chains():
+    n = sum(1 for k in GOLD.files if k.startswith("crop_"))
+    assert n >= 6
+    for i in range(n):
+        rgb = GOLD[f"crop_{i}"]
+        assert np.array_equal(oe.enhance_for_ocrspace(rgb, "text"), GOLD[f"text_{i}"])
+        assert np.array_equal(oe.enhance_for_ocrspace(rgb, "amount"), GOLD[f"amount_{i}"])
+        assert np.array_equal(oe.enhance_for_date_ocr(rgb), GOLD[f"date_{i}"])
+
+
+def test_golden_inputs_are_the_seeded_crops():
+    import json
+    note = json.loads(str(GOLD["note"]))
+    crops = synthetic_crops_u8([tuple(s) for s in note["sizes"]], seed=note["seed"])
+    for i, c in enumerate(crops):
+        assert np.array_equal(c, GOLD[f"crop_{i}"])
+
+
+def test_gray_sharpen_blur_clahe_otsu_against_live_opencv():
+    rng = np.random.default_rng(5)
+    rgb = rng.integers(0, 256, (67, 131, 3), dtype=np.uint8)
+    assert np.array_equal(oe.rgb_to_gray(rgb), cv2.cvtColor(rgb, cv2.COLOR_RGB2GRAY))
+    kernel = np.array([[-1, -1, -1], [-1, 9, -1], [-1, -1, -1]])
+    for g in _images(rng, 18, lo=1):
+        assert np.array_equal(oe.sharpen(g), cv2.filter2D(g, -1, kernel))
+        assert np.array_equal(oe.gaussian_blur3(g), cv2.GaussianBlur(g, (3, 3), 0))
+        t, b = cv2.threshold(g, 0, 255, cv2.THRESH_OTSU)
+        assert oe.otsu_threshold(g) == int(t)
+    for t, g in enumerate(_images(rng, 12, lo=8)):
+        if t % 4 == 0:
+            g = g[:g.shape[0] - g.shape[0] % 8 or 8, :g.shape[1] - g.shape[1] % 8 or 8]
+        for clip in (4.0, 3.0):
+            assert np.array_equal(oe.clahe(g, clip), cv2.createCLAHE(clipLimit=clip, tileGridSize=(8, 8)).apply(g))
+
+
+def test_clahe_tiny_images():
+    """height/width below the 8x8 grid: the reflect-101 extension wraps more than once."""
+    rng = np.random.default_rng(6)
+    for h, w in [(4, 4), (4, 36), (12, 4), (8, 8), (4, 8)]:
+        g = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        assert np.array_equal(oe.clahe(g, 4.0), cv2.createCLAHE(clipLimit=4.0, tileGridSize=(8, 8)).apply(g)), (h, w)
+
+
+_CHILD = r"""
+import sys, numpy as np, cv2
+rng = np.random.default_rng(int(sys.argv[2]))
+out = {}
+for t in range(int(sys.argv[3])):
+    h, w = int(rng.integers(1, 90)), int(rng.integers(1, 150))
+    g = rng.integers(0, 256, (h, w), dtype=np.uint8) if t % 2 else np.clip(rng.normal(200, 40, (h, w)), 0, 255).astype(np.uint8)
+    out[f"g{t}"] = g
+    out[f"r{t}"] = cv2.resize(g, None, fx=4, fy=4, interpolation=cv2.INTER_CUBIC)
+np.savez(sys.argv[1], **out)
+"""
+
+
+def test_resize_against_opencv_native_path(tmp_path):
+    """cv2.resize with Intel IPP disabled (OpenCV's own HResizeCubic / VResizeCubicVec path)."""
+    path = str(tmp_path / "r.npz")
+    env = dict(os.environ, OPENCV_IPP="disabled")
+    subprocess.run([sys.executable, "-c", _CHILD, path, "9", "40"], env=env, check=True, stderr=subprocess.DEVNULL)
+    z = np.load(path)
+    for t in range(40):
+        assert np.array_equal(oe.resize_cubic_x4(z[f"g{t}"]), z[f"r{t}"]), z[f"g{t}"].shape
+
+
+def test_resize_against_installed_opencv_is_within_one():
+    """Whatever cv2.resize the installed wheel uses (IPP here): at most +-1 on a few ppm of pixels."""
+    rng = np.random.default_rng(10)
+    bad = tot = 0
+    for g in _images(rng, 12, lo=2, hi=100):
+        r, o = cv2.resize(g, None, fx=4, fy=4, interpolation=cv2.INTER_CUBIC), oe.resize_cubic_x4(g)
+        d = np.abs(r.astype(int) - o.astype(int))
+        assert d.max() <= 1
+        bad += int((d != 0).sum())
+        tot += d.size
+    assert bad <= 1e-4 * tot
+
+
+def test_c_abi_plan_matches_oracle_geometry():
+    """unetb200_enhance_plan is host-only: CLAHE tile sizes / clip limits equal the oracle's, buffers are
+    packed at 16-byte aligned, non-overlapping offsets, output blocks are numbered consecutively."""
+    from tw_invoice_unet_ocr_llm_b200 import enhance
+    rng = np.random.default_rng(7)
+    sizes = [(int(rng.integers(1, 300)), int(rng.integers(1, 500))) for _ in range(40)] + [(1, 1), (2, 2), (8, 8)]
+    kinds = [("text", "amount", "date")[i % 3] for i in range(len(sizes))]
+    table, sb, ob, wb = enhance.plan(sizes, kinds)
+    blocks = so = oo = wo = 0
+    for (h, w), k, t in zip(sizes, kinds, table):
+        flags, clip = enhance.KINDS[k]
+        assert (flags, clip) == oe.MODES[k]
+        _, _, th, tw = oe.clahe_geometry(4 * h, 4 * w)
+        assert (t.tile_h, t.tile_w) == (th, tw)
+        assert t.clip_count == oe.clahe_clip_limit(clip, th * tw)
+        assert t.first_block == blocks and t.blocks_x == -(-4 * w // 32) and t.n_blocks == t.blocks_x * -(-4 * h // 32)
+        blocks += t.n_blocks
+        assert (t.src_off, t.out_off, t.ws_off) == (so, oo, wo)
+        assert t.src_off % 16 == 0 and t.out_off % 16 == 0 and t.ws_off % 16 == 0
+        so += -(-3 * h * w // 16) * 16
+        oo += -(-16 * h * w // 16) * 16
+        wo += -(-16 * h * w // 16) * 16 + 64 * 256 + 1024 + 16
+    assert (sb, ob, wb) == (so, oo, wo)
+
+
+def test_c_abi_plan_rejects_bad_crops():
+    from tw_invoice_unet_ocr_llm_b200 import _native as nat, enhance
+    for sizes, kinds in [([(0, 4)], ["text"]), ([(4, -1)], ["text"]), ([(9000, 4)], ["text"]),
+                         ([(4, 4)], [(8, 4.0)]), ([(4, 4)], [(1, 0.0)])]:
+        with pytest.raises(nat.UnetB200Error):
+            enhance.plan(sizes, kinds)
+    with pytest.raises(ValueError):
+        enhance.plan([(4, 4)], ["bogus"])

@@ -69,6 +69,44 @@ def test_gpu_preprocess_equals_host_preprocess(checkpoint, cuda_dev):
             assert c1[k].size == c2[k].size
 
 
+def test_near_black_rejection_on_gpu_equals_host(cuda_dev):
+    """reference inference.py:118-125: a crop whose mean is below 3 is dropped.  boxes_to_crops with the
+    frame on the device (integer sums) must decide exactly like the host's ``np.array(crop).mean() < 3``,
+    including means that sit just below / exactly at / just above 3."""
+    from tw_invoice_unet_ocr_llm_b200 import inference as inf
+    rng = np.random.default_rng(90)
+    h, w = 300, 400
+    frame = np.zeros((h, w, 3), np.uint8)
+    # three regions: mean exactly 3, one count below 3, one count above
+    frame[:100] = 3
+    frame[100:200] = 3
+    frame[100, 0, 0] = 2
+    frame[200:] = 3
+    frame[200, 0, 0] = 4
+    frame[:, 300:] = rng.integers(0, 7, (h, 100, 3), dtype=np.uint8)
+    pil = Image.fromarray(frame)
+    dev_frame = torch.from_numpy(frame).to(cuda_dev)
+    sx, sy = 512 / w, 512 / h
+    cases = []
+    for (x1, y1, x2, y2) in [(0, 0, 299, 99), (0, 100, 299, 199), (0, 200, 299, 299), (0, 0, 399, 299),
+                             (310, 10, 390, 290), (0, 100, 10, 101), (0, 200, 3, 203)]:
+        cases.append([int(x1 * sx), int(x2 * sx), int(y1 * sy), int(y2 * sy), 1])
+    cases.append([512, -1, 512, -1, 0])          # empty mask
+    for i in range(0, len(cases), 3):
+        chunk = cases[i:i + 3]
+        while len(chunk) < 3:
+            chunk.append([512, -1, 512, -1, 0])
+        boxes = np.array(chunk, dtype=np.int32)
+        host = inf.boxes_to_crops(pil, boxes)
+        gpu = inf.boxes_to_crops(pil, boxes, dev_frame)
+        for k in inf.FIELDS:
+            assert (host[k] is None) == (gpu[k] is None), (k, chunk)
+            if host[k] is not None:
+                assert host[k].size == gpu[k].size and np.array_equal(np.array(host[k]), np.array(gpu[k]))
+    # the three constructed regions really straddle the threshold
+    assert frame[:100, :300].mean() == 3 and frame[100:200, :300].mean() < 3 < frame[200:, :300].mean()
+
+
 def test_load_model_is_cached_and_strict(checkpoint, cuda_dev):
     from tw_invoice_unet_ocr_llm_b200 import inference as inf
     m1 = inf.load_model(checkpoint)

@@ -80,3 +80,23 @@ def test_gpu_mask_bbox_bit_exact(cuda_dev):
     odd[0, 0, 5:9, 17:23] = 255
     got = prepost.mask_bbox(torch.from_numpy(odd).to(cuda_dev)).cpu().numpy()
     assert tuple(int(v) for v in got[0, 0]) == mask_bbox(odd[0, 0].astype(bool))
+
+
+@pytest.mark.gpu
+def test_gpu_box_sums_exact(cuda_dev):
+    """unetb200_box_sums == numpy sums of the same rectangles (unaligned starts, 1-pixel boxes, the
+    whole frame), for 3- and 4-channel frames."""
+    import torch
+    from tw_invoice_unet_ocr_llm_b200 import prepost
+    rng = np.random.default_rng(12)
+    for (h, w, c) in [(1080, 1920, 3), (333, 517, 3), (64, 50, 4), (5, 7, 1)]:
+        frame = rng.integers(0, 256, (h, w, c), dtype=np.uint8)
+        rects = [(0, 0, w, h), (1, 1, 2, 2), (w - 1, h - 1, w, h), (3, 2, w - 2, h - 1), (0, h // 2, w, h // 2 + 1)]
+        for _ in range(8):
+            x1, y1 = int(rng.integers(0, w)), int(rng.integers(0, h))
+            rects.append((x1, y1, int(rng.integers(x1 + 1, w + 1)), int(rng.integers(y1 + 1, h + 1))))
+        got = prepost.box_sums(torch.from_numpy(frame).to(cuda_dev), rects).cpu().numpy()
+        want = np.array([frame[y1:y2, x1:x2].astype(np.int64).sum() for x1, y1, x2, y2 in rects])
+        assert np.array_equal(got, want), (h, w, c)
+    with pytest.raises(RuntimeError):
+        prepost.box_sums(torch.zeros((4, 4, 3), dtype=torch.uint8, device=cuda_dev), [(0, 0, 5, 4)])

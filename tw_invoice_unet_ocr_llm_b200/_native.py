@@ -38,6 +38,17 @@ class Layer(C.Structure):
     ]
 
 
+class EnhCrop(C.Structure):
+    """``unetb200_enh_crop`` (include/unetb200.h): one crop of an enhancement batch."""
+    _fields_ = [
+        ("h", C.c_int32), ("w", C.c_int32), ("flags", C.c_int32), ("clip", C.c_float),
+        ("clip_count", C.c_int32), ("tile_h", C.c_int32), ("tile_w", C.c_int32),
+        ("first_block", C.c_int32), ("blocks_x", C.c_int32), ("n_blocks", C.c_int32),
+        ("reserved", C.c_int32 * 2),
+        ("src_off", C.c_uint64), ("out_off", C.c_uint64), ("ws_off", C.c_uint64),
+    ]
+
+
 # every symbol include/unetb200.h declares: name -> (restype, argtypes)
 _VP, _I, _U64, _F = C.c_void_p, C.c_int, C.c_uint64, C.c_float
 SYMBOLS = {
@@ -68,6 +79,9 @@ SYMBOLS = {
     "unetb200_resize_coeffs": (_I, [_I, _I, _VP, _VP]),
     "unetb200_resize_bicubic_u8": (_I, [_VP, _I, _I, _I, _I, _VP, _VP, _I, _VP, _VP, _I, _VP, _VP, _I, _I, _VP]),
     "unetb200_mask_bbox": (_I, [_VP, _I, _I, _I, _VP, _VP]),
+    "unetb200_box_sums": (_I, [_VP, _I, _I, _I, C.POINTER(C.c_int32), _I, _VP, _VP]),
+    "unetb200_enhance_plan": (_I, [C.POINTER(EnhCrop), _I, C.POINTER(_U64), C.POINTER(_U64), C.POINTER(_U64)]),
+    "unetb200_enhance_run": (_I, [C.POINTER(EnhCrop), _VP, _I, _VP, _VP, _VP, _VP]),
 }
 
 _lib = None

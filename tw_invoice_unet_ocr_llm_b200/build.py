@@ -39,7 +39,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     """Compile every CUDA source into the shared library; returns its path."""
     if not force and up_to_date():
         return OUT
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", OUT + ".tmp", os.path.join(CSRC, "unet_b200.cu")]
+    cmd = [_nvcc(), *NVCC_FLAGS, "-o", OUT + ".tmp", *sorted(glob.glob(os.path.join(CSRC, "*.cu")))]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     res = subprocess.run(cmd, capture_output=True, text=True)

@@ -120,4 +120,39 @@ __global__ void __launch_bounds__(256) mask_bbox_kernel(const uint8_t* __restric
     }
 }
 
+// Byte sums of up to kMaxBoxes rectangles [x1, x2) x [y1, y2) of one uint8 [h][w][c] frame: the
+// `np.array(crop).mean() < 3` rejection of inference.py:121-125 as an integer test (sum < 3 * count)
+// on the frame that is already on the device.  grid = (row chunks, boxes); sums must start at zero.
+constexpr int kMaxBoxes = 16;
+struct BoxList { int n; int x1[kMaxBoxes], y1[kMaxBoxes], x2[kMaxBoxes], y2[kMaxBoxes]; };
+
+__global__ void __launch_bounds__(256) box_sum_kernel(const uint8_t* __restrict__ img, int w, int c,
+                                                      const __grid_constant__ BoxList boxes,
+                                                      unsigned long long* __restrict__ sums) {
+    const int b = blockIdx.y;
+    const int x1 = boxes.x1[b], y1 = boxes.y1[b], x2 = boxes.x2[b], y2 = boxes.y2[b];
+    const int row_bytes = (x2 - x1) * c;
+    unsigned long long acc = 0;
+    for (int y = y1 + blockIdx.x; y < y2; y += gridDim.x) {
+        const uint8_t* row = img + (static_cast<size_t>(y) * w + x1) * c;
+        // head bytes up to 16-byte alignment, 16-byte body, tail
+        const int head = min(row_bytes, static_cast<int>((16 - (reinterpret_cast<uintptr_t>(row) & 15)) & 15));
+        const int body = (row_bytes - head) / 16;
+        unsigned int part = 0;
+        if (static_cast<int>(threadIdx.x) < head) part += row[threadIdx.x];
+        const uint4* r4 = reinterpret_cast<const uint4*>(row + head);
+        for (int i = threadIdx.x; i < body; i += blockDim.x) {
+            const uint4 v = __ldg(r4 + i);
+            // per-byte sums of four words: __vsadu4(x, 0) adds the four bytes of x
+            part += __vsadu4(v.x, 0u) + __vsadu4(v.y, 0u) + __vsadu4(v.z, 0u) + __vsadu4(v.w, 0u);
+        }
+        const int tail0 = head + body * 16;
+        if (tail0 + static_cast<int>(threadIdx.x) < row_bytes) part += row[tail0 + threadIdx.x];
+        acc += part;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(sums + b, acc);
+}
+
 }  // namespace ub

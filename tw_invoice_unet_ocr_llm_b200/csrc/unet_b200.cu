@@ -6,6 +6,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cmath>
 #include <cstring>
@@ -16,6 +17,7 @@
 #include <vector>
 
 #include "conv_tc.cuh"
+#include "errors.h"
 #include "pack.cuh"
 #include "prepost.cuh"
 #include "stem.cuh"
@@ -28,6 +30,12 @@ int fail(int code, const std::string& msg) {
     g_err = msg;
     return code;
 }
+
+}  // namespace
+
+int ub_fail(int code, const char* msg) { return fail(code, msg); }
+
+namespace {
 
 #define UB_CUDA(expr)                                                                          \
     do {                                                                                       \
@@ -1265,6 +1273,28 @@ int unetb200_mask_bbox(const uint8_t* mask, int n_planes, int h, int w, int32_t*
     ub::mask_bbox_kernel<<<n_planes, 256, 0, static_cast<cudaStream_t>(stream)>>>(mask, h, w, out);
     UB_CUDA(cudaGetLastError());
     return 0;
+}
+
+int unetb200_box_sums(const uint8_t* img, int h, int w, int c, const int32_t* boxes_host, int n_boxes,
+                      uint64_t* sums_dev, void* stream) {
+    if (!img || !boxes_host || !sums_dev || h <= 0 || w <= 0 || c <= 0 || n_boxes <= 0 || n_boxes > ub::kMaxBoxes)
+        return fail(UNETB200_EINVAL, "box_sums: bad argument");
+    ub::BoxList bl;
+    bl.n = n_boxes;
+    int rows = 1;
+    for (int i = 0; i < n_boxes; ++i) {
+        const int32_t* b = boxes_host + 4 * i;
+        if (b[0] < 0 || b[1] < 0 || b[2] > w || b[3] > h || b[2] < b[0] || b[3] < b[1])
+            return fail(UNETB200_EINVAL, "box_sums: rectangle outside the frame");
+        bl.x1[i] = b[0]; bl.y1[i] = b[1]; bl.x2[i] = b[2]; bl.y2[i] = b[3];
+        rows = std::max(rows, b[3] - b[1]);
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    UB_CUDA(cudaMemsetAsync(sums_dev, 0, sizeof(uint64_t) * n_boxes, s));
+    dim3 grid(static_cast<unsigned>(std::min(rows, 296)), static_cast<unsigned>(n_boxes));
+    ub::box_sum_kernel<<<grid, 256, 0, s>>>(img, w, c, bl, reinterpret_cast<unsigned long long*>(sums_dev));
+    UB_CUDA(cudaGetLastError());
+    return UNETB200_OK;
 }
 
 }  // extern "C"

@@ -38,6 +38,7 @@ THRESHOLDS = {"invoice_no": 0.25, "date": 0.40, "total_amount": 0.30}
 MAX_CHUNK = 64            # images per forward in the batched entry points
 
 _model_cache: Dict[tuple, UNet] = {}
+_engine_cache: Dict[tuple, object] = {}     # same key -> the packed replica of that cached model
 _cache_lock = threading.Lock()
 
 
@@ -57,8 +58,24 @@ def load_model(checkpoint_path: str):
             model.load_state_dict(state)
             model.eval()
             _model_cache.clear()          # keep one checkpoint resident
+            _engine_cache.clear()
             _model_cache[key] = model
     return model
+
+
+def _cached_engine(checkpoint_path: str):
+    """(model, engine) of the cached checkpoint.  ``UNet.engine()`` re-validates its packed replica
+    against all 136 tensors on every call (0.9 ms); the cached model is private to this module, so
+    its replica is looked up by the checkpoint key instead."""
+    model = load_model(checkpoint_path)
+    with _cache_lock:
+        key = next((k for k, m in _model_cache.items() if m is model), None)
+        eng = _engine_cache.get(key)
+        if eng is None:
+            eng = model.engine(DEVICE)
+            if key is not None:
+                _engine_cache[key] = eng
+    return model, eng
 
 
 def _resized_rgb_u8(pil_img: Image.Image) -> np.ndarray:
@@ -77,13 +94,13 @@ def preprocess(pil_img: Image.Image):
     return torch.from_numpy(np.ascontiguousarray(arr)).unsqueeze(0).to(DEVICE)
 
 
-def _crop_from_extent(pil_img: Image.Image, extent) -> Optional[Image.Image]:
-    """Mask extent (xmin, xmax, ymin, ymax in 512-space, or None) -> crop of the ORIGINAL image
-    (reference :95-127): scale by (orig / 512) with ``int()`` truncation, grow by 15 % of the box
-    size, clamp to the image; an empty box or a near-black crop (mean < 3) gives ``None``."""
+def _crop_rect(size, extent):
+    """Mask extent (xmin, xmax, ymin, ymax in 512-space, or None) -> crop rectangle (x1, y1, x2, y2) in
+    the ORIGINAL image (reference :95-116): scale by (orig / 512) with ``int()`` truncation, grow by
+    15 % of the box size, clamp to the image; ``None`` for an empty mask or an empty rectangle."""
     if extent is None:
         return None
-    ow, oh = pil_img.size
+    ow, oh = size
     sx, sy = ow / IMG_SIZE, oh / IMG_SIZE
     mx1, mx2, my1, my2 = extent
     x1, x2 = int(mx1 * sx), int(mx2 * sx)
@@ -93,7 +110,16 @@ def _crop_from_extent(pil_img: Image.Image, extent) -> Optional[Image.Image]:
     x2, y2 = min(ow, x2 + px), min(oh, y2 + py)
     if x2 <= x1 or y2 <= y1:
         return None
-    crop = pil_img.crop((x1, y1, x2, y2))
+    return x1, y1, x2, y2
+
+
+def _crop_from_extent(pil_img: Image.Image, extent) -> Optional[Image.Image]:
+    """Extent -> crop of the original image, or ``None`` for an empty box or a near-black crop
+    (``np.array(crop).mean() < 3``, reference :118-125), entirely on the host."""
+    rect = _crop_rect(pil_img.size, extent)
+    if rect is None:
+        return None
+    crop = pil_img.crop(rect)
     arr = np.array(crop)
     return None if (arr.size == 0 or arr.mean() < 3) else crop
 
@@ -109,13 +135,31 @@ def masks_to_crops(pil_img: Image.Image, masks: Dict[str, np.ndarray]) -> Dict[s
     return crops
 
 
-def boxes_to_crops(pil_img: Image.Image, boxes: np.ndarray) -> Dict[str, Optional[Image.Image]]:
+def _extent(box) -> Optional[tuple]:
+    xmin, xmax, ymin, ymax, count = (int(v) for v in box)
+    return None if count == 0 else (xmin, xmax, ymin, ymax)
+
+
+def boxes_to_crops(pil_img: Image.Image, boxes: np.ndarray, frame_dev=None) -> Dict[str, Optional[Image.Image]]:
     """Same, from the GPU reduction ``prepost.mask_bbox``: ``boxes`` int32 [3, 5] = xmin, xmax, ymin,
-    ymax, count per field."""
+    ymax, count per field.  With ``frame_dev`` (the uint8 [H, W, 3] frame already on the device) the
+    near-black test runs there as well: ``mean < 3`` is the integer test ``sum < 3 * bytes`` (exact: the
+    float64 mean of fewer than 2^52 bytes cannot round across 3), so only accepted crops are cut."""
+    if frame_dev is None:
+        return {key: _crop_from_extent(pil_img, _extent(boxes[i])) for i, key in enumerate(FIELDS)}
+    from . import prepost
+    rects = [_crop_rect(pil_img.size, _extent(boxes[i])) for i in range(len(FIELDS))]
+    live = [r for r in rects if r is not None]
+    sums = prepost.box_sums(frame_dev, live).cpu().tolist() if live else []
     crops: Dict[str, Optional[Image.Image]] = {}
-    for i, key in enumerate(FIELDS):
-        xmin, xmax, ymin, ymax, count = (int(v) for v in boxes[i])
-        crops[key] = _crop_from_extent(pil_img, None if count == 0 else (xmin, xmax, ymin, ymax))
+    channels = frame_dev.shape[2]
+    for key, r in zip(FIELDS, rects):
+        if r is None:
+            crops[key] = None
+            continue
+        total = sums.pop(0)
+        nbytes = (r[2] - r[0]) * (r[3] - r[1]) * channels
+        crops[key] = None if total < 3 * nbytes else pil_img.crop(r)
     return crops
 
 
@@ -125,11 +169,10 @@ def _require_cuda():
                            "(the CPU oracle lives in oracle/ and is test-only)")
 
 
-def _segment_u8(model: UNet, frames: np.ndarray):
+def _segment_u8(eng, frames: np.ndarray):
     """uint8 frames (B, 512, 512, 3) -> (uint8 masks (B, 3, 512, 512), int32 boxes (B, 3, 5))."""
     from . import prepost
     _require_cuda()
-    eng = model.engine(DEVICE)
     thr = [THRESHOLDS[f] for f in FIELDS]
     masks = np.empty((frames.shape[0], len(FIELDS), IMG_SIZE, IMG_SIZE), dtype=np.uint8)
     boxes = np.empty((frames.shape[0], len(FIELDS), 5), dtype=np.int32)
@@ -186,19 +229,21 @@ def run_unet(pil_img: Image.Image, checkpoint_path: str):
     """
     from . import prepost
     _require_cuda()
-    model = load_model(checkpoint_path)
-    eng = model.engine(DEVICE)
+    _, eng = _cached_engine(checkpoint_path)
     thr = [THRESHOLDS[f] for f in FIELDS]
+    frame = None
     # the reference resizes twice (:63 then :35); the second resize is the identity
     if _gpu_resizable(pil_img):
-        x = prepost.resize_u8(_upload_rgb(pil_img), IMG_SIZE, IMG_SIZE)   # the resized frame never leaves the GPU
+        frame = _upload_rgb(pil_img)                       # uint8 [1, H, W, 3]; stays on the GPU
+        x = prepost.resize_u8(frame, IMG_SIZE, IMG_SIZE)   # the resized frame never leaves the GPU
     else:
         x = torch.from_numpy(_resized_rgb_u8(pil_img.resize((IMG_SIZE, IMG_SIZE)))[None]).to(DEVICE)
     _, mask = eng.run(x, want_logits=False, thresholds=thr)
     boxes = prepost.mask_bbox(mask)
     m = mask[0].cpu().numpy()
-    masks = {f: m[i].astype(bool) for i, f in enumerate(FIELDS)}
-    return masks, boxes_to_crops(pil_img, boxes[0].cpu().numpy())
+    masks = {f: m[i] != 0 for i, f in enumerate(FIELDS)}
+    crops = boxes_to_crops(pil_img, boxes[0].cpu().numpy(), None if frame is None else frame[0])
+    return masks, crops
 
 
 def run_unet_batch(pil_imgs: Sequence[Image.Image], checkpoint_path: str
@@ -207,8 +252,8 @@ def run_unet_batch(pil_imgs: Sequence[Image.Image], checkpoint_path: str
     if len(pil_imgs) == 0:
         return []
     _require_cuda()
-    model = load_model(checkpoint_path)
-    m, boxes = _segment_u8(model, _frames_512(pil_imgs))
+    _, eng = _cached_engine(checkpoint_path)
+    m, boxes = _segment_u8(eng, _frames_512(pil_imgs))
     out = []
     for b, im in enumerate(pil_imgs):
         masks = {f: m[b, i].astype(bool) for i, f in enumerate(FIELDS)}

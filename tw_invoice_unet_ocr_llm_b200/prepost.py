@@ -81,3 +81,20 @@ def mask_bbox(mask: torch.Tensor) -> torch.Tensor:
         nat.check(nat.lib().unetb200_mask_bbox(mask.data_ptr(), n * c, h, w, out.data_ptr(),
                                                torch.cuda.current_stream(mask.device).cuda_stream))
     return out
+
+
+def box_sums(frame: torch.Tensor, rects) -> torch.Tensor:
+    """uint8 ``[H, W, C]`` frame on a CUDA device + up to 16 half-open rectangles ``(x1, y1, x2, y2)``
+    -> int64 ``[n]`` byte sums on the device (the ``np.array(crop).mean() < 3`` test of reference
+    inference.py:121-125 becomes ``sum < 3 * area * C``).  Enqueued on the current stream."""
+    if frame.dtype != torch.uint8 or frame.dim() != 3 or not frame.is_cuda or not frame.is_contiguous():
+        raise RuntimeError("box_sums expects a contiguous CUDA uint8 [H,W,C] tensor")
+    import ctypes as C
+    h, w, c = frame.shape
+    n = len(rects)
+    flat = (C.c_int32 * (4 * n))(*[int(v) for r in rects for v in r])
+    out = torch.empty((n,), dtype=torch.int64, device=frame.device)
+    with torch.cuda.device(frame.device):
+        nat.check(nat.lib().unetb200_box_sums(frame.data_ptr(), h, w, c, flat, n, out.data_ptr(),
+                                              torch.cuda.current_stream(frame.device).cuda_stream))
+    return out

@@ -98,3 +98,13 @@ def make_fixture_state(seed: int = 1234, calib_size: int = 64, calib_batches: in
     finally:
         torch.random.set_rng_state(gen_state)
     return state
+
+
+def synthetic_crops_u8(sizes, seed: int = 11) -> list:
+    """uint8 ``(h, w, 3)`` field crops of the given ``(h, w)`` sizes, the kind ``run_unet`` hands to
+    the OCR stage: a window of a synthetic invoice around dark strokes on light paper."""
+    out = []
+    for i, (h, w) in enumerate(sizes):
+        page = synthetic_invoices_u8(1, max(64, 2 * h), max(64, 2 * w), seed=seed + i)[0]
+        out.append(np.ascontiguousarray(page[:h, :w]))
+    return out
