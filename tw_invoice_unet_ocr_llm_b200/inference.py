@@ -169,29 +169,13 @@ def _require_cuda():
                            "(the CPU oracle lives in oracle/ and is test-only)")
 
 
-def _segment_u8(eng, frames: np.ndarray):
-    """uint8 frames (B, 512, 512, 3) -> (uint8 masks (B, 3, 512, 512), int32 boxes (B, 3, 5))."""
-    from . import prepost
-    _require_cuda()
-    thr = [THRESHOLDS[f] for f in FIELDS]
-    masks = np.empty((frames.shape[0], len(FIELDS), IMG_SIZE, IMG_SIZE), dtype=np.uint8)
-    boxes = np.empty((frames.shape[0], len(FIELDS), 5), dtype=np.int32)
-    for lo in range(0, frames.shape[0], MAX_CHUNK):
-        chunk = torch.from_numpy(np.ascontiguousarray(frames[lo:lo + MAX_CHUNK])).pin_memory()
-        x = chunk.to(eng.device, non_blocking=True)
-        _, mask = eng.run(x, want_logits=False, thresholds=thr)
-        box = prepost.mask_bbox(mask)
-        masks[lo:lo + MAX_CHUNK] = mask.cpu().numpy()
-        boxes[lo:lo + MAX_CHUNK] = box.cpu().numpy()
-    return masks, boxes
-
-
 _staging: Dict[tuple, torch.Tensor] = {}
 
 
-def _upload_rgb(pil_img: Image.Image) -> torch.Tensor:
+def _upload_rgb(pil_img: Image.Image, wait: bool = False) -> torch.Tensor:
     """RGB PIL image -> uint8 [1, H, W, 3] on DEVICE through a cached pinned staging buffer.
-    Callers synchronise (``.cpu()``) before the next call, so the buffer is free to reuse."""
+    Callers synchronise (``.cpu()``) before the next call, so the buffer is free to reuse; with
+    ``wait`` the copy is awaited here (several uploads back to back)."""
     arr = np.asarray(pil_img)
     key = (threading.get_ident(), arr.shape)
     buf = _staging.get(key)
@@ -200,7 +184,10 @@ def _upload_rgb(pil_img: Image.Image) -> torch.Tensor:
             _staging.clear()
         buf = _staging[key] = torch.empty(arr.shape, dtype=torch.uint8).pin_memory()
     buf.numpy()[...] = arr
-    return buf.to(DEVICE, non_blocking=True)[None]
+    dev = buf.to(DEVICE, non_blocking=True)[None]
+    if wait:
+        torch.cuda.current_stream().synchronize()
+    return dev
 
 
 def _gpu_resizable(pil_img: Image.Image) -> bool:
@@ -209,16 +196,35 @@ def _gpu_resizable(pil_img: Image.Image) -> bool:
     return pil_img.mode == "RGB" and pil_img.size[0] > 0 and pil_img.size[1] > 0
 
 
-def _frames_512(pil_imgs: Sequence[Image.Image]) -> np.ndarray:
-    """Resized uint8 frames (B, 512, 512, 3): on the GPU for plain RGB inputs, PIL otherwise."""
+def _segment_images(eng, pil_imgs: Sequence[Image.Image]):
+    """Images -> (uint8 masks (B, 3, 512, 512), per-image crops).  Per chunk of ``MAX_CHUNK`` images:
+    plain RGB frames are uploaded raw and resized on the GPU straight into their slot of the batch
+    tensor (other modes: the reference's PIL calls on the host), one forward, one mask -> box reduction,
+    one download; the uploaded frames stay on the device for the near-black crop test."""
     from . import prepost
-    out = np.empty((len(pil_imgs), IMG_SIZE, IMG_SIZE, 3), dtype=np.uint8)
-    for i, im in enumerate(pil_imgs):
-        if DEVICE == "cuda" and _gpu_resizable(im):
-            out[i] = prepost.resize_u8(_upload_rgb(im), IMG_SIZE, IMG_SIZE)[0].cpu().numpy()
-        else:
-            out[i] = _resized_rgb_u8(im.resize((IMG_SIZE, IMG_SIZE)))
-    return out
+    _require_cuda()
+    thr = [THRESHOLDS[f] for f in FIELDS]
+    masks = np.empty((len(pil_imgs), len(FIELDS), IMG_SIZE, IMG_SIZE), dtype=np.uint8)
+    crops = []
+    for lo in range(0, len(pil_imgs), MAX_CHUNK):
+        chunk = pil_imgs[lo:lo + MAX_CHUNK]
+        x = torch.empty((len(chunk), IMG_SIZE, IMG_SIZE, 3), dtype=torch.uint8, device=DEVICE)
+        frames = []
+        for i, im in enumerate(chunk):
+            if _gpu_resizable(im):
+                # fresh device copy per image (the pinned staging buffer is reused after the copy lands)
+                f = _upload_rgb(im, wait=True)
+                prepost.resize_u8(f, IMG_SIZE, IMG_SIZE, out=x[i:i + 1])
+                frames.append(f[0])
+            else:
+                x[i].copy_(torch.from_numpy(_resized_rgb_u8(im.resize((IMG_SIZE, IMG_SIZE)))))
+                frames.append(None)
+        _, mask = eng.run(x, want_logits=False, thresholds=thr)
+        boxes = prepost.mask_bbox(mask).cpu().numpy()
+        masks[lo:lo + len(chunk)] = mask.cpu().numpy()
+        for im, bx, f in zip(chunk, boxes, frames):
+            crops.append(boxes_to_crops(im, bx, f))
+    return masks, crops
 
 
 def run_unet(pil_img: Image.Image, checkpoint_path: str):
@@ -253,9 +259,5 @@ def run_unet_batch(pil_imgs: Sequence[Image.Image], checkpoint_path: str
         return []
     _require_cuda()
     _, eng = _cached_engine(checkpoint_path)
-    m, boxes = _segment_u8(eng, _frames_512(pil_imgs))
-    out = []
-    for b, im in enumerate(pil_imgs):
-        masks = {f: m[b, i].astype(bool) for i, f in enumerate(FIELDS)}
-        out.append((masks, boxes_to_crops(im, boxes[b])))
-    return out
+    m, crops = _segment_images(eng, list(pil_imgs))
+    return [({f: m[b, i] != 0 for i, f in enumerate(FIELDS)}, crops[b]) for b in range(len(pil_imgs))]

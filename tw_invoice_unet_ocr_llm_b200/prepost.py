@@ -44,15 +44,23 @@ def _tables(in_size: int, out_size: int, device: torch.device):
     return t
 
 
-def resize_u8(frames: torch.Tensor, oh: int, ow: int) -> torch.Tensor:
+def resize_u8(frames: torch.Tensor, oh: int, ow: int, out: torch.Tensor = None) -> torch.Tensor:
     """uint8 ``[N, H, W, C]`` on a CUDA device -> uint8 ``[N, oh, ow, C]``, bit-identical to
-    ``PIL.Image.resize((ow, oh))`` (default BICUBIC) of each frame.  Enqueued on the current stream."""
+    ``PIL.Image.resize((ow, oh))`` (default BICUBIC) of each frame.  Enqueued on the current stream.
+    ``out``: optional contiguous destination (e.g. a slot of a batch tensor)."""
     if frames.dtype != torch.uint8 or frames.dim() != 4 or not frames.is_cuda:
         raise RuntimeError("resize_u8 expects a CUDA uint8 [N,H,W,C] tensor")
     frames = frames.contiguous()
     n, h, w, c = frames.shape
     dev = frames.device
-    out = torch.empty((n, oh, ow, c), dtype=torch.uint8, device=dev)
+    if out is None:
+        out = torch.empty((n, oh, ow, c), dtype=torch.uint8, device=dev)
+    elif (out.dtype != torch.uint8 or tuple(out.shape) != (n, oh, ow, c) or out.device != dev
+          or not out.is_contiguous()):
+        raise RuntimeError("resize_u8: out must be a contiguous uint8 [N,oh,ow,C] tensor on the same device")
+    if oh == h and ow == w:
+        out.copy_(frames)
+        return out
     kx = bx = ky = by = tmp = None
     ksx = ksy = 0
     if ow != w:
