@@ -397,6 +397,15 @@ def main():
                             ts.append((time.perf_counter() - t0) * 1e3)
                     ts.sort()
                     res[tag] = {"p50_ms": ts[len(ts) // 2], "p95_ms": ts[int(len(ts) * 0.95)]}
+                # + the crop enhancement the app applies next (app_camera.py:800-811), same device frame
+                ts = []
+                for i in range(60):
+                    t0 = time.perf_counter()
+                    inf.run_unet_enhanced(rgb, ckpt)
+                    if i >= 10:
+                        ts.append((time.perf_counter() - t0) * 1e3)
+                ts.sort()
+                res["with_crop_enhancement"] = {"p50_ms": ts[len(ts) // 2], "p95_ms": ts[int(len(ts) * 0.95)]}
             if lat is not None:
                 lat["run_unet_1080p"] = res
         except Exception as e:          # informational only

@@ -188,13 +188,16 @@ typedef struct unetb200_enh_crop {
     int32_t first_block;      /* out: index of this crop's first 32x32 output block in the batch */
     int32_t blocks_x;         /* out: output blocks per row */
     int32_t n_blocks;         /* out: output blocks of this crop */
-    int32_t reserved[2];
-    uint64_t src_off;         /* out: byte offset of the uint8 [h][w][3] crop in `src` */
+    int32_t src_stride;       /* in : pixels per source row; 0 = the crop is packed ([h][w][3], plan places it),
+                               *      > w = the crop is a window of a larger frame already in `src` */
+    int32_t reserved;
+    uint64_t src_off;         /* out (in when src_stride != 0): byte offset of the crop's first pixel in `src` */
     uint64_t out_off;         /* out: byte offset of the uint8 [4h][4w] result in `out` */
     uint64_t ws_off;          /* out: byte offset of this crop's scratch in `workspace` */
 } unetb200_enh_crop;
 /* Host only: fills the `out` fields of table[0..n) from the `in` fields and returns the sizes of the
- * three device buffers (crops packed back to back at 16-byte aligned offsets). */
+ * three device buffers (packed crops back to back at 16-byte aligned offsets; windows of a frame
+ * (src_stride != 0) keep their src_off and take no room in src_bytes). */
 int unetb200_enhance_plan(unetb200_enh_crop* table, int n, uint64_t* src_bytes, uint64_t* out_bytes,
                           uint64_t* workspace_bytes);
 /* Enqueues the five kernels on `stream`.  table_host = the planned table (read for validation and grid

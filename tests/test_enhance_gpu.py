@@ -137,3 +137,21 @@ def test_bad_arguments(cuda_dev):
         enhance.enhance_batch([np.zeros((4, 4), np.uint8)], ["text"])
     with pytest.raises(ValueError):
         enhance.enhance_batch([np.zeros((4, 4, 3), np.uint8)], ["text", "date"])
+
+
+def test_windows_of_a_device_frame_equal_packed_crops(cuda_dev):
+    """enhance_windows reads the crops in place from a frame in HBM (row stride = frame width)."""
+    import torch
+    from tw_invoice_unet_ocr_llm_b200 import enhance
+    from tw_invoice_unet_ocr_llm_b200.synthetic import synthetic_invoices_u8
+    frame = synthetic_invoices_u8(1, 360, 640, seed=71)[0]
+    rects = [(0, 0, 640, 360), (3, 5, 4, 6), (639, 359, 640, 360), (17, 40, 230, 91), (401, 100, 640, 133), (0, 300, 77, 360)]
+    kinds = ["text", "amount", "date", "text", "date", "amount"]
+    got = enhance.enhance_windows(torch.from_numpy(frame).to(cuda_dev), rects, kinds)
+    packed = enhance.enhance_batch([frame[y1:y2, x1:x2] for x1, y1, x2, y2 in rects], kinds)
+    for g, p, (x1, y1, x2, y2), k in zip(got, packed, rects, kinds):
+        assert np.array_equal(g, p)
+        assert np.array_equal(g, _oracle(np.ascontiguousarray(frame[y1:y2, x1:x2]), k))
+    with pytest.raises(ValueError):
+        enhance.enhance_windows(torch.from_numpy(frame).to(cuda_dev), [(0, 0, 641, 10)], ["text"])
+    assert enhance.enhance_windows(torch.from_numpy(frame).to(cuda_dev), [], []) == []

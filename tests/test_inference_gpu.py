@@ -107,6 +107,36 @@ def test_near_black_rejection_on_gpu_equals_host(cuda_dev):
     assert frame[:100, :300].mean() == 3 and frame[100:200, :300].mean() < 3 < frame[200:, :300].mean()
 
 
+def test_run_unet_enhanced_matches_reference_helpers(checkpoint, cuda_dev):
+    """run_unet_enhanced = run_unet + the app's enhance_for_ocrspace calls (app_camera.py:787-811) on the
+    device frame; the enhanced images must equal the OpenCV oracle applied to the returned PIL crops, and
+    the RGB (device) and RGBA (host preprocessing) routes must agree."""
+    from oracle import opencv_enhance as oe
+    from tw_invoice_unet_ocr_llm_b200 import inference as inf
+    from tw_invoice_unet_ocr_llm_b200.synthetic import synthetic_invoices_u8
+    rgb = Image.fromarray(synthetic_invoices_u8(1, 540, 960, seed=83)[0])
+    masks, crops, enhanced = inf.run_unet_enhanced(rgb, checkpoint)
+    m0, c0 = inf.run_unet(rgb, checkpoint)
+    assert list(enhanced) == inf.FIELDS
+    n_live = 0
+    for k in inf.FIELDS:
+        assert np.array_equal(masks[k], m0[k])
+        assert (crops[k] is None) == (c0[k] is None) == (enhanced[k] is None)
+        if crops[k] is None:
+            continue
+        n_live += 1
+        assert crops[k].size == c0[k].size
+        want = oe.enhance_for_ocrspace(np.array(crops[k].convert("RGB")), "text" if inf.ENHANCE_KINDS[k] == "text" else "amount")
+        assert enhanced[k].mode == "L" and enhanced[k].size == (4 * crops[k].size[0], 4 * crops[k].size[1])
+        assert np.array_equal(np.array(enhanced[k]), want), k
+    assert n_live >= 1
+    _, crops_a, enh_a = inf.run_unet_enhanced(rgb.convert("RGBA"), checkpoint)
+    for k in inf.FIELDS:
+        assert (enh_a[k] is None) == (enhanced[k] is None)
+        if enhanced[k] is not None:
+            assert np.array_equal(np.array(enh_a[k]), np.array(enhanced[k]))
+
+
 def test_load_model_is_cached_and_strict(checkpoint, cuda_dev):
     from tw_invoice_unet_ocr_llm_b200 import inference as inf
     m1 = inf.load_model(checkpoint)

@@ -44,7 +44,7 @@ class EnhCrop(C.Structure):
         ("h", C.c_int32), ("w", C.c_int32), ("flags", C.c_int32), ("clip", C.c_float),
         ("clip_count", C.c_int32), ("tile_h", C.c_int32), ("tile_w", C.c_int32),
         ("first_block", C.c_int32), ("blocks_x", C.c_int32), ("n_blocks", C.c_int32),
-        ("reserved", C.c_int32 * 2),
+        ("src_stride", C.c_int32), ("reserved", C.c_int32),
         ("src_off", C.c_uint64), ("out_off", C.c_uint64), ("ws_off", C.c_uint64),
     ]
 

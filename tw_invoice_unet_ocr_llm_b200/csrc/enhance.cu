@@ -6,6 +6,8 @@
 
 #include "errors.h"
 
+static_assert(sizeof(unetb200_enh_crop) == 72, "unetb200_enh_crop layout is part of the ABI");
+
 namespace {
 
 // cv::interpolateCubic (A = -0.75) in float, then saturate_cast<short>(c * INTER_RESIZE_COEF_SCALE)
@@ -31,7 +33,8 @@ constexpr int kMaxSide = 8192;          // 4x -> 32768: keeps every int product 
 
 bool crop_ok(const unetb200_enh_crop& c) {
     return c.h > 0 && c.w > 0 && c.h <= kMaxSide && c.w <= kMaxSide &&
-           (c.flags & ~(UNETB200_ENH_SHARPEN | UNETB200_ENH_BLUR | UNETB200_ENH_OTSU)) == 0 && c.clip > 0.f;
+           (c.flags & ~(UNETB200_ENH_SHARPEN | UNETB200_ENH_BLUR | UNETB200_ENH_OTSU)) == 0 && c.clip > 0.f &&
+           (c.src_stride == 0 || c.src_stride >= c.w);
 }
 
 }  // namespace
@@ -69,11 +72,14 @@ int unetb200_enhance_plan(unetb200_enh_crop* table, int n, uint64_t* src_bytes, 
         if (blocks + c.n_blocks > 0x7fffffff) return ub_fail(UNETB200_EINVAL, "enhance_plan: batch too large");
         c.first_block = static_cast<int32_t>(blocks);
         blocks += c.n_blocks;
-        c.reserved[0] = c.reserved[1] = 0;
-        c.src_off = so;
+        c.reserved = 0;
+        if (c.src_stride == 0) {             // packed crop: placed here
+            c.src_stride = c.w;
+            c.src_off = so;
+            so += (static_cast<uint64_t>(3) * c.h * c.w + 15) & ~static_cast<uint64_t>(15);
+        }
         c.out_off = oo;
         c.ws_off = wo;
-        so += (static_cast<uint64_t>(3) * c.h * c.w + 15) & ~static_cast<uint64_t>(15);
         oo += ub::enh_img_bytes(c.h, c.w);
         wo += ub::enh_ws_bytes(c.h, c.w);
     }
@@ -85,19 +91,23 @@ int unetb200_enhance_plan(unetb200_enh_crop* table, int n, uint64_t* src_bytes, 
 
 int unetb200_enhance_run(const unetb200_enh_crop* table_host, const void* table_dev, int n,
                          const uint8_t* src_dev, uint8_t* out_dev, void* workspace_dev, void* stream) {
-    if (!table_host || !table_dev || n <= 0 || !src_dev || !out_dev || !workspace_dev)
+    if (!table_host || !table_dev || n <= 0 || !src_dev || !out_dev || !workspace_dev)  // src_dev: packed crops and/or the frame
         return ub_fail(UNETB200_EINVAL, "enhance_run: bad argument");
     if ((reinterpret_cast<uintptr_t>(out_dev) | reinterpret_cast<uintptr_t>(workspace_dev) |
          reinterpret_cast<uintptr_t>(table_dev)) & 15)
         return ub_fail(UNETB200_EINVAL, "enhance_run: device buffers must be 16-byte aligned");
     int64_t blocks = 0;
+    uint64_t out_bytes = 0;
     bool any_otsu = false;
     for (int i = 0; i < n; ++i) {
         const unetb200_enh_crop& c = table_host[i];
-        if (!crop_ok(c) || c.first_block != blocks || c.n_blocks <= 0 || c.tile_h <= 0 || c.tile_w <= 0 ||
+        if (!crop_ok(c) || c.src_stride < c.w || c.first_block != blocks || c.n_blocks <= 0 || c.tile_h <= 0 || c.tile_w <= 0 ||
             c.blocks_x != (4 * c.w + ub::kEnhBlock - 1) / ub::kEnhBlock)
             return ub_fail(UNETB200_EINVAL, "enhance_run: table was not produced by unetb200_enhance_plan");
+        if (c.out_off != out_bytes)
+            return ub_fail(UNETB200_EINVAL, "enhance_run: table was not produced by unetb200_enhance_plan");
         blocks += c.n_blocks;
+        out_bytes += ub::enh_img_bytes(c.h, c.w);
         any_otsu = any_otsu || (c.flags & UNETB200_ENH_OTSU);
     }
     if (static_cast<int64_t>(n) * ub::kEnhTiles * ub::kEnhTiles > 0x7fffffff)
@@ -107,12 +117,15 @@ int unetb200_enhance_run(const unetb200_enh_crop* table_host, const void* table_
     const auto* tab = static_cast<const unetb200_enh_crop*>(table_dev);
     uint8_t* ws = static_cast<uint8_t*>(workspace_dev);
     const unsigned nb = static_cast<unsigned>(blocks);
-    ub::enh_resize_kernel<<<nb, ub::kEnhThreads, 0, s>>>(tab, n, src_dev, ws, taps);
+    // persistent grid for the upscale: 148 SMs x 8 resident CTAs walk the block list
+    const unsigned grid = nb < 148u * 8u ? nb : 148u * 8u;
+    ub::enh_resize_kernel<<<grid, ub::kEnhThreads, 0, s>>>(tab, n, static_cast<int>(nb), src_dev, ws, taps);
     ub::enh_lut_kernel<<<static_cast<unsigned>(n) * ub::kEnhTiles * ub::kEnhTiles, ub::kEnhThreads, 0, s>>>(tab, ws);
     ub::enh_clahe_kernel<<<nb, ub::kEnhThreads, 0, s>>>(tab, n, ws, out_dev);
     if (any_otsu) {
         ub::enh_otsu_kernel<<<static_cast<unsigned>(n), 32, 0, s>>>(tab, ws);
-        ub::enh_binarize_kernel<<<nb, ub::kEnhThreads, 0, s>>>(tab, n, ws, out_dev);
+        const unsigned spans = static_cast<unsigned>((out_bytes + ub::kEnhBinSpan - 1) / ub::kEnhBinSpan);
+        ub::enh_binarize_kernel<<<spans, ub::kEnhThreads, 0, s>>>(tab, n, ws, out_dev, out_bytes);
     }
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {

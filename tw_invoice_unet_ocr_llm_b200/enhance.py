@@ -77,6 +77,21 @@ def plan(sizes: Sequence[tuple], kinds: Sequence):
     return table, sb.value, ob.value, wb.value
 
 
+def _execute(table, n: int, table_dev_ptr: int, src_ptr: int, out_bytes: int, ws_bytes: int, dev, keep) -> list:
+    """Run the five kernels on the current stream and bring the results back: list of uint8 (4h, 4w)."""
+    stream = torch.cuda.current_stream(dev)
+    d_out = torch.empty(out_bytes, dtype=torch.uint8, device=dev)
+    d_ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    nat.check(nat.lib().unetb200_enhance_run(table, table_dev_ptr, n, src_ptr, d_out.data_ptr(), d_ws.data_ptr(),
+                                             stream.cuda_stream))
+    down = _pinned("down", out_bytes)
+    down[:out_bytes].copy_(d_out, non_blocking=True)
+    stream.synchronize()
+    del keep                                   # inputs stay referenced until the stream has drained
+    res = down.numpy()
+    return [res[t.out_off: t.out_off + 16 * t.h * t.w].reshape(4 * t.h, 4 * t.w).copy() for t in table]
+
+
 def enhance_batch(crops: Sequence, kinds: Sequence, device=None) -> List[Optional[np.ndarray]]:
     """Enhance many crops at once.  ``crops``: PIL images or uint8 (h, w, 3) RGB arrays (``None``
     entries pass through); ``kinds``: "text" | "amount" | "date" per crop (or an explicit
@@ -94,7 +109,6 @@ def enhance_batch(crops: Sequence, kinds: Sequence, device=None) -> List[Optiona
         return out
     arrays = [_as_rgb_array(crops[i]) for i in live]
     table, src_bytes, out_bytes, ws_bytes = plan([a.shape[:2] for a in arrays], [kinds[i] for i in live])
-    n = len(live)
     tab_bytes = (C.sizeof(table) + 15) & ~15
     stage = _pinned("up", tab_bytes + src_bytes)
     host = stage.numpy()
@@ -102,21 +116,40 @@ def enhance_batch(crops: Sequence, kinds: Sequence, device=None) -> List[Optiona
     for a, t in zip(arrays, table):
         host[tab_bytes + t.src_off: tab_bytes + t.src_off + a.size] = a.reshape(-1)
     with torch.cuda.device(dev):
-        stream = torch.cuda.current_stream(dev)
         d_in = torch.empty(tab_bytes + src_bytes, dtype=torch.uint8, device=dev)
         d_in.copy_(stage[:tab_bytes + src_bytes], non_blocking=True)
-        d_out = torch.empty(out_bytes, dtype=torch.uint8, device=dev)
-        d_ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        nat.check(nat.lib().unetb200_enhance_run(table, d_in.data_ptr(), n, d_in.data_ptr() + tab_bytes,
-                                                 d_out.data_ptr(), d_ws.data_ptr(), stream.cuda_stream))
-        down = _pinned("down", out_bytes)
-        down[:out_bytes].copy_(d_out, non_blocking=True)
-        stream.synchronize()
-    res = down.numpy()
-    for i, a, t in zip(live, arrays, table):
-        h4, w4 = 4 * a.shape[0], 4 * a.shape[1]
-        out[i] = res[t.out_off: t.out_off + h4 * w4].reshape(h4, w4).copy()
+        res = _execute(table, len(live), d_in.data_ptr(), d_in.data_ptr() + tab_bytes, out_bytes, ws_bytes, dev, d_in)
+    for i, r in zip(live, res):
+        out[i] = r
     return out
+
+
+def enhance_windows(frame: torch.Tensor, rects: Sequence[tuple], kinds: Sequence) -> List[np.ndarray]:
+    """Enhance rectangles ``(x1, y1, x2, y2)`` (half-open) of a uint8 ``[H, W, 3]`` RGB frame that is
+    already on the device -- the crops ``run_unet`` cuts from the frame it uploaded -- without packing or
+    re-uploading them: only the 72-byte descriptors go up."""
+    if frame.dtype != torch.uint8 or frame.dim() != 3 or frame.shape[2] != 3 or not frame.is_cuda \
+            or not frame.is_contiguous():
+        raise RuntimeError("enhance_windows expects a contiguous CUDA uint8 [H,W,3] frame")
+    if len(rects) != len(kinds):
+        raise ValueError("rects and kinds differ in length")
+    if not rects:
+        return []
+    fh, fw = int(frame.shape[0]), int(frame.shape[1])
+    n = len(rects)
+    table = (nat.EnhCrop * n)()
+    for t, (x1, y1, x2, y2), kind in zip(table, rects, kinds):
+        x1, y1, x2, y2 = int(x1), int(y1), int(x2), int(y2)
+        if not (0 <= x1 < x2 <= fw and 0 <= y1 < y2 <= fh):
+            raise ValueError(f"rectangle {(x1, y1, x2, y2)} outside the {fw}x{fh} frame")
+        t.flags, t.clip = _recipe(kind)
+        t.h, t.w, t.src_stride, t.src_off = y2 - y1, x2 - x1, fw, (y1 * fw + x1) * 3
+    sb, ob, wb = C.c_uint64(), C.c_uint64(), C.c_uint64()
+    nat.check(nat.lib().unetb200_enhance_plan(table, n, C.byref(sb), C.byref(ob), C.byref(wb)))
+    dev = frame.device
+    with torch.cuda.device(dev):
+        d_tab = torch.frombuffer(bytearray(table), dtype=torch.uint8).to(dev)
+        return _execute(table, n, d_tab.data_ptr(), frame.data_ptr(), ob.value, wb.value, dev, (d_tab, frame))
 
 
 def enhance_for_ocrspace(pil_crop, mode: str = "text"):

@@ -140,7 +140,8 @@ def _extent(box) -> Optional[tuple]:
     return None if count == 0 else (xmin, xmax, ymin, ymax)
 
 
-def boxes_to_crops(pil_img: Image.Image, boxes: np.ndarray, frame_dev=None) -> Dict[str, Optional[Image.Image]]:
+def boxes_to_crops(pil_img: Image.Image, boxes: np.ndarray, frame_dev=None, rects_out: Optional[dict] = None
+                   ) -> Dict[str, Optional[Image.Image]]:
     """Same, from the GPU reduction ``prepost.mask_bbox``: ``boxes`` int32 [3, 5] = xmin, xmax, ymin,
     ymax, count per field.  With ``frame_dev`` (the uint8 [H, W, 3] frame already on the device) the
     near-black test runs there as well: ``mean < 3`` is the integer test ``sum < 3 * bytes`` (exact: the
@@ -160,6 +161,8 @@ def boxes_to_crops(pil_img: Image.Image, boxes: np.ndarray, frame_dev=None) -> D
         total = sums.pop(0)
         nbytes = (r[2] - r[0]) * (r[3] - r[1]) * channels
         crops[key] = None if total < 3 * nbytes else pil_img.crop(r)
+        if rects_out is not None and crops[key] is not None:
+            rects_out[key] = r
     return crops
 
 
@@ -250,6 +253,42 @@ def run_unet(pil_img: Image.Image, checkpoint_path: str):
     masks = {f: m[i] != 0 for i, f in enumerate(FIELDS)}
     crops = boxes_to_crops(pil_img, boxes[0].cpu().numpy(), None if frame is None else frame[0])
     return masks, crops
+
+
+# which enhancement the app applies to which field before OCR.space (reference app_camera.py:800-811)
+ENHANCE_KINDS = {"invoice_no": "text", "date": "text", "total_amount": "amount"}
+
+
+def run_unet_enhanced(pil_img: Image.Image, checkpoint_path: str):
+    """``run_unet`` plus the crop enhancement the app applies next (reference app_camera.py:787-811:
+    ``enhance_for_ocrspace(crop, "text")`` for invoice number and date, ``"amount"`` for the total), as
+    one device pipeline: the frame is uploaded once, resized, segmented, reduced to boxes, tested for
+    near-black crops and enhanced from the same device buffer.  New, additive.
+
+    Returns ``(masks, crops, enhanced)``; ``enhanced``: dict field -> mode-"L" ``PIL.Image`` (four times
+    the crop size) or ``None``, equal to what the reference's helpers return for ``crops[field]``."""
+    from . import enhance, prepost
+    _require_cuda()
+    _, eng = _cached_engine(checkpoint_path)
+    thr = [THRESHOLDS[f] for f in FIELDS]
+    if not _gpu_resizable(pil_img):
+        masks, crops = run_unet(pil_img, checkpoint_path)
+        live = [f for f in FIELDS if crops[f] is not None]
+        arrs = enhance.enhance_batch([crops[f] for f in live], [ENHANCE_KINDS[f] for f in live])
+        done = dict(zip(live, arrs))
+        return masks, crops, {f: Image.fromarray(done[f]) if f in done else None for f in FIELDS}
+    frame = _upload_rgb(pil_img)
+    x = prepost.resize_u8(frame, IMG_SIZE, IMG_SIZE)
+    _, mask = eng.run(x, want_logits=False, thresholds=thr)
+    boxes = prepost.mask_bbox(mask)
+    m = mask[0].cpu().numpy()
+    masks = {f: m[i] != 0 for i, f in enumerate(FIELDS)}
+    rects: dict = {}
+    crops = boxes_to_crops(pil_img, boxes[0].cpu().numpy(), frame[0], rects)
+    live = [f for f in FIELDS if f in rects]
+    arrs = enhance.enhance_windows(frame[0], [rects[f] for f in live], [ENHANCE_KINDS[f] for f in live])
+    done = dict(zip(live, arrs))
+    return masks, crops, {f: Image.fromarray(done[f]) if f in done else None for f in FIELDS}
 
 
 def run_unet_batch(pil_imgs: Sequence[Image.Image], checkpoint_path: str
