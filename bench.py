@@ -76,7 +76,7 @@ def ncu_traffic_bytes():
     `ncu --set full` capture (profiles/*_ncu_raw.csv, batch 64 @ 512x512); None if absent."""
     import csv
     import glob
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_raw.csv")))
+    files = sorted(f for f in glob.glob(os.path.join(ROOT, "profiles", "*_ncu_raw.csv")) if "enhance" not in f)
     if not files:
         return None, None
     try:
@@ -406,6 +406,26 @@ def main():
                         ts.append((time.perf_counter() - t0) * 1e3)
                 ts.sort()
                 res["with_crop_enhancement"] = {"p50_ms": ts[len(ts) // 2], "p95_ms": ts[int(len(ts) * 0.95)]}
+                # the same sequence with the reference's cv2 calls on the host for the enhancement
+                # (this fixture's crops cover most of the frame: ~90 Mpixel of enhanced output per call)
+                try:
+                    sys.path.insert(0, os.path.join(ROOT, "tools"))
+                    import enhance_bench
+                    ts = []
+                    for i in range(6):
+                        t0 = time.perf_counter()
+                        _, crops = inf.run_unet(rgb, ckpt)
+                        out_px = 0
+                        for f, c in crops.items():
+                            if c is not None:
+                                e = enhance_bench._cv2_chain(np.array(c.convert("RGB")), inf.ENHANCE_KINDS[f])
+                                out_px += e.size
+                        if i >= 1:
+                            ts.append((time.perf_counter() - t0) * 1e3)
+                    ts.sort()
+                    res["with_crop_enhancement_cv2_on_host"] = {"p50_ms": ts[len(ts) // 2], "enhanced_megapixels": out_px / 1e6}
+                except Exception as e:
+                    res["with_crop_enhancement_cv2_on_host"] = {"error": repr(e)}
             if lat is not None:
                 lat["run_unet_1080p"] = res
         except Exception as e:          # informational only

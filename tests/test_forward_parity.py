@@ -158,6 +158,32 @@ def test_cta_pairs_identical(model, cuda_dev):
     assert torch.equal(z0, z1)
 
 
+def test_fill_sms_policy_identical(model, cuda_dev):
+    """Small batches narrow the column block of the deep layers so their tiles cover the SMs (batch-1
+    latency); every output element still accumulates over K in the same order: bit-identical logits, and
+    a batch-1 forward equals the same image inside a batch that keeps the wide blocks."""
+    from tw_invoice_unet_ocr_llm_b200.synthetic import synthetic_invoices
+    eng = model.engine(cuda_dev)
+    keep = eng.get_option("fill_sms")
+    assert keep == 1
+    try:
+        for n, h, w in [(1, 512, 512), (2, 256, 384), (1, 64, 96)]:
+            x = synthetic_invoices(n, h, w, seed=52).to(cuda_dev)
+            eng.set_option("fill_sms", 0)
+            z0, m0 = eng.run(x, thresholds=[0.25, 0.40, 0.30])
+            eng.set_option("fill_sms", 1)
+            z1, m1 = eng.run(x, thresholds=[0.25, 0.40, 0.30])
+            torch.cuda.synchronize()
+            assert torch.equal(z0, z1) and torch.equal(m0, m1), (n, h, w)
+    finally:
+        eng.set_option("fill_sms", keep)
+    big = synthetic_invoices(24, 512, 512, seed=53).to(cuda_dev)
+    zb, _ = eng.run(big)
+    z1, _ = eng.run(big[5:6].contiguous())
+    torch.cuda.synchronize()
+    assert torch.equal(zb[5:6], z1)
+
+
 def test_stem_variants_agree(model, cuda_dev):
     """The three first-conv implementations (CUDA cores fp32, tensor cores + im2col, tensor cores
     implicit GEMM; the last two with the bf16 hi/lo split) agree to the accuracy of one bf16 rounding

@@ -349,6 +349,7 @@ struct ConvDesc {
     int epi2 = 1;               // two epilogue groups: 0 never, 1 weight-stationary launches, 2 always
     int min_na = 3;             // weight-stationary launches: activation stages wanted before staging slots
     int pair = 0;               // CTA pairs (cta_group::2) where an instantiation exists
+    int fill_sms = 0;           // small batches: narrow the column block until the tiles cover the SMs
     const void* stem_x = nullptr;   // A_STEM: network input, its format and channel count
     int stem_fmt = 0, stem_cin = 0;
     int* dbg = nullptr;
@@ -421,6 +422,18 @@ int build_conv_step(const ConvDesc& d, int num_sms, Step* st) {
     if (d.epi == ub::EPI_HEAD) bn = 64;
     if (bn > cols) bn = cols;
     while (cols % bn) bn >>= 1;
+    if (d.fill_sms && !stem && d.taps == 9 && d.epi != ub::EPI_HEAD) {
+        // Batch-1 latency (BASELINE configs[4]): the deep layers have few pixel tiles (32x32 pixels = 8), so
+        // 256-wide column blocks leave most SMs idle; a narrower block runs each CTA at a lower tensor-pipe
+        // rate (more A re-reads) but on up to 4x as many SMs.  Same K order per output -> same bits.
+        // Measured at batch 1 (tools/ab.py fill_sms=0,1): bottleneck.net.3 53 -> 29 us, whole forward
+        // 0.483 -> 0.421 ms; the up-convs (epilogue-bound scatter) got slower and keep their block.
+        const long long m_tiles = 1LL * ((d.wd + 7) / 8) * ((d.h + 15) / 16) * d.n;
+        const bool paired = d.pair != 0 && (d.taps == 1 || d.amode == ub::A_HALO);
+        const long long m_units = paired ? (m_tiles + 1) / 2 : m_tiles;
+        const long long slots = paired ? num_sms / 2 : num_sms;
+        while (bn > 64 && m_units * (cols / bn) < slots) bn >>= 1;
+    }
     if (!(bn == 64 || bn == 128 || bn == 256)) return fail(UNETB200_EINVAL, "conv: bad column block");
     if (d.epi == ub::EPI_HEAD && d.cout != 64)
         return fail(UNETB200_EINVAL, "fused head needs cout == 64");
@@ -642,6 +655,7 @@ struct unetb200_handle_s {
     int min_na = 3;             // weight-stationary launches: activation stages wanted before staging slots
     int pair = 2;               // CTA pairs (cta_group::2): 0 = never, 1 = wherever instantiated, 2 = where measured faster
     int pdl = 1;                // programmatic dependent launch between the layers of one forward
+    int fill_sms = 1;           // narrow the column block of launches whose tiles do not cover the SMs (small batches)
     int profile = 0;
     int* dbg = nullptr;         // pinned, device-visible watchdog record
     std::map<PlanKey, Plan> plans;
@@ -697,7 +711,7 @@ int build_plan(unetb200_handle_t h, const void* x, int x_fmt, int n, int H, int 
         d.n = n; d.h = H >> lvl; d.wd = W >> lvl; d.cout = h->layers[li].cout;
         d.relu = 1; d.taps = 9; d.epi = pool ? ub::EPI_STORE_POOL : ub::EPI_STORE;
         d.out = out; d.pool = pool;
-        d.bn = h->bn_max; d.amode = h->amode; d.wstat = h->wstat; d.pf_items = h->pf_items; d.epi2 = h->epi2; d.min_na = h->min_na; d.dbg = h->dbg;
+        d.bn = h->bn_max; d.amode = h->amode; d.wstat = h->wstat; d.pf_items = h->pf_items; d.epi2 = h->epi2; d.min_na = h->min_na; d.dbg = h->dbg; d.fill_sms = h->fill_sms;
         // measured on B200 (profiles/): CTA pairs win or tie on every 3x3 conv, lose slightly on the up-convs
         d.pair = h->pair >= 1;
         Step st;
@@ -712,7 +726,7 @@ int build_plan(unetb200_handle_t h, const void* x, int x_fmt, int n, int H, int 
         d.w = Wp(li); d.bias = Bp(li);
         d.n = n; d.h = H >> lvl; d.wd = W >> lvl; d.cout = h->layers[li].cout;
         d.relu = 0; d.taps = 1; d.epi = ub::EPI_UPSAMPLE; d.out = out;
-        d.bn = h->bn_max; d.amode = ub::A_TAP; d.wstat = h->wstat; d.pf_items = h->pf_items; d.epi2 = h->epi2; d.min_na = h->min_na; d.pair = h->pair == 1; d.dbg = h->dbg;
+        d.bn = h->bn_max; d.amode = ub::A_TAP; d.wstat = h->wstat; d.pf_items = h->pf_items; d.epi2 = h->epi2; d.min_na = h->min_na; d.pair = h->pair == 1; d.dbg = h->dbg; d.fill_sms = h->fill_sms;
         Step st;
         if ((rc = build_conv_step(d, h->num_sms, &st))) return rc;
         st.layer = li;
@@ -942,6 +956,8 @@ int unetb200_set_option(unetb200_handle_t h, const char* key, int value) {
     } else if (k == "pf_items") {
         if (value < 0 || value > 64) return fail(UNETB200_EINVAL, "pf_items must be in 0..64");
         h->pf_items = value;
+    } else if (k == "fill_sms") {
+        h->fill_sms = value ? 1 : 0;
     } else if (k == "profile") {
         h->profile = value ? 1 : 0;
     } else {
@@ -963,6 +979,7 @@ int unetb200_get_option(unetb200_handle_t h, const char* key, int* value) {
     else if (k == "min_na") *value = h->min_na;
     else if (k == "pair") *value = h->pair;
     else if (k == "pdl") *value = h->pdl;
+    else if (k == "fill_sms") *value = h->fill_sms;
     else if (k == "profile") *value = h->profile;
     else if (k == "num_sms") *value = h->num_sms;
     else return fail(UNETB200_EINVAL, "unknown option " + k);
