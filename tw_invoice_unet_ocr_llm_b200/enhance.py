@@ -14,7 +14,6 @@ download, bit-identical to OpenCV's own code path.  ``enhance_batch`` is the bat
 from __future__ import annotations
 
 import ctypes as C
-import threading
 from typing import List, Optional, Sequence
 
 import numpy as np
@@ -31,17 +30,11 @@ KINDS = {
     "date": (BLUR | OTSU, 3.0),
 }
 
-_tls = threading.local()
-
-
-def _pinned(name: str, nbytes: int) -> torch.Tensor:
-    """Per-thread pinned staging buffer, grown geometrically."""
-    buf = getattr(_tls, name, None)
-    if buf is None or buf.numel() < nbytes:
-        buf = torch.empty(max(nbytes, 1 << 16, 2 * (buf.numel() if buf is not None else 0)),
-                          dtype=torch.uint8).pin_memory()
-        setattr(_tls, name, buf)
-    return buf
+def _pinned(nbytes: int) -> torch.Tensor:
+    """Pinned host buffer from torch's caching host allocator: a block is recycled only after every
+    tensor / numpy view of it is gone and the copies queued on it have completed, so results can be
+    handed out as views (no extra host copy) and staging buffers need no bookkeeping here."""
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, pin_memory=True)
 
 
 def _as_rgb_array(crop) -> np.ndarray:
@@ -84,12 +77,12 @@ def _execute(table, n: int, table_dev_ptr: int, src_ptr: int, out_bytes: int, ws
     d_ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     nat.check(nat.lib().unetb200_enhance_run(table, table_dev_ptr, n, src_ptr, d_out.data_ptr(), d_ws.data_ptr(),
                                              stream.cuda_stream))
-    down = _pinned("down", out_bytes)
+    down = _pinned(out_bytes)
     down[:out_bytes].copy_(d_out, non_blocking=True)
     stream.synchronize()
     del keep                                   # inputs stay referenced until the stream has drained
-    res = down.numpy()
-    return [res[t.out_off: t.out_off + 16 * t.h * t.w].reshape(4 * t.h, 4 * t.w).copy() for t in table]
+    res = down.numpy()                         # the views below keep the pinned block alive
+    return [res[t.out_off: t.out_off + 16 * t.h * t.w].reshape(4 * t.h, 4 * t.w) for t in table]
 
 
 def enhance_batch(crops: Sequence, kinds: Sequence, device=None) -> List[Optional[np.ndarray]]:
@@ -110,7 +103,7 @@ def enhance_batch(crops: Sequence, kinds: Sequence, device=None) -> List[Optiona
     arrays = [_as_rgb_array(crops[i]) for i in live]
     table, src_bytes, out_bytes, ws_bytes = plan([a.shape[:2] for a in arrays], [kinds[i] for i in live])
     tab_bytes = (C.sizeof(table) + 15) & ~15
-    stage = _pinned("up", tab_bytes + src_bytes)
+    stage = _pinned(tab_bytes + src_bytes)
     host = stage.numpy()
     host[:C.sizeof(table)] = np.frombuffer(table, dtype=np.uint8)
     for a, t in zip(arrays, table):
