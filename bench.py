@@ -374,6 +374,27 @@ def main():
         ts.sort()
         lat = {"p50_ms": ts[len(ts) // 2], "p95_ms": ts[int(len(ts) * 0.95)], "calls": len(ts),
                "what": "engine.run on one resident 3x512x512 frame, host-synchronised per call"}
+        # the same forward replayed as a CUDA graph
+        try:
+            g1 = torch.cuda.CUDAGraph()
+            cap = torch.cuda.Stream(dev)
+            with torch.cuda.stream(cap):
+                eng.run(x1, want_logits=True, thresholds=thr, logits_out=l1, mask_out=m1)
+                torch.cuda.synchronize(dev)
+                with torch.cuda.graph(g1, stream=cap):
+                    eng.run(x1, want_logits=True, thresholds=thr, logits_out=l1, mask_out=m1)
+            ts = []
+            for i in range(220):
+                t0 = time.perf_counter()
+                g1.replay()
+                torch.cuda.synchronize(dev)
+                if i >= 20:
+                    ts.append((time.perf_counter() - t0) * 1e3)
+            ts.sort()
+            lat["graph_replay"] = {"p50_ms": ts[len(ts) // 2], "p95_ms": ts[int(len(ts) * 0.95)]}
+            del g1
+        except Exception as e:          # informational only
+            lat["graph_replay"] = {"error": repr(e)}
 
     # ---------------- run_unet end to end (BASELINE.json configs[4]b): 1920x1080 RGB frame -> masks + crops
     # through the reference-facing entry point with the model cached; GPU resize vs host PIL resize

@@ -14,7 +14,11 @@ from tw_invoice_unet_ocr_llm_b200.synthetic import synthetic_crops_u8
 HERE = os.path.dirname(os.path.abspath(__file__))
 GOLD = np.load(os.path.join(HERE, "golden", "golden_enhance.npz"))
 
-cv2 = pytest.importorskip("cv2")
+
+
+def _cv2():
+    """OpenCV is only needed by the live comparisons; the golden-vector and plan tests run without it."""
+    return pytest.importorskip("cv2")
 
 
 def _images(rng, n, lo=3, hi=160):
@@ -48,6 +52,7 @@ def test_golden_inputs_are_the_seeded_crops():
 
 
 def test_gray_sharpen_blur_clahe_otsu_against_live_opencv():
+    cv2 = _cv2()
     rng = np.random.default_rng(5)
     rgb = rng.integers(0, 256, (67, 131, 3), dtype=np.uint8)
     assert np.array_equal(oe.rgb_to_gray(rgb), cv2.cvtColor(rgb, cv2.COLOR_RGB2GRAY))
@@ -66,6 +71,7 @@ def test_gray_sharpen_blur_clahe_otsu_against_live_opencv():
 
 def test_clahe_tiny_images():
     """height/width below the 8x8 grid: the reflect-101 extension wraps more than once."""
+    cv2 = _cv2()
     rng = np.random.default_rng(6)
     for h, w in [(4, 4), (4, 36), (12, 4), (8, 8), (4, 8)]:
         g = rng.integers(0, 256, (h, w), dtype=np.uint8)
@@ -87,6 +93,7 @@ np.savez(sys.argv[1], **out)
 
 def test_resize_against_opencv_native_path(tmp_path):
     """cv2.resize with Intel IPP disabled (OpenCV's own HResizeCubic / VResizeCubicVec path)."""
+    _cv2()
     path = str(tmp_path / "r.npz")
     env = dict(os.environ, OPENCV_IPP="disabled")
     subprocess.run([sys.executable, "-c", _CHILD, path, "9", "40"], env=env, check=True, stderr=subprocess.DEVNULL)
@@ -97,6 +104,7 @@ def test_resize_against_opencv_native_path(tmp_path):
 
 def test_resize_against_installed_opencv_is_within_one():
     """Whatever cv2.resize the installed wheel uses (IPP here): at most +-1 on a few ppm of pixels."""
+    cv2 = _cv2()
     rng = np.random.default_rng(10)
     bad = tot = 0
     for g in _images(rng, 12, lo=2, hi=100):
