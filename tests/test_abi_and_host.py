@@ -169,3 +169,23 @@ def test_module_copies_and_pickles_without_the_engine(fixture_state):
     buf.seek(0)
     m3 = torch.load(buf, weights_only=False)
     assert m3._engine is None and torch.equal(m3.down1.net[0].weight, m.down1.net[0].weight)
+
+
+def test_enhance_surface_matches_reference_and_has_no_cpu_path():
+    """enhance_for_ocrspace / enhance_for_date_ocr keep the reference's signatures (app_camera.py:572, 685);
+    None passes through without touching the GPU; without a CUDA device the batched entry raises."""
+    import inspect
+    import numpy as np
+    from tw_invoice_unet_ocr_llm_b200 import enhance, inference as inf
+    sig = inspect.signature(enhance.enhance_for_ocrspace)
+    assert list(sig.parameters) == ["pil_crop", "mode"] and sig.parameters["mode"].default == "text"
+    assert list(inspect.signature(enhance.enhance_for_date_ocr).parameters) == ["pil_crop"]
+    assert enhance.enhance_for_ocrspace(None) is None and enhance.enhance_for_ocrspace(None, mode="amount") is None
+    assert enhance.enhance_for_date_ocr(None) is None
+    assert set(inf.ENHANCE_KINDS) == set(inf.FIELDS) and set(inf.ENHANCE_KINDS.values()) <= set(enhance.KINDS)
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no CPU path"):
+            enhance.enhance_batch([np.zeros((4, 4, 3), np.uint8)], ["text"])
+        with pytest.raises(RuntimeError, match="no CPU path"):
+            from PIL import Image
+            inf.run_unet_enhanced(Image.new("RGB", (32, 32)), "missing.pth")
