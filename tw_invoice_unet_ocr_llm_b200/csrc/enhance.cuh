@@ -1,19 +1,21 @@
 // OCR crop enhancement: what app_camera.py:572-598 (enhance_for_ocrspace) and
 // :685-705 (enhance_for_date_ocr) ask OpenCV to do to every field crop before OCR, as five byte
-// kernels over a ragged batch of crops.  Integer / byte work, HBM- and launch-bound, bit-exact with
-// OpenCV's own code path (oracle/opencv_enhance.py restates it; the float steps below spell out the
+// kernels over a ragged batch of crops.  Integer / byte work (instruction-issue bound in practice: the
+// working set of a batch is L2-resident), bit-exact with OpenCV's own code path (oracle/opencv_enhance.py restates it; the float steps below spell out the
 // operation order with __f*_rn so that nothing is contracted into an FMA):
 //
 //   enh_resize_kernel   RGB -> gray (15-bit fixed point), 4x bicubic upscale (A = -0.75, 11-bit taps,
 //                       integer horizontal pass, float32 vertical pass on full groups of 8 columns,
-//                       integer tail), optional 3x3 sharpen (REFLECT_101, saturated), one 32x32 output
-//                       block per CTA with the source window and the 34x34 upscaled halo in shared memory
-//   enh_lut_kernel      CLAHE_CalcLut_Body: one CTA per (crop, tile): histogram of the (reflect-extended)
-//                       tile, clip + redistribute, prefix sum, LUT
-//   enh_clahe_kernel    CLAHE_Interpolation_Body (bilinear blend of four LUTs in float32), optional 3x3
-//                       Gaussian [1 2 1]^2 / 16, per-crop histogram for Otsu
+//                       integer tail), optional 3x3 sharpen (REFLECT_101, saturated); a persistent grid walks
+//                       the batch-wide list of 32x32 output blocks with the 12x12 source window, the 12x34
+//                       horizontal sums and the 34x34 upscaled halo in shared memory
+//   enh_lut_kernel      CLAHE_CalcLut_Body: one CTA per (crop, tile): per-warp histograms of the
+//                       (reflect-extended) tile, clip + redistribute, prefix sum, LUT
+//   enh_clahe_kernel    CLAHE_Interpolation_Body (bilinear blend of four LUTs in float32; the LUTs a block can
+//                       touch are cached in shared memory), optional 3x3 Gaussian [1 2 1]^2 / 16, per-crop
+//                       histogram for Otsu
 //   enh_otsu_kernel     getThreshVal_Otsu_8u: sequential double-precision scan of 256 bins per crop
-//   enh_binarize_kernel v > thr ? 255 : 0, in place
+//   enh_binarize_kernel v > thr ? 255 : 0, in place, as a flat 16-byte pass over the packed output buffer
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
