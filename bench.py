@@ -178,10 +178,34 @@ def run_reference(args, rank, world):
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_JSON_FD = None
+
+
+def _reserve_stdout():
+    """The contract is ONE JSON line on stdout.  Native libraries print there too (NCCL's version banner
+    with NCCL_DEBUG set, cuDNN / driver notices), so file descriptor 1 is pointed at stderr for the whole
+    run and the JSON line is written to a private duplicate of the original stdout."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
 
 
 def main():
+    _reserve_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -487,7 +511,7 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "latency_b1": lat, "enhance": enh, "clocks": clocks,
             "gpu_launches": launches_per_step * args.steps,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
