@@ -72,6 +72,32 @@ enum : int { A_TAP = 0, A_COL3 = 1, A_HALO = 2, A_STEM = 3, A_STEMP = 4 };
 
 constexpr int kMaxClasses = 8;
 
+// Division by a launch constant as multiply-high + shift (dividends < 2^31): the per-tile index
+// arithmetic of every role (tile -> image / row / column, unit -> column block, ring slots) used ~20 %
+// of the first conv's instructions as 32-bit divides.
+struct FastDiv {
+    uint32_t d, mul, shr;
+};
+inline FastDiv make_fastdiv(uint32_t d) {
+    FastDiv f{d, 0u, 0u};
+    if (d > 1) {
+        uint32_t lg = 0;
+        while ((1ull << lg) < d) ++lg;                        // ceil(log2 d)
+        const uint32_t pw = 31 + lg;
+        f.mul = static_cast<uint32_t>(((1ull << pw) + d - 1) / d);
+        f.shr = pw - 32;
+    }
+    return f;
+}
+__device__ __forceinline__ uint32_t fdiv(uint32_t x, const FastDiv& f) {
+    return f.d == 1 ? x : __umulhi(x, f.mul) >> f.shr;
+}
+__device__ __forceinline__ void fdivmod(uint32_t x, const FastDiv& f, int& q, int& r) {
+    const uint32_t qq = fdiv(x, f);
+    q = static_cast<int>(qq);
+    r = static_cast<int>(x - qq * f.d);
+}
+
 struct ConvParams {
     CUtensorMap tmA0;        // source 0 activations, dims (C, W, H, N)
     CUtensorMap tmA1;        // source 1 activations (skip tensor), or == tmA0
@@ -90,6 +116,7 @@ struct ConvParams {
     int Cout;                // output channels (per tap for convT)
     int tiles_x, tiles_y;    // ceil(W/8), ceil(H/16)
     int n_blocks;            // column blocks per pixel tile
+    FastDiv fd_tpi, fd_tx, fd_nb, fd_na, fd_nout;   // dividers: tiles per image, tiles_x, n_blocks, na, n_out
     int total_tiles;
     int relu;
     int ncls;
@@ -219,8 +246,8 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
     const int first_unit = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
     const int unit_stride = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
     auto decode = [&](int u, int& mt, int& nb) -> bool {
-        nb = u % p.n_blocks;
-        const int g = u / p.n_blocks;
+        int g;
+        fdivmod(static_cast<uint32_t>(u), p.fd_nb, g, nb);
         mt = PAIR ? 2 * g + static_cast<int>(rank) : g;
         const bool valid = mt < m_tiles;
         if (!valid) mt = m_tiles - 1;
@@ -239,9 +266,10 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
         const bool has1 = r + 128 < 180;
         auto fetch = [&](int t, float (&v)[2][CI]) {
             if (t >= p.total_tiles) return;
-            const int n = t / tiles_per_img;
-            const int rr = t - n * tiles_per_img;
-            const int y0 = (rr / p.tiles_x) * 16 - 1, x0 = (rr % p.tiles_x) * 8 - 1;
+            int n, rr, ty_, tx_;
+            fdivmod(static_cast<uint32_t>(t), p.fd_tpi, n, rr);
+            fdivmod(static_cast<uint32_t>(rr), p.fd_tx, ty_, tx_);
+            const int y0 = ty_ * 16 - 1, x0 = tx_ * 8 - 1;
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
                 const int y = y0 + (j ? py1 : py0), x = x0 + (j ? px1 : px0);
@@ -325,9 +353,10 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
             ecode[i] = e < PE ? ((ci << 16) | ((rem / 10) << 8) | (rem % 10)) : -1;
         }
         auto fetch = [&](int t, float (&regs)[NL]) {
-            const int n = t / tiles_per_img;
-            const int rr = t - n * tiles_per_img;
-            const int y0 = (rr / p.tiles_x) * 16 - 1, x0 = (rr % p.tiles_x) * 8 - 1;
+            int n, rr, ty_, tx_;
+            fdivmod(static_cast<uint32_t>(t), p.fd_tpi, n, rr);
+            fdivmod(static_cast<uint32_t>(rr), p.fd_tx, ty_, tx_);
+            const int y0 = ty_ * 16 - 1, x0 = tx_ * 8 - 1;
 #pragma unroll
             for (int i = 0; i < NL; ++i) {
                 float v = 0.f;
@@ -391,8 +420,8 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
             // ring item of this CTA-local tile (2 * it + grp)
             {
                 const uint32_t item = 2u * static_cast<uint32_t>(it) + grp;
-                const uint32_t na = static_cast<uint32_t>(p.na);
-                const uint32_t sa = item % na, pa = (item / na) & 1;
+                const uint32_t qa = fdiv(item, p.fd_na);
+                const uint32_t sa = item - qa * p.fd_na.d, pa = qa & 1;
                 mbar_wait(bar_a_empty + 8 * sa, pa ^ 1, 1, p.dbg);
                 const uint32_t row = sA + sa * Cfg::A_STAGE + r * 128;
 #pragma unroll
@@ -418,10 +447,11 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
                 const int cs = rem / ITEMS, item = rem - cs * ITEMS;
                 int mt, nb_unused;
                 decode(first_unit + tl * unit_stride, mt, nb_unused);
-                n = mt / tiles_per_img;
-                const int r = mt - n * tiles_per_img;
-                by = (r / p.tiles_x) * 16;
-                bx = (r % p.tiles_x) * 8;
+                int r;
+                fdivmod(static_cast<uint32_t>(mt), p.fd_tpi, n, r);
+                fdivmod(static_cast<uint32_t>(r), p.fd_tx, by, bx);
+                by *= 16;
+                bx *= 8;
                 const bool src0 = (cs << 6) < p.C0;
                 tm = src0 ? &p.tmA0 : &p.tmA1;
                 ca = src0 ? (cs << 6) : (cs << 6) - p.C0;
@@ -491,7 +521,7 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
             } else {
                 uint32_t sb = 0, pb = 0;
                 for (int u = first_unit; u < n_units; u += unit_stride) {
-                    const int nb = u % p.n_blocks;
+                    const int nb = u - static_cast<int>(fdiv(static_cast<uint32_t>(u), p.fd_nb)) * p.n_blocks;
                     for (int cs = 0; cs < n_cs; ++cs) {
 #pragma unroll 1
                         for (int i = 0; i < TAPS; i += Cfg::TPB) {
@@ -678,10 +708,11 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
              u += estep * unit_stride, tile_it += estep) {
             int mt, nb;
             const bool valid = decode(u, mt, nb);
-            const int n = mt / tiles_per_img;
-            const int r = mt - n * tiles_per_img;
-            const int y0 = (r / p.tiles_x) * 16;
-            const int x0 = (r % p.tiles_x) * 8;
+            int n, r, y0, x0;
+            fdivmod(static_cast<uint32_t>(mt), p.fd_tpi, n, r);
+            fdivmod(static_cast<uint32_t>(r), p.fd_tx, y0, x0);
+            y0 *= 16;
+            x0 *= 8;
             const uint32_t acc = tile_it % Cfg::NACC, acc_ph = (tile_it / Cfg::NACC) & 1;
             mbar_wait(bar_t_full + 8 * acc, acc_ph, 7, p.dbg);
             tc_fence_after();
@@ -749,7 +780,7 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
                 // Each warp owns a quarter of the tile (4 pixel rows): its own 4 KB slab of the staging
                 // slot, its own TMA stores, its own bulk groups -- no barrier between the four warps.
                 // Each group owns n_out slots; a slab was last read by this warp's store n_out chunks ago.
-                const uint32_t buf = eg * p.n_out + chunk_it % static_cast<uint32_t>(p.n_out);
+                const uint32_t buf = eg * p.n_out + (chunk_it - fdiv(chunk_it, p.fd_nout) * p.fd_nout.d);
                 const uint32_t obuf = sOut + buf * kOutStage;
                 const uint32_t pbuf = sPool + buf * kPoolStage;
                 if (lane == 0) {

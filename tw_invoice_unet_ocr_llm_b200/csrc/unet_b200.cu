@@ -514,6 +514,11 @@ int build_conv_step(const ConvDesc& d, int num_sms, Step* st) {
                         d.epi == ub::EPI_STORE_POOL, d.epi != ub::EPI_HEAD, stem ? 1 : d.wstat,
                         (stem && !stemp) ? 4 * d.stem_cin * 180 * 4 : 0, d.epi2, d.min_na)))
         return rc;
+    p.fd_tpi = ub::make_fastdiv(static_cast<uint32_t>(p.tiles_x * p.tiles_y));
+    p.fd_tx = ub::make_fastdiv(static_cast<uint32_t>(p.tiles_x));
+    p.fd_nb = ub::make_fastdiv(static_cast<uint32_t>(p.n_blocks));
+    p.fd_na = ub::make_fastdiv(static_cast<uint32_t>(p.na > 0 ? p.na : 1));
+    p.fd_nout = ub::make_fastdiv(static_cast<uint32_t>(p.n_out > 0 ? p.n_out : 1));
     if (st->conv.pair) {
         const long long m_tiles = 1LL * p.tiles_x * p.tiles_y * d.n;
         const long long units = (m_tiles + 1) / 2 * p.n_blocks;
