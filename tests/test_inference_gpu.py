@@ -69,6 +69,23 @@ def test_gpu_preprocess_equals_host_preprocess(checkpoint, cuda_dev):
             assert c1[k].size == c2[k].size
 
 
+def test_preprocess_on_gpu_equals_reference_definition(cuda_dev):
+    """inference.preprocess (reference :30-44) with the resize and the /255 on the device: bit-identical to
+    ``np.array(pil.convert("RGB").resize((512, 512))).astype(float32) / 255`` for RGB inputs of any size."""
+    from tw_invoice_unet_ocr_llm_b200 import inference as inf
+    from tw_invoice_unet_ocr_llm_b200.synthetic import synthetic_invoices_u8
+    for h, w in [(300, 420), (1080, 1920), (512, 512), (97, 1031)]:
+        pil = Image.fromarray(synthetic_invoices_u8(1, h, w, seed=3)[0])
+        t = inf.preprocess(pil)
+        assert t.is_cuda and t.shape == (1, 3, 512, 512) and t.dtype == torch.float32 and t.is_contiguous()
+        ref = np.array(pil.convert("RGB").resize((512, 512))).astype(np.float32) / 255.0
+        assert np.array_equal(t[0].cpu().numpy(), ref.transpose(2, 0, 1)), (h, w)
+    gray = Image.fromarray(synthetic_invoices_u8(1, 200, 300, seed=4)[0]).convert("L")   # host route
+    t = inf.preprocess(gray)
+    ref = np.array(gray.convert("RGB").resize((512, 512))).astype(np.float32) / 255.0
+    assert np.array_equal(t[0].cpu().numpy(), ref.transpose(2, 0, 1))
+
+
 def test_near_black_rejection_on_gpu_equals_host(cuda_dev):
     """reference inference.py:118-125: a crop whose mean is below 3 is dropped.  boxes_to_crops with the
     frame on the device (integer sums) must decide exactly like the host's ``np.array(crop).mean() < 3``,
@@ -212,3 +229,22 @@ def test_multi_gpu_segmenter_all_devices(fixture_state, cuda_dev):
     n = torch.cuda.device_count()
     every = MultiGpuSegmenter(fixture_state, devices=[f"cuda:{i}" for i in range(n)], chunk=4).segment(frames)
     assert torch.equal(one, every)
+
+
+def test_launcher_boxes_equal_numpy_extents(fixture_state, cuda_dev):
+    """MultiGpuSegmenter(return_boxes=True): the GPU mask -> box reduction next to every chunk equals the
+    np.where min/max of reference inference.py:85-93 on the returned masks, across chunk boundaries."""
+    from tw_invoice_unet_ocr_llm_b200.launcher import MultiGpuSegmenter
+    from tw_invoice_unet_ocr_llm_b200.synthetic import synthetic_invoices_u8
+    frames = synthetic_invoices_u8(7, 128, 160, seed=84)
+    n = torch.cuda.device_count()
+    seg = MultiGpuSegmenter(fixture_state, devices=[f"cuda:{i}" for i in range(n)], chunk=3)
+    masks, boxes = seg.segment(frames, return_boxes=True)
+    assert torch.equal(masks, seg.segment(frames))
+    assert boxes.shape == (7, 3, 5) and boxes.dtype == torch.int32
+    m, bx = masks.numpy(), boxes.numpy()
+    for i in range(7):
+        for c in range(3):
+            ys, xs = np.where(m[i, c] != 0)
+            want = [160, -1, 128, -1, 0] if ys.size == 0 else [xs.min(), xs.max(), ys.min(), ys.max(), ys.size]
+            assert list(bx[i, c]) == want, (i, c)

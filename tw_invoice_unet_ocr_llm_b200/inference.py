@@ -88,7 +88,22 @@ def _resized_rgb_u8(pil_img: Image.Image) -> np.ndarray:
 
 
 def preprocess(pil_img: Image.Image):
-    """PIL image -> float32 tensor ``[1, 3, 512, 512]`` in [0, 1] on ``DEVICE`` (reference :30-44)."""
+    """PIL image -> float32 tensor ``[1, 3, 512, 512]`` in [0, 1] on ``DEVICE`` (reference :30-44).
+
+    Plain RGB images on a CUDA device take the GPU resize (bit-identical to Pillow's) and the ``/ 255.0``
+    there too (IEEE float32 division, the same values as numpy's); everything else follows the reference's
+    PIL / numpy calls on the host.  Same tensor either way."""
+    if DEVICE == "cuda" and _gpu_resizable(pil_img):
+        from . import prepost
+        w, h = pil_img.size
+        if h <= 0 or w <= 0:
+            raise ValueError(f"Invalid image shape: {(h, w, 3)}")
+        x = prepost.resize_u8(_upload_rgb(pil_img), IMG_SIZE, IMG_SIZE)           # uint8 [1, 512, 512, 3]
+        # a device-tensor divisor keeps this a true IEEE division (torch turns `/ python_scalar` into a
+        # multiplication by the reciprocal on CUDA, which is 1 ulp off numpy's `/ 255.0` for some k)
+        out = (x.permute(0, 3, 1, 2).to(torch.float32) / torch.full((), 255.0, device=x.device)).contiguous()
+        torch.cuda.current_stream().synchronize()            # the pinned staging buffer is reusable again
+        return out
     arr = _resized_rgb_u8(pil_img).astype(np.float32) / 255.0
     arr = arr.transpose(2, 0, 1)
     return torch.from_numpy(np.ascontiguousarray(arr)).unsqueeze(0).to(DEVICE)

@@ -65,12 +65,14 @@ class GpuWorker:
             self._bufs[key] = [(mk(shape_in), mk(shape_out)) for _ in range(2)]
         return self._bufs[key]
 
-    def segment_async(self, frames: torch.Tensor, out: torch.Tensor) -> None:
+    def segment_async(self, frames: torch.Tensor, out: torch.Tensor, boxes_out: Optional[torch.Tensor] = None
+                      ) -> None:
         """Enqueue ``frames`` uint8 [B,H,W,3] (pinned host) -> ``out`` uint8 [B,3,H,W] (pinned host)
         and return without waiting.  Per chunk: H2D on the upload stream, forward on the compute
         stream, D2H on the download stream; the upload of the next chunk (or of the next call) and
         the download of the previous one overlap the forward of the current one.  ``out`` is valid
-        after :meth:`synchronize`."""
+        after :meth:`synchronize`.  ``boxes_out`` (optional, int32 [B,3,5] pinned host) also receives the
+        mask extents {xmin, xmax, ymin, ymax, count} of reference inference.py:85-93, reduced on the GPU."""
         b = frames.shape[0]
         bufs = self._staging(frames.shape, out.shape)
         cs, ks, ds = self.copy_stream, self.compute_stream, self.down_stream
@@ -90,10 +92,17 @@ class GpuWorker:
                     ks.wait_event(ready)
                     self.engine.run(xin[:n], want_logits=False, thresholds=self.thresholds,
                                     mask_out=mout[:n])
+                    box = None
+                    if boxes_out is not None:
+                        from . import prepost
+                        box = prepost.mask_bbox(mout[:n])
+                        box.record_stream(ds)
                     done.record(ks)
                 with torch.cuda.stream(ds):
                     ds.wait_event(done)
                     out[lo:hi].copy_(mout[:n], non_blocking=True)
+                    if box is not None:
+                        boxes_out[lo:hi].copy_(box, non_blocking=True)
                     drained.record(ds)
                     self._drained[slot] = drained
 
@@ -110,9 +119,12 @@ class GpuWorker:
         cur.wait_stream(self.compute_stream)
         cur.wait_stream(self.down_stream)
 
-    def segment(self, frames: torch.Tensor, out: torch.Tensor) -> None:
-        """Synchronous form: enqueue, then wait until ``out`` is complete."""
-        self.segment_async(frames, out)
+    def segment(self, frames: torch.Tensor, out: torch.Tensor, boxes_out: Optional[torch.Tensor] = None) -> None:
+        """Synchronous form: enqueue, then wait until ``out`` (and ``boxes_out``) are complete."""
+        if boxes_out is None:
+            self.segment_async(frames, out)
+        else:
+            self.segment_async(frames, out, boxes_out)
         self.synchronize()
 
 
@@ -129,8 +141,10 @@ class MultiGpuSegmenter:
         factory = worker_factory or (lambda dev: GpuWorker(state, dev, thresholds, chunk))
         self.workers = [factory(d) for d in devices]
 
-    def segment(self, frames, out=None):
-        """uint8 frames [B,H,W,3] -> uint8 masks [B,3,H,W] (host).  Order is preserved."""
+    def segment(self, frames, out=None, return_boxes: bool = False):
+        """uint8 frames [B,H,W,3] -> uint8 masks [B,3,H,W] (host).  Order is preserved.  With
+        ``return_boxes`` the result is ``(masks, boxes)``, boxes int32 [B,3,5] = xmin, xmax, ymin, ymax,
+        count per field (empty mask: W, -1, H, -1, 0), reduced on each GPU next to its masks."""
         if isinstance(frames, np.ndarray):
             frames = torch.from_numpy(np.ascontiguousarray(frames))
         if frames.dtype != torch.uint8 or frames.dim() != 4 or frames.shape[-1] != 3:
@@ -141,13 +155,17 @@ class MultiGpuSegmenter:
             frames = frames.pin_memory()
         if out is None:
             out = torch.empty((b, 3, h, w), dtype=torch.uint8, pin_memory=pin)
+        boxes = torch.empty((b, 3, 5), dtype=torch.int32, pin_memory=pin) if return_boxes else None
         errors: List[BaseException] = []
 
         def work(rank: int):
             lo, hi = shard_bounds(b, len(self.workers), rank)
             if hi > lo:
                 try:
-                    self.workers[rank].segment(frames[lo:hi], out[lo:hi])
+                    if boxes is None:
+                        self.workers[rank].segment(frames[lo:hi], out[lo:hi])
+                    else:
+                        self.workers[rank].segment(frames[lo:hi], out[lo:hi], boxes[lo:hi])
                 except BaseException as e:      # surfaced to the caller below
                     errors.append(e)
 
@@ -158,7 +176,7 @@ class MultiGpuSegmenter:
             t.join()
         if errors:
             raise errors[0]
-        return out
+        return out if boxes is None else (out, boxes)
 
 
 def gather_masks(local: torch.Tensor, total: int, group=None) -> Optional[torch.Tensor]:
