@@ -214,6 +214,8 @@ def main():
     ap.add_argument("--batch", type=int, default=64, help="images per GPU per step")
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the informational sections (batch-1 latency, run_unet, crop enhancement): profiling runs")
     ap.add_argument("--layers-out", default=None, help="write the per-layer table (JSON) here")
     ap.add_argument("--graph", type=int, default=0, help="1: replay the step as a CUDA graph")
     ap.add_argument("--e2e-chunk", type=int, default=64,
@@ -384,7 +386,7 @@ def main():
     # ---------------- batch-1 latency (BASELINE.json configs[4]): one resident 3x512x512 frame ->
     # logits + masks, synchronised per call; p50/p95 over 200 calls (rank 0, informational)
     lat = None
-    if rank == 0:
+    if rank == 0 and not args.no_extras:
         x1 = x_dev[:1].contiguous()
         l1 = torch.empty((1, 3, S, S), dtype=torch.float32, device=dev)
         m1 = torch.empty((1, 3, S, S), dtype=torch.uint8, device=dev)
@@ -422,7 +424,7 @@ def main():
 
     # ---------------- run_unet end to end (BASELINE.json configs[4]b): 1920x1080 RGB frame -> masks + crops
     # through the reference-facing entry point with the model cached; GPU resize vs host PIL resize
-    if rank == 0:
+    if rank == 0 and not args.no_extras:
         try:
             import tempfile
             from PIL import Image
@@ -480,7 +482,7 @@ def main():
     # ---------------- OCR crop enhancement (rank 0, informational): 192 ragged crops
     # through enhance_batch vs the reference's cv2 calls on the host cores
     enh = None
-    if rank == 0 and world == 1:
+    if rank == 0 and world == 1 and not args.no_extras:
         try:
             sys.path.insert(0, os.path.join(ROOT, "tools"))
             import enhance_bench

@@ -6,7 +6,7 @@
 tag=${1:-r01}
 out=gpurun_out
 mkdir -p $out /tmp/ncu
-CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
+CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extras"
 # 22 launches per forward; 3 warm-up forwards + 1 profile-priming -> skip 66, list two forwards
 $CMD > $out/plain_$tag.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -s 66 -c 44 --csv \

@@ -1,7 +1,7 @@
 #!/bin/bash
 # source-level ncu capture of selected launches of the 4th forward: args = launch indices (0..21)
 mkdir -p gpurun_out /tmp/ncu
-CMD="python bench.py --steps 1 --warmup 3 --no-cpu-baseline"
+CMD="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-extras"
 $CMD > gpurun_out/plain_src.log 2>&1 || { echo "plain run failed"; tail -n 5 gpurun_out/plain_src.log; exit 1; }
 for j in "$@"; do
   s=$((66 + j))
