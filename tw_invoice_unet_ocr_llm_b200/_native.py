@@ -11,7 +11,8 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libunetb200.so")
+# UNETB200_LIB: load an alternative build of the same sources (A/B of compile-time switches); default in-tree
+LIB_PATH = os.environ.get("UNETB200_LIB") or os.path.join(_HERE, "libunetb200.so")
 
 OK, EINVAL, ECUDA, EARCH, ENOMEM = 0, 1, 2, 3, 4
 STEM, CONV3X3, CONVT2X2, HEAD = 0, 1, 2, 3

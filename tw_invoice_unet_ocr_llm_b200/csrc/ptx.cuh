@@ -52,8 +52,24 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// UB_WAIT_HINT_NS > 0: pass a suspend-time hint, so a waiting warp sleeps in hardware until the phase
+// completes (or the hint expires) instead of re-issuing try_wait from the spin loop.
+#ifndef UB_WAIT_HINT_NS
+#define UB_WAIT_HINT_NS 0
+#endif
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
+#if UB_WAIT_HINT_NS > 0
+    asm volatile(
+        "{\n"
+        ".reg .pred P;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n"
+        "selp.u32 %0, 1, 0, P;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(static_cast<uint32_t>(UB_WAIT_HINT_NS))
+        : "memory");
+#else
     asm volatile(
         "{\n"
         ".reg .pred P;\n"
@@ -63,6 +79,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "=r"(ok)
         : "r"(bar), "r"(parity)
         : "memory");
+#endif
     return ok != 0;
 }
 // Bounded wait.  `tag` identifies the wait site in the trap record.
