@@ -426,13 +426,24 @@ int build_conv_step(const ConvDesc& d, int num_sms, Step* st) {
         // Batch-1 latency (BASELINE configs[4]): the deep layers have few pixel tiles (32x32 pixels = 8), so
         // 256-wide column blocks leave most SMs idle; a narrower block runs each CTA at a lower tensor-pipe
         // rate (more A re-reads) but on up to 4x as many SMs.  Same K order per output -> same bits.
-        // Measured at batch 1 (tools/ab.py fill_sms=0,1): bottleneck.net.3 53 -> 29 us, whole forward
-        // 0.483 -> 0.421 ms; the up-convs (epilogue-bound scatter) got slower and keep their block.
+        // Measured (tools/ab.py fill_sms=0,1): batch 1 0.472 -> 0.393 ms (bottleneck.net.3 53 -> 29 us),
+        // batch 2 / 3 / 8 -4 / -5 / -2.5 %, batch >= 16 unchanged; the up-convs (epilogue-bound scatter)
+        // got slower with narrow blocks and keep theirs.
         const long long m_tiles = 1LL * ((d.wd + 7) / 8) * ((d.h + 15) / 16) * d.n;
         const bool paired = d.pair != 0 && (d.taps == 1 || d.amode == ub::A_HALO);
         const long long m_units = paired ? (m_tiles + 1) / 2 : m_tiles;
         const long long slots = paired ? num_sms / 2 : num_sms;
-        while (bn > 64 && m_units * (cols / bn) < slots) bn >>= 1;
+        // cost of a launch ~ waves x (columns per unit / tensor-pipe efficiency of that block width);
+        // efficiencies as measured at batch 64 (profiles/): 0.97 / 0.95 / 0.70 for 256 / 128 / 64 columns
+        auto cost = [&](int b) {
+            const long long units = m_units * (cols / b);
+            const long long waves = (units + slots - 1) / slots;
+            return static_cast<double>(waves) * b / (b == 256 ? 0.97 : (b == 128 ? 0.95 : 0.70));
+        };
+        int best = bn;
+        for (int b = bn >> 1; b >= 64; b >>= 1)
+            if (cols % b == 0 && cost(b) < 0.97 * cost(best)) best = b;     // near ties keep the wider block
+        bn = best;
     }
     if (!(bn == 64 || bn == 128 || bn == 256)) return fail(UNETB200_EINVAL, "conv: bad column block");
     if (d.epi == ub::EPI_HEAD && d.cout != 64)
