@@ -422,7 +422,7 @@ int build_conv_step(const ConvDesc& d, int num_sms, Step* st) {
     if (d.epi == ub::EPI_HEAD) bn = 64;
     if (bn > cols) bn = cols;
     while (cols % bn) bn >>= 1;
-    if (d.fill_sms && !stem && d.taps == 9 && d.epi != ub::EPI_HEAD) {
+    if (d.fill_sms && !stem && (d.taps == 9 || d.fill_sms > 1) && d.epi != ub::EPI_HEAD) {
         // Batch-1 latency (BASELINE configs[4]): the deep layers have few pixel tiles (32x32 pixels = 8), so
         // 256-wide column blocks leave most SMs idle; a narrower block runs each CTA at a lower tensor-pipe
         // rate (more A re-reads) but on up to 4x as many SMs.  Same K order per output -> same bits.
@@ -973,7 +973,8 @@ int unetb200_set_option(unetb200_handle_t h, const char* key, int value) {
         if (value < 0 || value > 64) return fail(UNETB200_EINVAL, "pf_items must be in 0..64");
         h->pf_items = value;
     } else if (k == "fill_sms") {
-        h->fill_sms = value ? 1 : 0;
+        if (value < 0 || value > 2) return fail(UNETB200_EINVAL, "fill_sms must be 0, 1 or 2");
+        h->fill_sms = value;                 // 2 = also the up-convs (measured: no gain at batch 1-4)
     } else if (k == "profile") {
         h->profile = value ? 1 : 0;
     } else {
