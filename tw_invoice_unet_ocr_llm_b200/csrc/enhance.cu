@@ -117,9 +117,18 @@ int unetb200_enhance_run(const unetb200_enh_crop* table_host, const void* table_
     const auto* tab = static_cast<const unetb200_enh_crop*>(table_dev);
     uint8_t* ws = static_cast<uint8_t*>(workspace_dev);
     const unsigned nb = static_cast<unsigned>(blocks);
-    // persistent grid for the upscale: 148 SMs x 8 resident CTAs walk the block list
-    const unsigned grid = nb < 148u * 8u ? nb : 148u * 8u;
-    ub::enh_resize_kernel<<<grid, ub::kEnhThreads, 0, s>>>(tab, n, static_cast<int>(nb), src_dev, ws, taps);
+    // persistent grid for the upscale: one wave of resident CTAs (SMs x occupancy), each walking a
+    // contiguous run of the block list
+    int dev = 0, sms = 148, occ = 8;
+    if (cudaGetDevice(&dev) == cudaSuccess) {
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ub::enh_resize_kernel, ub::kEnhResThreads, 0) !=
+                cudaSuccess || occ < 1)
+            occ = 8;
+    }
+    const unsigned wave = static_cast<unsigned>(sms) * static_cast<unsigned>(occ);
+    const unsigned grid = nb < wave ? nb : wave;
+    ub::enh_resize_kernel<<<grid, ub::kEnhResThreads, 0, s>>>(tab, n, static_cast<int>(nb), src_dev, ws, taps);
     ub::enh_lut_kernel<<<static_cast<unsigned>(n) * ub::kEnhTiles * ub::kEnhTiles, ub::kEnhThreads, 0, s>>>(tab, ws);
     ub::enh_clahe_kernel<<<nb, ub::kEnhThreads, 0, s>>>(tab, n, ws, out_dev);
     if (any_otsu) {

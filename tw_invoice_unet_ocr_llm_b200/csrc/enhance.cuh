@@ -6,9 +6,9 @@
 //
 //   enh_resize_kernel   RGB -> gray (15-bit fixed point), 4x bicubic upscale (A = -0.75, 11-bit taps,
 //                       integer horizontal pass, float32 vertical pass on full groups of 8 columns,
-//                       integer tail), optional 3x3 sharpen (REFLECT_101, saturated); a persistent grid walks
-//                       the batch-wide list of 32x32 output blocks with the 12x12 source window, the 12x34
-//                       horizontal sums and the 34x34 upscaled halo in shared memory
+//                       integer tail), optional 3x3 sharpen (REFLECT_101, saturated); one wave of CTAs, each
+//                       walking a contiguous run of the batch-wide list of 32x32 output blocks, one thread per
+//                       4x4 output cell (shared 4x4 source window), halo and 3x3 from shared memory
 //   enh_lut_kernel      CLAHE_CalcLut_Body: one CTA per (crop, tile): per-warp histograms of the
 //                       (reflect-extended) tile, clip + redistribute, prefix sum, LUT
 //   enh_clahe_kernel    CLAHE_Interpolation_Body (bilinear blend of four LUTs in float32; the LUTs a block can
@@ -80,99 +80,147 @@ __device__ __forceinline__ void enh_hist_add(int* hist, int bin, bool valid) {
 }
 
 // ------------------------------------------------------------------ gray + 4x bicubic (+ sharpen)
-// 32x32 output blocks, a persistent grid walking the batch-wide block list: 12x12 gray source window ->
-// horizontal pass (12 rows x 34 columns of int sums, shared by the four vertical phases) -> vertical
-// pass (34x34 with the sharpen halo) -> 3x3.
+// 32x32 output blocks, a persistent grid walking the batch-wide block list.  For a 4x upscale the sixteen
+// outputs (4s+2 .. 4s+5)^2 read the same 4x4 source window (taps s-1 .. s+2 on both axes) and differ only
+// in the phase of their taps, so one thread produces such a 4x4 cell: 16 gray loads, 16 horizontal sums
+// (source row x column phase), 16 outputs.  A block with its sharpen halo is covered by 9x9 cells laid
+// out from (y0-2, x0-2); rows / columns outside the image are then overwritten with their REFLECT_101
+// partners, and the 3x3 runs from shared memory.
+constexpr int kEnhResThreads = 128;
+constexpr int kEnhCells = kEnhBlock / 4 + 1;                 // 9 cells per axis
 struct EnhResizeSmem {
-    uint8_t gs[kEnhWin][kEnhWin + 4];
-    int hs[kEnhWin][kEnhBlock + 3];
-    alignas(4) uint8_t rs[kEnhBlock + 2][kEnhBlock + 4];
+    uint8_t gs[kEnhWin][kEnhWin + 4];                        // gray source window (rows / cols y0/4-2 .. +11)
+    alignas(4) uint8_t rs[4 * kEnhCells][4 * kEnhCells + 4]; // upscaled cells, origin (y0-2, x0-2)
     int16_t st[4][4];
     float sb[4][4];
 };
 
-template <int HALO>
-__device__ __forceinline__ void enh_resize_block(EnhResizeSmem& sm, const unetb200_enh_crop* __restrict__ c, int bx,
-                                                 int by, const uint8_t* __restrict__ src, uint8_t* __restrict__ ws) {
-    constexpr int side = kEnhBlock + 2 * HALO;
-    const int h = c->h, w = c->w, H = 4 * h, W = 4 * w, stride = c->src_stride;
-    const int x0 = bx * kEnhBlock, y0 = by * kEnhBlock;
+// the (up to two) gray source-window pixels thread t of a CTA loads for block (bx, by) of crop c
+constexpr int kEnhWinPerThread = (kEnhWin * kEnhWin + kEnhResThreads - 1) / kEnhResThreads;
+__device__ __forceinline__ void enh_fetch_window(const unetb200_enh_crop* __restrict__ c, int bx, int by,
+                                                 const uint8_t* __restrict__ src, uint8_t (&g)[kEnhWinPerThread]) {
+    const int h = c->h, w = c->w, stride = c->src_stride;
     const uint8_t* in = src + c->src_off;
-    uint8_t* img = ws + c->ws_off;
-
-    // source window, border-clamped like the resize tap indices
-    if (threadIdx.x < kEnhWin * kEnhWin) {
-        const int r = threadIdx.x / kEnhWin, q = threadIdx.x - r * kEnhWin;
-        const int sy = min(max(y0 / 4 - 2 + r, 0), h - 1), sx = min(max(x0 / 4 - 2 + q, 0), w - 1);
-        const uint8_t* p = in + (static_cast<size_t>(sy) * stride + sx) * 3;
-        sm.gs[r][q] = static_cast<uint8_t>((p[0] * 9798 + p[1] * 19235 + p[2] * 3735 + (1 << 14)) >> 15);
-    }
-    __syncthreads();
-
-    const int ylast = min(y0 + kEnhBlock - 1, H - 1) + HALO, xlast = min(x0 + kEnhBlock - 1, W - 1) + HALO;
-    const int nvec = W - (W & 7);
-
-    // HResizeCubic<uchar, int, short>: int sums per (window row, output column)
-    for (int i = threadIdx.x; i < kEnhWin * side; i += kEnhThreads) {
-        const int r = i / side, rx = i - r * side;
-        int gx = x0 + rx - HALO;
-        if (gx > xlast) continue;
-        gx = enh_reflect101(gx, W);
-        const int q0 = ((2 * gx - 3) >> 3) - 1 - (x0 / 4 - 2);
-        const int16_t* tx = sm.st[gx & 3];
-        sm.hs[r][rx] = sm.gs[r][q0] * tx[0] + sm.gs[r][q0 + 1] * tx[1] + sm.gs[r][q0 + 2] * tx[2] +
-                       sm.gs[r][q0 + 3] * tx[3];
-    }
-    __syncthreads();
-
-    for (int i = threadIdx.x; i < side * side; i += kEnhThreads) {
-        const int ry = i / side, rx = i - ry * side;
-        int gy = y0 + ry - HALO, gx = x0 + rx - HALO;
-        if (gy > ylast || gx > xlast) continue;
-        gy = enh_reflect101(gy, H);
-        gx = enh_reflect101(gx, W);
-        const int r0 = ((2 * gy - 3) >> 3) - 1 - (y0 / 4 - 2);
-        const int s0 = sm.hs[r0][rx], s1 = sm.hs[r0 + 1][rx], s2 = sm.hs[r0 + 2][rx], s3 = sm.hs[r0 + 3][rx];
-        int v;
-        if (gx < nvec) {
-            // VResizeCubicVec_32s8u: S0*b0 + (S1*b1 + (S2*b2 + S3*b3)), v_round, saturating packs
-            const float* b = sm.sb[gy & 3];
-            float acc = __fmul_rn(enh_i2f(s3), b[3]);          // |S| <= 255 * 2048 * 1.27 < 2^22
-            acc = __fadd_rn(__fmul_rn(enh_i2f(s2), b[2]), acc);
-            acc = __fadd_rn(__fmul_rn(enh_i2f(s1), b[1]), acc);
-            acc = __fadd_rn(__fmul_rn(enh_i2f(s0), b[0]), acc);
-            v = enh_f2i_rn(acc);
-        } else {
-            // VResizeCubic + FixedPtCast<int, uchar, 22>
-            const int16_t* ty = sm.st[gy & 3];
-            v = (s0 * ty[0] + s1 * ty[1] + s2 * ty[2] + s3 * ty[3] + (1 << 21)) >> 22;
-        }
-        sm.rs[ry][rx] = static_cast<uint8_t>(min(max(v, 0), 255));
-    }
-    __syncthreads();
-
-    // 4 pixels per thread, one 32-bit store (W is a multiple of 4: all four columns are inside)
-    const int ty4 = threadIdx.x >> 3, tx4 = (threadIdx.x & 7) * 4;
-    const int gy = y0 + ty4, gx = x0 + tx4;
-    if (gy >= H || gx >= W) return;
-    uint32_t packed = 0;
-    if (HALO) {
-        // filter2D [[-1,-1,-1],[-1,9,-1],[-1,-1,-1]]: 10*centre - (3x3 sum), saturated
-        int col[6];
 #pragma unroll
-        for (int j = 0; j < 6; ++j) col[j] = sm.rs[ty4][tx4 + j] + sm.rs[ty4 + 1][tx4 + j] + sm.rs[ty4 + 2][tx4 + j];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int v = 10 * sm.rs[ty4 + 1][tx4 + j + 1] - (col[j] + col[j + 1] + col[j + 2]);
-            packed |= static_cast<uint32_t>(min(max(v, 0), 255)) << (8 * j);
+    for (int k = 0; k < kEnhWinPerThread; ++k) {
+        const int i = threadIdx.x + k * kEnhResThreads;
+        g[k] = 0;
+        if (i < kEnhWin * kEnhWin) {
+            // source window rows / cols (block origin / 4) - 2 .. + 9, border-clamped like the resize tap indices
+            const int r = i / kEnhWin, q = i - r * kEnhWin;
+            const int sy = min(max(by * (kEnhBlock / 4) - 2 + r, 0), h - 1), sx = min(max(bx * (kEnhBlock / 4) - 2 + q, 0), w - 1);
+            const uint8_t* p = in + (static_cast<size_t>(sy) * stride + sx) * 3;
+            g[k] = static_cast<uint8_t>((p[0] * 9798 + p[1] * 19235 + p[2] * 3735 + (1 << 14)) >> 15);
         }
-    } else {
-        packed = *reinterpret_cast<const uint32_t*>(&sm.rs[ty4][tx4]);
     }
-    *reinterpret_cast<uint32_t*>(img + static_cast<size_t>(gy) * W + gx) = packed;
 }
 
-__global__ void __launch_bounds__(kEnhThreads)
+__device__ __forceinline__ void enh_resize_block(EnhResizeSmem& sm, const unetb200_enh_crop* __restrict__ c, int bx,
+                                                 int by, uint8_t* __restrict__ ws) {
+    const int H = 4 * c->h, W = 4 * c->w;
+    const int x0 = bx * kEnhBlock, y0 = by * kEnhBlock;
+    const bool sharpen = (c->flags & UNETB200_ENH_SHARPEN) != 0;
+    uint8_t* img = ws + c->ws_off;
+
+    // last output row / column this block needs (with the sharpen halo)
+    const int ylast = min(y0 + kEnhBlock - 1, H - 1) + (sharpen ? 1 : 0);
+    const int xlast = min(x0 + kEnhBlock - 1, W - 1) + (sharpen ? 1 : 0);
+    const int nvec = W - (W & 7);
+    if (threadIdx.x < kEnhCells * kEnhCells) {
+        const int cy = threadIdx.x / kEnhCells, cx = threadIdx.x - cy * kEnhCells;
+        // cell (cy, cx): outputs (y0 - 2 + 4cy + i, x0 - 2 + 4cx + j), source window rows cy .. cy+3 of gs
+        const int gy0 = y0 - 2 + 4 * cy, gx0 = x0 - 2 + 4 * cx;
+        if (gy0 <= ylast && gx0 <= xlast && gy0 + 3 >= 0 && gx0 + 3 >= 0) {
+            // horizontal pass (HResizeCubic<uchar, int, short>): hor[r][j], column phase (gx0 + j) & 3 = (j + 2) & 3
+            int hor[4][4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int g0 = sm.gs[cy + r][cx], g1 = sm.gs[cy + r][cx + 1], g2 = sm.gs[cy + r][cx + 2],
+                          g3 = sm.gs[cy + r][cx + 3];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int16_t* tx = sm.st[(j + 2) & 3];
+                    hor[r][j] = g0 * tx[0] + g1 * tx[1] + g2 * tx[2] + g3 * tx[3];
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int ph = (i + 2) & 3;                  // row phase (gy0 + i) & 3
+                uint32_t packed = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    int v;
+                    if (gx0 + j < nvec) {
+                        // VResizeCubicVec_32s8u: S0*b0 + (S1*b1 + (S2*b2 + S3*b3)), v_round, saturating packs
+                        float acc = __fmul_rn(enh_i2f(hor[3][j]), sm.sb[ph][3]);       // |S| <= 255 * 2048 * 1.27 < 2^22
+                        acc = __fadd_rn(__fmul_rn(enh_i2f(hor[2][j]), sm.sb[ph][2]), acc);
+                        acc = __fadd_rn(__fmul_rn(enh_i2f(hor[1][j]), sm.sb[ph][1]), acc);
+                        acc = __fadd_rn(__fmul_rn(enh_i2f(hor[0][j]), sm.sb[ph][0]), acc);
+                        v = enh_f2i_rn(acc);
+                    } else {
+                        // VResizeCubic + FixedPtCast<int, uchar, 22>
+                        const int16_t* ty = sm.st[ph];
+                        v = (hor[0][j] * ty[0] + hor[1][j] * ty[1] + hor[2][j] * ty[2] + hor[3][j] * ty[3] + (1 << 21)) >> 22;
+                    }
+                    packed |= static_cast<uint32_t>(min(max(v, 0), 255)) << (8 * j);
+                }
+                *reinterpret_cast<uint32_t*>(&sm.rs[4 * cy + i][4 * cx]) = packed;
+            }
+        }
+    }
+    __syncthreads();
+
+    const int ty4 = threadIdx.x >> 3, tx4 = (threadIdx.x & 7) * 4;     // 16 rows x 32 columns per pass
+    if (!sharpen) {
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {
+            const int gy = y0 + ty4 + 16 * pass, gx = x0 + tx4;
+            if (gy < H && gx < W) {                // W is a multiple of 4: all four columns are inside
+                const uint8_t* p = &sm.rs[ty4 + 16 * pass + 2][tx4 + 2];       // 2-byte aligned
+                const uint32_t lo = *reinterpret_cast<const uint16_t*>(p), hi = *reinterpret_cast<const uint16_t*>(p + 2);
+                *reinterpret_cast<uint32_t*>(img + static_cast<size_t>(gy) * W + gx) = lo | (hi << 16);
+            }
+        }
+        return;
+    }
+    // REFLECT_101 halo: output row -1 is row 1, row H is row H-2 (same for columns); rows first, then whole
+    // columns, so the corners come out right.  rs row of output row y is y - y0 + 2.
+    if (y0 == 0) {
+        for (int i = threadIdx.x; i < 4 * kEnhCells; i += kEnhResThreads) sm.rs[1][i] = sm.rs[3][i];
+    }
+    if (H - y0 <= kEnhBlock) {
+        for (int i = threadIdx.x; i < 4 * kEnhCells; i += kEnhResThreads) sm.rs[H - y0 + 2][i] = sm.rs[H - y0][i];
+    }
+    __syncthreads();
+    if (x0 == 0) {
+        for (int i = threadIdx.x; i < 4 * kEnhCells; i += kEnhResThreads) sm.rs[i][1] = sm.rs[i][3];
+    }
+    if (W - x0 <= kEnhBlock) {
+        for (int i = threadIdx.x; i < 4 * kEnhCells; i += kEnhResThreads) sm.rs[i][W - x0 + 2] = sm.rs[i][W - x0];
+    }
+    __syncthreads();
+
+    // filter2D [[-1,-1,-1],[-1,9,-1],[-1,-1,-1]]: 10*centre - (3x3 sum), saturated; 4 pixels per thread and pass
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+        const int ly = ty4 + 16 * pass;
+        const int gy = y0 + ly, gx = x0 + tx4;
+        if (gy >= H || gx >= W) continue;
+        int col[6];
+#pragma unroll
+        for (int j = 0; j < 6; ++j)
+            col[j] = sm.rs[ly + 1][tx4 + 1 + j] + sm.rs[ly + 2][tx4 + 1 + j] + sm.rs[ly + 3][tx4 + 1 + j];
+        uint32_t packed = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int v = 10 * sm.rs[ly + 2][tx4 + 2 + j] - (col[j] + col[j + 1] + col[j + 2]);
+            packed |= static_cast<uint32_t>(min(max(v, 0), 255)) << (8 * j);
+        }
+        *reinterpret_cast<uint32_t*>(img + static_cast<size_t>(gy) * W + gx) = packed;
+    }
+}
+
+__global__ void __launch_bounds__(kEnhResThreads)
 enh_resize_kernel(const unetb200_enh_crop* __restrict__ tab, int n, int total_blocks,
                   const uint8_t* __restrict__ src, uint8_t* __restrict__ ws, EnhTaps taps) {
     __shared__ EnhResizeSmem sm;
@@ -186,15 +234,37 @@ enh_resize_kernel(const unetb200_enh_crop* __restrict__ tab, int n, int total_bl
                 sm.sb[d][k] = __fmul_rn(static_cast<float>(taps.t[d][k]), 1.0f / (2048.0f * 2048.0f));
             }
     }
-    int ci = enh_find_crop(tab, n, blockIdx.x);
-    for (int blk = blockIdx.x; blk < total_blocks; blk += gridDim.x) {
+    // each CTA takes a contiguous run of blocks (the crop index then moves rarely and the descriptor stays
+    // cached); the gray window of block i+1 is fetched into registers while block i is computed
+    const int per = (total_blocks + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+    const int first = static_cast<int>(blockIdx.x) * per, last = min(first + per, total_blocks);
+    if (first >= last) return;
+    int ci = enh_find_crop(tab, n, first);
+    auto locate = [&](int blk, int& bx, int& by) {
         while (ci + 1 < n && tab[ci + 1].first_block <= blk) ++ci;     // blocks only move forward
+        const int bi = blk - tab[ci].first_block, nbx = tab[ci].blocks_x;
+        by = bi / nbx;
+        bx = bi - by * nbx;
+    };
+    uint8_t g[kEnhWinPerThread];
+    int bx, by;
+    locate(first, bx, by);
+    enh_fetch_window(tab + ci, bx, by, src, g);
+    for (int blk = first; blk < last; ++blk) {
         const unetb200_enh_crop* c = tab + ci;
-        const int bi = blk - c->first_block, nbx = c->blocks_x;
-        const int by = bi / nbx, bx = bi - by * nbx;
+        const int cbx = bx, cby = by;
         __syncthreads();                                               // shared memory of the previous block is free
-        if (c->flags & UNETB200_ENH_SHARPEN) enh_resize_block<1>(sm, c, bx, by, src, ws);
-        else enh_resize_block<0>(sm, c, bx, by, src, ws);
+#pragma unroll
+        for (int k = 0; k < kEnhWinPerThread; ++k) {
+            const int i = threadIdx.x + k * kEnhResThreads;
+            if (i < kEnhWin * kEnhWin) sm.gs[i / kEnhWin][i % kEnhWin] = g[k];
+        }
+        if (blk + 1 < last) {
+            locate(blk + 1, bx, by);
+            enh_fetch_window(tab + ci, bx, by, src, g);                // in flight during the cell phase
+        }
+        __syncthreads();
+        enh_resize_block(sm, c, cbx, cby, ws);
     }
 }
 
