@@ -359,8 +359,11 @@ __device__ __forceinline__ EnhAxis enh_axis(int p, float inv_tile) {
 }
 
 // One 32x32 block per CTA.  Measured alternatives on the 192-crop batch (ncu, this kernel alone): this
-// form 178 us; compile-time halo + descriptor by pointer 206-221 us; a persistent block loop 254 us
-// (64 registers); crop search through shared memory 236 us.
+// form 178 us; compile-time halo + descriptor by pointer 206-221 us; a strided persistent block loop 254 us
+// (64 registers); crop search through shared memory 236 us; one wave of 128-thread CTAs walking contiguous
+// block runs (the upscale's scheme) 178 us with 36 % fewer instructions -- the kernel is bound by the latency
+// of the pixel load -> LUT gather chain, not by issue; the same with the pixel loads hoisted above the table
+// set-up 197 us (56 registers).
 __global__ void __launch_bounds__(kEnhThreads)
 enh_clahe_kernel(const unetb200_enh_crop* __restrict__ tab, int n, uint8_t* __restrict__ ws,
                  uint8_t* __restrict__ out) {
