@@ -161,6 +161,13 @@ int unetb200_resize_coeffs(int in_size, int out_size, int32_t* kk, int32_t* boun
 int unetb200_resize_bicubic_u8(const uint8_t* src, int n, int h, int w, int c, const int32_t* kx_dev,
                                const int32_t* bx_dev, int ksx, const int32_t* ky_dev, const int32_t* by_dev,
                                int ksy, uint8_t* tmp_dev, uint8_t* dst_dev, int oh, int ow, void* stream);
+/* Same with a padded source: every source pixel is `pixel_stride` bytes of which the first c are read (c = 3,
+ * pixel_stride = 4: the RGBX buffer Pillow keeps for an RGB image, exported without a host-side repack); the
+ * result is packed [n,oh,ow,c].  Needs a horizontal pass (ow != w). */
+int unetb200_resize_bicubic_u8_ps(const uint8_t* src, int n, int h, int w, int c, int pixel_stride,
+                                  const int32_t* kx_dev, const int32_t* bx_dev, int ksx, const int32_t* ky_dev,
+                                  const int32_t* by_dev, int ksy, uint8_t* tmp_dev, uint8_t* dst_dev, int oh, int ow,
+                                  void* stream);
 /* np.where(mask) min/max of inference.py:85-93: mask uint8 [n_planes,h,w] ->
  * out int32 [n_planes,5] = {xmin, xmax, ymin, ymax, count}; an empty plane gives {w, -1, h, -1, 0}. */
 int unetb200_mask_bbox(const uint8_t* mask, int n_planes, int h, int w, int32_t* out, void* stream);
@@ -169,6 +176,9 @@ int unetb200_mask_bbox(const uint8_t* mask, int n_planes, int h, int w, int32_t*
  * rejection of inference.py:121-125 as the exact integer test sum < 3 * (x2-x1)*(y2-y1)*c. */
 int unetb200_box_sums(const uint8_t* img, int h, int w, int c, const int32_t* boxes_host, int n_boxes,
                       uint64_t* sums_dev, void* stream);
+/* Same for c-byte pixels of which only the first `used` bytes count (c = 4, used = 3: RGBX frames). */
+int unetb200_box_sums_ps(const uint8_t* img, int h, int w, int c, int used, const int32_t* boxes_host, int n_boxes,
+                         uint64_t* sums_dev, void* stream);
 
 /* ---- OCR crop enhancement: app_camera.py:572-598 enhance_for_ocrspace and
  * :685-705 enhance_for_date_ocr, i.e. cv2.cvtColor(RGB2GRAY) -> cv2.resize(fx=4, fy=4, INTER_CUBIC)
@@ -190,7 +200,7 @@ typedef struct unetb200_enh_crop {
     int32_t n_blocks;         /* out: output blocks of this crop */
     int32_t src_stride;       /* in : pixels per source row; 0 = the crop is packed ([h][w][3], plan places it),
                                *      > w = the crop is a window of a larger frame already in `src` */
-    int32_t reserved;
+    int32_t src_pixel_bytes;  /* in : bytes per source pixel, the first 3 are R, G, B; 0 = 3 (packed RGB), 4 = RGBX */
     uint64_t src_off;         /* out (in when src_stride != 0): byte offset of the crop's first pixel in `src` */
     uint64_t out_off;         /* out: byte offset of the uint8 [4h][4w] result in `out` */
     uint64_t ws_off;          /* out: byte offset of this crop's scratch in `workspace` */

@@ -86,6 +86,25 @@ def test_preprocess_on_gpu_equals_reference_definition(cuda_dev):
     assert np.array_equal(t[0].cpu().numpy(), ref.transpose(2, 0, 1))
 
 
+def test_zero_copy_upload_equals_packed_upload(checkpoint, cuda_dev, monkeypatch):
+    """run_unet / run_unet_enhanced give the same masks, crops and enhanced crops whether the frame goes up as
+    Pillow's RGBX buffer (Arrow export, no host repack) or as the packed np.asarray copy."""
+    from tw_invoice_unet_ocr_llm_b200 import inference as inf
+    from tw_invoice_unet_ocr_llm_b200.synthetic import synthetic_invoices_u8
+    pil = Image.fromarray(synthetic_invoices_u8(1, 480, 800, seed=85)[0])
+    view = inf._rgb_host_view(pil)
+    assert view.shape in ((480, 800, 4), (480, 800, 3)) and np.array_equal(view[..., :3], np.asarray(pil))
+    m1, c1, e1 = inf.run_unet_enhanced(pil, checkpoint)
+    monkeypatch.setattr(inf, "_HAVE_ARROW", False)
+    assert inf._rgb_host_view(pil).shape == (480, 800, 3)
+    m2, c2, e2 = inf.run_unet_enhanced(pil, checkpoint)
+    for k in inf.FIELDS:
+        assert np.array_equal(m1[k], m2[k])
+        assert (c1[k] is None) == (c2[k] is None) and (e1[k] is None) == (e2[k] is None)
+        if c1[k] is not None:
+            assert np.array_equal(np.array(c1[k]), np.array(c2[k])) and np.array_equal(np.array(e1[k]), np.array(e2[k]))
+
+
 def test_near_black_rejection_on_gpu_equals_host(cuda_dev):
     """reference inference.py:118-125: a crop whose mean is below 3 is dropped.  boxes_to_crops with the
     frame on the device (integer sums) must decide exactly like the host's ``np.array(crop).mean() < 3``,

@@ -100,3 +100,33 @@ def test_gpu_box_sums_exact(cuda_dev):
         assert np.array_equal(got, want), (h, w, c)
     with pytest.raises(RuntimeError):
         prepost.box_sums(torch.zeros((4, 4, 3), dtype=torch.uint8, device=cuda_dev), [(0, 0, 5, 4)])
+
+
+@pytest.mark.gpu
+def test_gpu_rgbx_sources_equal_packed(cuda_dev):
+    """Pillow keeps RGB images as 4-byte RGBX pixels; resize / box sums / crop enhancement read that layout in
+    place (pixel stride 4, 3 channels used) and must give exactly what the packed RGB frame gives, whatever
+    the padding byte holds."""
+    import torch
+    from PIL import Image
+    from tw_invoice_unet_ocr_llm_b200 import enhance, prepost
+    rng = np.random.default_rng(13)
+    for (h, w) in [(333, 517), (1080, 1920), (64, 512), (512, 640)]:
+        rgb = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        rgbx = np.concatenate([rgb, rng.integers(0, 256, (h, w, 1), dtype=np.uint8)], axis=2)   # junk padding
+        d3, d4 = torch.from_numpy(rgb).to(cuda_dev), torch.from_numpy(rgbx).to(cuda_dev)
+        want = np.array(Image.fromarray(rgb).resize((512, 512)))
+        got3 = prepost.resize_u8(d3[None], 512, 512)[0].cpu().numpy()
+        got4 = prepost.resize_u8(d4[None], 512, 512, channels=3)[0].cpu().numpy()
+        assert np.array_equal(got3, want) and np.array_equal(got4, want), (h, w)
+        rects = [(0, 0, w, h), (1, 1, 2, 2), (w - 1, h - 1, w, h), (3, 2, w - 2, h - 1), (5, 7, 41, 60)]
+        s3 = prepost.box_sums(d3, rects).cpu().numpy()
+        s4 = prepost.box_sums(d4, rects, channels=3).cpu().numpy()
+        ref = np.array([rgb[y1:y2, x1:x2].astype(np.int64).sum() for x1, y1, x2, y2 in rects])
+        assert np.array_equal(s3, ref) and np.array_equal(s4, ref), (h, w)
+        wins = [(5, 7, 41, 60), (0, 0, 33, 9), (w - 30, h - 20, w, h)]
+        kinds = ["text", "date", "amount"]
+        e3 = enhance.enhance_windows(d3, wins, kinds)
+        e4 = enhance.enhance_windows(d4, wins, kinds)
+        for a, b in zip(e3, e4):
+            assert np.array_equal(a, b)

@@ -45,7 +45,7 @@ class EnhCrop(C.Structure):
         ("h", C.c_int32), ("w", C.c_int32), ("flags", C.c_int32), ("clip", C.c_float),
         ("clip_count", C.c_int32), ("tile_h", C.c_int32), ("tile_w", C.c_int32),
         ("first_block", C.c_int32), ("blocks_x", C.c_int32), ("n_blocks", C.c_int32),
-        ("src_stride", C.c_int32), ("reserved", C.c_int32),
+        ("src_stride", C.c_int32), ("src_pixel_bytes", C.c_int32),
         ("src_off", C.c_uint64), ("out_off", C.c_uint64), ("ws_off", C.c_uint64),
     ]
 
@@ -79,8 +79,10 @@ SYMBOLS = {
     "unetb200_resize_ksize": (_I, [_I, _I]),
     "unetb200_resize_coeffs": (_I, [_I, _I, _VP, _VP]),
     "unetb200_resize_bicubic_u8": (_I, [_VP, _I, _I, _I, _I, _VP, _VP, _I, _VP, _VP, _I, _VP, _VP, _I, _I, _VP]),
+    "unetb200_resize_bicubic_u8_ps": (_I, [_VP, _I, _I, _I, _I, _I, _VP, _VP, _I, _VP, _VP, _I, _VP, _VP, _I, _I, _VP]),
     "unetb200_mask_bbox": (_I, [_VP, _I, _I, _I, _VP, _VP]),
     "unetb200_box_sums": (_I, [_VP, _I, _I, _I, C.POINTER(C.c_int32), _I, _VP, _VP]),
+    "unetb200_box_sums_ps": (_I, [_VP, _I, _I, _I, _I, C.POINTER(C.c_int32), _I, _VP, _VP]),
     "unetb200_enhance_plan": (_I, [C.POINTER(EnhCrop), _I, C.POINTER(_U64), C.POINTER(_U64), C.POINTER(_U64)]),
     "unetb200_enhance_run": (_I, [C.POINTER(EnhCrop), _VP, _I, _VP, _VP, _VP, _VP]),
 }

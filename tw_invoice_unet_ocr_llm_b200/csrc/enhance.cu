@@ -34,7 +34,9 @@ constexpr int kMaxSide = 8192;          // 4x -> 32768: keeps every int product 
 bool crop_ok(const unetb200_enh_crop& c) {
     return c.h > 0 && c.w > 0 && c.h <= kMaxSide && c.w <= kMaxSide &&
            (c.flags & ~(UNETB200_ENH_SHARPEN | UNETB200_ENH_BLUR | UNETB200_ENH_OTSU)) == 0 && c.clip > 0.f &&
-           (c.src_stride == 0 || c.src_stride >= c.w);
+           (c.src_stride == 0 || c.src_stride >= c.w) &&
+           (c.src_pixel_bytes == 0 || c.src_pixel_bytes == 3 || c.src_pixel_bytes == 4) &&
+           (c.src_stride != 0 || c.src_pixel_bytes != 4);          // packed crops are RGB
 }
 
 }  // namespace
@@ -72,7 +74,7 @@ int unetb200_enhance_plan(unetb200_enh_crop* table, int n, uint64_t* src_bytes, 
         if (blocks + c.n_blocks > 0x7fffffff) return ub_fail(UNETB200_EINVAL, "enhance_plan: batch too large");
         c.first_block = static_cast<int32_t>(blocks);
         blocks += c.n_blocks;
-        c.reserved = 0;
+        if (c.src_pixel_bytes == 0) c.src_pixel_bytes = 3;
         if (c.src_stride == 0) {             // packed crop: placed here
             c.src_stride = c.w;
             c.src_off = so;
@@ -101,7 +103,7 @@ int unetb200_enhance_run(const unetb200_enh_crop* table_host, const void* table_
     bool any_otsu = false;
     for (int i = 0; i < n; ++i) {
         const unetb200_enh_crop& c = table_host[i];
-        if (!crop_ok(c) || c.src_stride < c.w || c.first_block != blocks || c.n_blocks <= 0 || c.tile_h <= 0 || c.tile_w <= 0 ||
+        if (!crop_ok(c) || c.src_stride < c.w || c.src_pixel_bytes == 0 || c.first_block != blocks || c.n_blocks <= 0 || c.tile_h <= 0 || c.tile_w <= 0 ||
             c.blocks_x != (4 * c.w + ub::kEnhBlock - 1) / ub::kEnhBlock)
             return ub_fail(UNETB200_EINVAL, "enhance_run: table was not produced by unetb200_enhance_plan");
         if (c.out_off != out_bytes)

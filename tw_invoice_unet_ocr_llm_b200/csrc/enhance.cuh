@@ -99,7 +99,7 @@ struct EnhResizeSmem {
 constexpr int kEnhWinPerThread = (kEnhWin * kEnhWin + kEnhResThreads - 1) / kEnhResThreads;
 __device__ __forceinline__ void enh_fetch_window(const unetb200_enh_crop* __restrict__ c, int bx, int by,
                                                  const uint8_t* __restrict__ src, uint8_t (&g)[kEnhWinPerThread]) {
-    const int h = c->h, w = c->w, stride = c->src_stride;
+    const int h = c->h, w = c->w, stride = c->src_stride, pb = c->src_pixel_bytes;
     const uint8_t* in = src + c->src_off;
 #pragma unroll
     for (int k = 0; k < kEnhWinPerThread; ++k) {
@@ -109,7 +109,7 @@ __device__ __forceinline__ void enh_fetch_window(const unetb200_enh_crop* __rest
             // source window rows / cols (block origin / 4) - 2 .. + 9, border-clamped like the resize tap indices
             const int r = i / kEnhWin, q = i - r * kEnhWin;
             const int sy = min(max(by * (kEnhBlock / 4) - 2 + r, 0), h - 1), sx = min(max(bx * (kEnhBlock / 4) - 2 + q, 0), w - 1);
-            const uint8_t* p = in + (static_cast<size_t>(sy) * stride + sx) * 3;
+            const uint8_t* p = in + (static_cast<size_t>(sy) * stride + sx) * pb;
             g[k] = static_cast<uint8_t>((p[0] * 9798 + p[1] * 19235 + p[2] * 3735 + (1 << 14)) >> 15);
         }
     }

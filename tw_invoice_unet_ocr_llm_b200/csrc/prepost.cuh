@@ -23,24 +23,25 @@ __device__ __forceinline__ uint8_t clip8(int v) {
     return static_cast<uint8_t>(v < 0 ? 0 : (v > 255 ? 255 : v));
 }
 
-// src [n][h][w][c] -> dst [n][h][ow][c]; one thread per (row, output column), all channels
+// src [n][h][w][ps] (the first C bytes of every ps-byte pixel) -> dst [n][h][ow][C]; one thread per (row,
+// output column), all channels.  ps = 4, C = 3 reads Pillow's own RGBX storage of an RGB image.
 template <int C>
 __global__ void resize_horizontal_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
                                          const int32_t* __restrict__ kk, const int32_t* __restrict__ bounds,
-                                         int ksize, int rows /* n*h */, int w, int ow) {
+                                         int ksize, int rows /* n*h */, int w, int ow, int ps) {
     const int xx = blockIdx.x * blockDim.x + threadIdx.x;
     const int row = blockIdx.y;
     if (xx >= ow || row >= rows) return;
     const int xmin = bounds[2 * xx], xn = bounds[2 * xx + 1];
     const int32_t* k = kk + static_cast<size_t>(xx) * ksize;
-    const uint8_t* in = src + (static_cast<size_t>(row) * w + xmin) * C;
+    const uint8_t* in = src + (static_cast<size_t>(row) * w + xmin) * ps;
     int acc[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) acc[c] = 1 << (kResizePrecisionBits - 1);
     for (int x = 0; x < xn; ++x) {
         const int kv = __ldg(k + x);
 #pragma unroll
-        for (int c = 0; c < C; ++c) acc[c] += static_cast<int>(__ldg(in + x * C + c)) * kv;
+        for (int c = 0; c < C; ++c) acc[c] += static_cast<int>(__ldg(in + x * ps + c)) * kv;
     }
     uint8_t* out = dst + (static_cast<size_t>(row) * ow + xx) * C;
 #pragma unroll
@@ -126,7 +127,8 @@ __global__ void __launch_bounds__(256) mask_bbox_kernel(const uint8_t* __restric
 constexpr int kMaxBoxes = 16;
 struct BoxList { int n; int x1[kMaxBoxes], y1[kMaxBoxes], x2[kMaxBoxes], y2[kMaxBoxes]; };
 
-__global__ void __launch_bounds__(256) box_sum_kernel(const uint8_t* __restrict__ img, int w, int c,
+// `used` < c (only c = 4, used = 3: RGBX frames) leaves the trailing byte of every pixel out of the sums.
+__global__ void __launch_bounds__(256) box_sum_kernel(const uint8_t* __restrict__ img, int w, int c, int used,
                                                       const __grid_constant__ BoxList boxes,
                                                       unsigned long long* __restrict__ sums) {
     const int b = blockIdx.y;
@@ -138,16 +140,19 @@ __global__ void __launch_bounds__(256) box_sum_kernel(const uint8_t* __restrict_
         // head bytes up to 16-byte alignment, 16-byte body, tail
         const int head = min(row_bytes, static_cast<int>((16 - (reinterpret_cast<uintptr_t>(row) & 15)) & 15));
         const int body = (row_bytes - head) / 16;
+        const uint32_t keep = used < c ? 0x00ffffffu : 0xffffffffu;   // pixels are 4-byte aligned when used < c
         unsigned int part = 0;
-        if (static_cast<int>(threadIdx.x) < head) part += row[threadIdx.x];
+        if (static_cast<int>(threadIdx.x) < head && (used == c || (threadIdx.x & 3) != 3)) part += row[threadIdx.x];
         const uint4* r4 = reinterpret_cast<const uint4*>(row + head);
         for (int i = threadIdx.x; i < body; i += blockDim.x) {
             const uint4 v = __ldg(r4 + i);
             // per-byte sums of four words: __vsadu4(x, 0) adds the four bytes of x
-            part += __vsadu4(v.x, 0u) + __vsadu4(v.y, 0u) + __vsadu4(v.z, 0u) + __vsadu4(v.w, 0u);
+            part += __vsadu4(v.x & keep, 0u) + __vsadu4(v.y & keep, 0u) + __vsadu4(v.z & keep, 0u) +
+                    __vsadu4(v.w & keep, 0u);
         }
         const int tail0 = head + body * 16;
-        if (tail0 + static_cast<int>(threadIdx.x) < row_bytes) part += row[tail0 + threadIdx.x];
+        if (tail0 + static_cast<int>(threadIdx.x) < row_bytes && (used == c || (threadIdx.x & 3) != 3))
+            part += row[tail0 + threadIdx.x];
         acc += part;
     }
 #pragma unroll

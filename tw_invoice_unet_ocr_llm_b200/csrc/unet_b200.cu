@@ -1258,10 +1258,20 @@ int unetb200_resize_coeffs(int in_size, int out_size, int32_t* kk, int32_t* boun
 int unetb200_resize_bicubic_u8(const uint8_t* src, int n, int h, int w, int c, const int32_t* kx_dev,
                                const int32_t* bx_dev, int ksx, const int32_t* ky_dev, const int32_t* by_dev,
                                int ksy, uint8_t* tmp_dev, uint8_t* dst_dev, int oh, int ow, void* stream) {
+    return unetb200_resize_bicubic_u8_ps(src, n, h, w, c, c, kx_dev, bx_dev, ksx, ky_dev, by_dev, ksy, tmp_dev,
+                                         dst_dev, oh, ow, stream);
+}
+
+int unetb200_resize_bicubic_u8_ps(const uint8_t* src, int n, int h, int w, int c, int ps, const int32_t* kx_dev,
+                                  const int32_t* bx_dev, int ksx, const int32_t* ky_dev, const int32_t* by_dev,
+                                  int ksy, uint8_t* tmp_dev, uint8_t* dst_dev, int oh, int ow, void* stream) {
     if (!src || !dst_dev || n <= 0 || h <= 0 || w <= 0 || oh <= 0 || ow <= 0)
         return fail(UNETB200_EINVAL, "resize: bad argument");
     if (!(c == 1 || c == 3 || c == 4)) return fail(UNETB200_EINVAL, "resize: channels must be 1, 3 or 4");
+    if (ps < c || ps > 16) return fail(UNETB200_EINVAL, "resize: pixel stride must be in [channels, 16]");
     const bool need_h = ow != w, need_v = oh != h;
+    if (ps != c && !need_h)
+        return fail(UNETB200_EINVAL, "resize: a padded source (pixel stride != channels) needs a horizontal pass");
     if (need_h && (!kx_dev || !bx_dev)) return fail(UNETB200_EINVAL, "resize: horizontal tables missing");
     if (need_v && (!ky_dev || !by_dev)) return fail(UNETB200_EINVAL, "resize: vertical tables missing");
     if (need_h && need_v && !tmp_dev) return fail(UNETB200_EINVAL, "resize: intermediate buffer missing");
@@ -1276,18 +1286,18 @@ int unetb200_resize_bicubic_u8(const uint8_t* src, int n, int h, int w, int c, c
             // rows beyond the grid.y limit: one launch per image
             for (int i = 0; i < n; ++i) {
                 dim3 g((ow + 127) / 128, h);
-                const uint8_t* si = src + static_cast<size_t>(i) * h * w * c;
+                const uint8_t* si = src + static_cast<size_t>(i) * h * w * ps;
                 uint8_t* oi = out + static_cast<size_t>(i) * h * ow * c;
-                if (c == 1) ub::resize_horizontal_kernel<1><<<g, 128, 0, s>>>(si, oi, kx_dev, bx_dev, ksx, h, w, ow);
-                else if (c == 3) ub::resize_horizontal_kernel<3><<<g, 128, 0, s>>>(si, oi, kx_dev, bx_dev, ksx, h, w, ow);
-                else ub::resize_horizontal_kernel<4><<<g, 128, 0, s>>>(si, oi, kx_dev, bx_dev, ksx, h, w, ow);
+                if (c == 1) ub::resize_horizontal_kernel<1><<<g, 128, 0, s>>>(si, oi, kx_dev, bx_dev, ksx, h, w, ow, ps);
+                else if (c == 3) ub::resize_horizontal_kernel<3><<<g, 128, 0, s>>>(si, oi, kx_dev, bx_dev, ksx, h, w, ow, ps);
+                else ub::resize_horizontal_kernel<4><<<g, 128, 0, s>>>(si, oi, kx_dev, bx_dev, ksx, h, w, ow, ps);
             }
         } else if (c == 1) {
-            ub::resize_horizontal_kernel<1><<<grid, 128, 0, s>>>(src, out, kx_dev, bx_dev, ksx, n * h, w, ow);
+            ub::resize_horizontal_kernel<1><<<grid, 128, 0, s>>>(src, out, kx_dev, bx_dev, ksx, n * h, w, ow, ps);
         } else if (c == 3) {
-            ub::resize_horizontal_kernel<3><<<grid, 128, 0, s>>>(src, out, kx_dev, bx_dev, ksx, n * h, w, ow);
+            ub::resize_horizontal_kernel<3><<<grid, 128, 0, s>>>(src, out, kx_dev, bx_dev, ksx, n * h, w, ow, ps);
         } else {
-            ub::resize_horizontal_kernel<4><<<grid, 128, 0, s>>>(src, out, kx_dev, bx_dev, ksx, n * h, w, ow);
+            ub::resize_horizontal_kernel<4><<<grid, 128, 0, s>>>(src, out, kx_dev, bx_dev, ksx, n * h, w, ow, ps);
         }
         cur = out;
     }
@@ -1311,8 +1321,15 @@ int unetb200_mask_bbox(const uint8_t* mask, int n_planes, int h, int w, int32_t*
 
 int unetb200_box_sums(const uint8_t* img, int h, int w, int c, const int32_t* boxes_host, int n_boxes,
                       uint64_t* sums_dev, void* stream) {
+    return unetb200_box_sums_ps(img, h, w, c, c, boxes_host, n_boxes, sums_dev, stream);
+}
+
+int unetb200_box_sums_ps(const uint8_t* img, int h, int w, int c, int used, const int32_t* boxes_host, int n_boxes,
+                         uint64_t* sums_dev, void* stream) {
     if (!img || !boxes_host || !sums_dev || h <= 0 || w <= 0 || c <= 0 || n_boxes <= 0 || n_boxes > ub::kMaxBoxes)
         return fail(UNETB200_EINVAL, "box_sums: bad argument");
+    if (!(used == c || (c == 4 && used == 3 && (reinterpret_cast<uintptr_t>(img) & 3) == 0)))
+        return fail(UNETB200_EINVAL, "box_sums: used bytes per pixel must equal the pixel size, or 3 of 4 (aligned RGBX)");
     ub::BoxList bl;
     bl.n = n_boxes;
     int rows = 1;
@@ -1326,7 +1343,7 @@ int unetb200_box_sums(const uint8_t* img, int h, int w, int c, const int32_t* bo
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     UB_CUDA(cudaMemsetAsync(sums_dev, 0, sizeof(uint64_t) * n_boxes, s));
     dim3 grid(static_cast<unsigned>(std::min(rows, 296)), static_cast<unsigned>(n_boxes));
-    ub::box_sum_kernel<<<grid, 256, 0, s>>>(img, w, c, bl, reinterpret_cast<unsigned long long*>(sums_dev));
+    ub::box_sum_kernel<<<grid, 256, 0, s>>>(img, w, c, used, bl, reinterpret_cast<unsigned long long*>(sums_dev));
     UB_CUDA(cudaGetLastError());
     return UNETB200_OK;
 }

@@ -118,17 +118,17 @@ def enhance_batch(crops: Sequence, kinds: Sequence, device=None) -> List[Optiona
 
 
 def enhance_windows(frame: torch.Tensor, rects: Sequence[tuple], kinds: Sequence) -> List[np.ndarray]:
-    """Enhance rectangles ``(x1, y1, x2, y2)`` (half-open) of a uint8 ``[H, W, 3]`` RGB frame that is
-    already on the device -- the crops ``run_unet`` cuts from the frame it uploaded -- without packing or
-    re-uploading them: only the 72-byte descriptors go up."""
-    if frame.dtype != torch.uint8 or frame.dim() != 3 or frame.shape[2] != 3 or not frame.is_cuda \
+    """Enhance rectangles ``(x1, y1, x2, y2)`` (half-open) of a uint8 ``[H, W, 3]`` RGB (or ``[H, W, 4]``
+    RGBX) frame that is already on the device -- the crops ``run_unet`` cuts from the frame it uploaded --
+    without packing or re-uploading them: only the 72-byte descriptors go up."""
+    if frame.dtype != torch.uint8 or frame.dim() != 3 or frame.shape[2] not in (3, 4) or not frame.is_cuda \
             or not frame.is_contiguous():
-        raise RuntimeError("enhance_windows expects a contiguous CUDA uint8 [H,W,3] frame")
+        raise RuntimeError("enhance_windows expects a contiguous CUDA uint8 [H,W,3] or [H,W,4] frame")
     if len(rects) != len(kinds):
         raise ValueError("rects and kinds differ in length")
     if not rects:
         return []
-    fh, fw = int(frame.shape[0]), int(frame.shape[1])
+    fh, fw, pb = int(frame.shape[0]), int(frame.shape[1]), int(frame.shape[2])
     n = len(rects)
     table = (nat.EnhCrop * n)()
     for t, (x1, y1, x2, y2), kind in zip(table, rects, kinds):
@@ -136,7 +136,7 @@ def enhance_windows(frame: torch.Tensor, rects: Sequence[tuple], kinds: Sequence
         if not (0 <= x1 < x2 <= fw and 0 <= y1 < y2 <= fh):
             raise ValueError(f"rectangle {(x1, y1, x2, y2)} outside the {fw}x{fh} frame")
         t.flags, t.clip = _recipe(kind)
-        t.h, t.w, t.src_stride, t.src_off = y2 - y1, x2 - x1, fw, (y1 * fw + x1) * 3
+        t.h, t.w, t.src_stride, t.src_pixel_bytes, t.src_off = y2 - y1, x2 - x1, fw, pb, (y1 * fw + x1) * pb
     sb, ob, wb = C.c_uint64(), C.c_uint64(), C.c_uint64()
     nat.check(nat.lib().unetb200_enhance_plan(table, n, C.byref(sb), C.byref(ob), C.byref(wb)))
     dev = frame.device

@@ -98,7 +98,7 @@ def preprocess(pil_img: Image.Image):
         w, h = pil_img.size
         if h <= 0 or w <= 0:
             raise ValueError(f"Invalid image shape: {(h, w, 3)}")
-        x = prepost.resize_u8(_upload_rgb(pil_img), IMG_SIZE, IMG_SIZE)           # uint8 [1, 512, 512, 3]
+        x = prepost.resize_u8(_upload_rgb(pil_img), IMG_SIZE, IMG_SIZE, channels=3)   # uint8 [1, 512, 512, 3]
         # a device-tensor divisor keeps this a true IEEE division (torch turns `/ python_scalar` into a
         # multiplication by the reciprocal on CUDA, which is 1 ulp off numpy's `/ 255.0` for some k)
         out = (x.permute(0, 3, 1, 2).to(torch.float32) / torch.full((), 255.0, device=x.device)).contiguous()
@@ -158,7 +158,7 @@ def _extent(box) -> Optional[tuple]:
 def boxes_to_crops(pil_img: Image.Image, boxes: np.ndarray, frame_dev=None, rects_out: Optional[dict] = None
                    ) -> Dict[str, Optional[Image.Image]]:
     """Same, from the GPU reduction ``prepost.mask_bbox``: ``boxes`` int32 [3, 5] = xmin, xmax, ymin,
-    ymax, count per field.  With ``frame_dev`` (the uint8 [H, W, 3] frame already on the device) the
+    ymax, count per field.  With ``frame_dev`` (the uint8 [H, W, 3] or RGBX [H, W, 4] frame on the device) the
     near-black test runs there as well: ``mean < 3`` is the integer test ``sum < 3 * bytes`` (exact: the
     float64 mean of fewer than 2^52 bytes cannot round across 3), so only accepted crops are cut."""
     if frame_dev is None:
@@ -166,9 +166,9 @@ def boxes_to_crops(pil_img: Image.Image, boxes: np.ndarray, frame_dev=None, rect
     from . import prepost
     rects = [_crop_rect(pil_img.size, _extent(boxes[i])) for i in range(len(FIELDS))]
     live = [r for r in rects if r is not None]
-    sums = prepost.box_sums(frame_dev, live).cpu().tolist() if live else []
+    sums = prepost.box_sums(frame_dev, live, channels=3).cpu().tolist() if live else []
     crops: Dict[str, Optional[Image.Image]] = {}
-    channels = frame_dev.shape[2]
+    channels = 3                    # R, G, B count (an RGBX frame's padding byte does not)
     for key, r in zip(FIELDS, rects):
         if r is None:
             crops[key] = None
@@ -190,11 +190,35 @@ def _require_cuda():
 _staging: Dict[tuple, torch.Tensor] = {}
 
 
+try:
+    import pyarrow as _pa
+    _HAVE_ARROW = True
+except Exception:
+    _pa = None
+    _HAVE_ARROW = False
+
+
+def _rgb_host_view(pil_img: Image.Image) -> np.ndarray:
+    """uint8 view of an RGB image's pixels: ``(H, W, 4)`` RGBX straight out of Pillow's own buffer when it can
+    be exported without a copy (Pillow >= 11.1 Arrow interface + pyarrow; the packed ``np.asarray`` costs
+    1.2 ms for a 1080p frame), else the packed ``(H, W, 3)`` array."""
+    if _HAVE_ARROW and hasattr(pil_img, "__arrow_c_array__"):
+        try:
+            flat = _pa.array(pil_img).flatten().to_numpy(zero_copy_only=True)
+            w, h = pil_img.size
+            if flat.dtype == np.uint8 and flat.size == h * w * 4:
+                return flat.reshape(h, w, 4)
+        except Exception:          # any export problem: the packed path below is always right
+            pass
+    return np.asarray(pil_img)
+
+
 def _upload_rgb(pil_img: Image.Image, wait: bool = False) -> torch.Tensor:
-    """RGB PIL image -> uint8 [1, H, W, 3] on DEVICE through a cached pinned staging buffer.
+    """RGB PIL image -> uint8 [1, H, W, 3] (packed) or [1, H, W, 4] (Pillow's RGBX storage; the fourth byte
+    is padding and is never read) on DEVICE through a cached pinned staging buffer.
     Callers synchronise (``.cpu()``) before the next call, so the buffer is free to reuse; with
     ``wait`` the copy is awaited here (several uploads back to back)."""
-    arr = np.asarray(pil_img)
+    arr = _rgb_host_view(pil_img)
     key = (threading.get_ident(), arr.shape)
     buf = _staging.get(key)
     if buf is None:
@@ -232,7 +256,7 @@ def _segment_images(eng, pil_imgs: Sequence[Image.Image]):
             if _gpu_resizable(im):
                 # fresh device copy per image (the pinned staging buffer is reused after the copy lands)
                 f = _upload_rgb(im, wait=True)
-                prepost.resize_u8(f, IMG_SIZE, IMG_SIZE, out=x[i:i + 1])
+                prepost.resize_u8(f, IMG_SIZE, IMG_SIZE, out=x[i:i + 1], channels=3)
                 frames.append(f[0])
             else:
                 x[i].copy_(torch.from_numpy(_resized_rgb_u8(im.resize((IMG_SIZE, IMG_SIZE)))))
@@ -258,8 +282,8 @@ def run_unet(pil_img: Image.Image, checkpoint_path: str):
     frame = None
     # the reference resizes twice (:63 then :35); the second resize is the identity
     if _gpu_resizable(pil_img):
-        frame = _upload_rgb(pil_img)                       # uint8 [1, H, W, 3]; stays on the GPU
-        x = prepost.resize_u8(frame, IMG_SIZE, IMG_SIZE)   # the resized frame never leaves the GPU
+        frame = _upload_rgb(pil_img)                       # uint8 [1, H, W, 3 or 4]; stays on the GPU
+        x = prepost.resize_u8(frame, IMG_SIZE, IMG_SIZE, channels=3)   # the resized frame never leaves the GPU
     else:
         x = torch.from_numpy(_resized_rgb_u8(pil_img.resize((IMG_SIZE, IMG_SIZE)))[None]).to(DEVICE)
     _, mask = eng.run(x, want_logits=False, thresholds=thr)
@@ -293,7 +317,7 @@ def run_unet_enhanced(pil_img: Image.Image, checkpoint_path: str):
         done = dict(zip(live, arrs))
         return masks, crops, {f: Image.fromarray(done[f]) if f in done else None for f in FIELDS}
     frame = _upload_rgb(pil_img)
-    x = prepost.resize_u8(frame, IMG_SIZE, IMG_SIZE)
+    x = prepost.resize_u8(frame, IMG_SIZE, IMG_SIZE, channels=3)
     _, mask = eng.run(x, want_logits=False, thresholds=thr)
     boxes = prepost.mask_bbox(mask)
     m = mask[0].cpu().numpy()

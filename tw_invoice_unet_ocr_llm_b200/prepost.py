@@ -44,20 +44,27 @@ def _tables(in_size: int, out_size: int, device: torch.device):
     return t
 
 
-def resize_u8(frames: torch.Tensor, oh: int, ow: int, out: torch.Tensor = None) -> torch.Tensor:
+def resize_u8(frames: torch.Tensor, oh: int, ow: int, out: torch.Tensor = None, channels: int = None) -> torch.Tensor:
     """uint8 ``[N, H, W, C]`` on a CUDA device -> uint8 ``[N, oh, ow, C]``, bit-identical to
     ``PIL.Image.resize((ow, oh))`` (default BICUBIC) of each frame.  Enqueued on the current stream.
-    ``out``: optional contiguous destination (e.g. a slot of a batch tensor)."""
+    ``out``: optional contiguous destination (e.g. a slot of a batch tensor).  ``channels`` < C reads only
+    the leading channels of every pixel (``channels=3`` of a ``[N, H, W, 4]`` RGBX frame, Pillow's own storage
+    of an RGB image) and returns ``[N, oh, ow, channels]``."""
     if frames.dtype != torch.uint8 or frames.dim() != 4 or not frames.is_cuda:
         raise RuntimeError("resize_u8 expects a CUDA uint8 [N,H,W,C] tensor")
     frames = frames.contiguous()
-    n, h, w, c = frames.shape
+    n, h, w, ps = frames.shape
+    c = ps if channels is None else int(channels)
+    if not (1 <= c <= ps):
+        raise RuntimeError(f"resize_u8: channels={c} of a {ps}-byte pixel")
     dev = frames.device
     if out is None:
         out = torch.empty((n, oh, ow, c), dtype=torch.uint8, device=dev)
     elif (out.dtype != torch.uint8 or tuple(out.shape) != (n, oh, ow, c) or out.device != dev
           or not out.is_contiguous()):
         raise RuntimeError("resize_u8: out must be a contiguous uint8 [N,oh,ow,C] tensor on the same device")
+    if ow == w and c != ps:          # no horizontal pass to drop the padding byte in: repack first
+        frames, ps = frames[..., :c].contiguous(), c
     if oh == h and ow == w:
         out.copy_(frames)
         return out
@@ -71,8 +78,8 @@ def resize_u8(frames: torch.Tensor, oh: int, ow: int, out: torch.Tensor = None) 
         tmp = torch.empty((n, h, ow, c), dtype=torch.uint8, device=dev)
     p = lambda t: None if t is None else t.data_ptr()
     with torch.cuda.device(dev):
-        nat.check(nat.lib().unetb200_resize_bicubic_u8(
-            frames.data_ptr(), n, h, w, c, p(kx), p(bx), ksx, p(ky), p(by), ksy, p(tmp), out.data_ptr(),
+        nat.check(nat.lib().unetb200_resize_bicubic_u8_ps(
+            frames.data_ptr(), n, h, w, c, ps, p(kx), p(bx), ksx, p(ky), p(by), ksy, p(tmp), out.data_ptr(),
             oh, ow, torch.cuda.current_stream(dev).cuda_stream))
     return out
 
@@ -91,18 +98,20 @@ def mask_bbox(mask: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def box_sums(frame: torch.Tensor, rects) -> torch.Tensor:
+def box_sums(frame: torch.Tensor, rects, channels: int = None) -> torch.Tensor:
     """uint8 ``[H, W, C]`` frame on a CUDA device + up to 16 half-open rectangles ``(x1, y1, x2, y2)``
     -> int64 ``[n]`` byte sums on the device (the ``np.array(crop).mean() < 3`` test of reference
-    inference.py:121-125 becomes ``sum < 3 * area * C``).  Enqueued on the current stream."""
+    inference.py:121-125 becomes ``sum < 3 * area * channels``).  ``channels=3`` on a ``[H, W, 4]`` RGBX frame
+    leaves the padding byte out.  Enqueued on the current stream."""
     if frame.dtype != torch.uint8 or frame.dim() != 3 or not frame.is_cuda or not frame.is_contiguous():
         raise RuntimeError("box_sums expects a contiguous CUDA uint8 [H,W,C] tensor")
     import ctypes as C
     h, w, c = frame.shape
+    used = c if channels is None else int(channels)
     n = len(rects)
     flat = (C.c_int32 * (4 * n))(*[int(v) for r in rects for v in r])
     out = torch.empty((n,), dtype=torch.int64, device=frame.device)
     with torch.cuda.device(frame.device):
-        nat.check(nat.lib().unetb200_box_sums(frame.data_ptr(), h, w, c, flat, n, out.data_ptr(),
-                                              torch.cuda.current_stream(frame.device).cuda_stream))
+        nat.check(nat.lib().unetb200_box_sums_ps(frame.data_ptr(), h, w, c, used, flat, n, out.data_ptr(),
+                                                 torch.cuda.current_stream(frame.device).cuda_stream))
     return out
