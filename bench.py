@@ -242,8 +242,12 @@ def main():
         raise SystemExit("bench.py needs a CUDA (B200) device: there is no CPU path for --impl b200")
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    numa_cores = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # one process per GPU: keep this rank and its pinned staging on the cores / memory local to its GPU
+        from tw_invoice_unet_ocr_llm_b200.launcher import bind_to_gpu_numa
+        numa_cores = bind_to_gpu_numa(local_rank)
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's version banner must not land on stdout
         dist.init_process_group("nccl", device_id=dev)
 
@@ -506,6 +510,7 @@ def main():
             "config": {"workload": f"configs[1]: fixture best_unet_model.pth (seeded, same 136-key fp32 format), "
                                    f"batch {B} x 3x{S}x{S} synthetic invoices per GPU, bf16 NHWC tensor-core forward, "
                                    "fp32 NCHW input resident in HBM, outputs fp32 logits + uint8 masks",
+                       "numa_bound_cores_rank0": len(numa_cores) if numa_cores else None,
                        "batch_per_gpu": B, "image": f"3x{S}x{S}", "parallelism": f"dp{world} (batch sharding, no collective)",
                        "l2": "no flush needed: per-step working set (~9 GB of activations, 201 MB input) exceeds the 126 MB L2",
                        "gflop_per_image": GFLOP_PER_IMAGE_512 * (S * S) / (512 * 512),
