@@ -180,6 +180,10 @@ int unetb200_box_sums(const uint8_t* img, int h, int w, int c, const int32_t* bo
 int unetb200_box_sums_ps(const uint8_t* img, int h, int w, int c, int used, const int32_t* boxes_host, int n_boxes,
                          uint64_t* sums_dev, void* stream);
 
+/* Test hook (host only): x / d as the kernels compute it for their per-tile index arithmetic (multiply-high by a
+ * precomputed magic number, then shift); valid for x < 2^31, d >= 1. */
+uint32_t unetb200_test_fastdiv(uint32_t d, uint32_t x);
+
 /* ---- OCR crop enhancement: app_camera.py:572-598 enhance_for_ocrspace and
  * :685-705 enhance_for_date_ocr, i.e. cv2.cvtColor(RGB2GRAY) -> cv2.resize(fx=4, fy=4, INTER_CUBIC)
  * -> [cv2.filter2D 3x3 sharpen] -> CLAHE(clip, 8x8) -> [cv2.GaussianBlur 3x3] -> [cv2.threshold OTSU],

@@ -189,3 +189,19 @@ def test_enhance_surface_matches_reference_and_has_no_cpu_path():
         with pytest.raises(RuntimeError, match="no CPU path"):
             from PIL import Image
             inf.run_unet_enhanced(Image.new("RGB", (32, 32)), "missing.pth")
+
+
+def test_fastdiv_magic_numbers(nat):
+    """The conv kernels divide tile indices by launch constants with multiply-high + shift; the magic numbers
+    must give floor(x / d) for every dividend below 2^31 (edge values, powers of two, and random pairs)."""
+    import random
+    lib = nat.lib()
+    rnd = random.Random(7)
+    ds = [1, 2, 3, 4, 5, 6, 7, 9, 10, 31, 32, 33, 63, 64, 65, 127, 128, 148, 255, 256, 1000, 4096, 4097, 65535, 65536,
+          131072, 999983, 2 ** 20 + 1, 2 ** 30, 2 ** 31 - 1] + [rnd.randrange(1, 2 ** 31) for _ in range(60)]
+    for d in ds:
+        xs = [0, 1, d - 1, d, d + 1, 2 * d - 1, 2 * d, 2 ** 31 - 1, 2 ** 31 - 2, (2 ** 31 - 1) // d * d,
+              max((2 ** 31 - 1) // d * d - 1, 0)] + [rnd.randrange(0, 2 ** 31) for _ in range(200)]
+        for x in xs:
+            if 0 <= x < 2 ** 31:
+                assert lib.unetb200_test_fastdiv(d, x) == x // d, (d, x)

@@ -83,6 +83,7 @@ SYMBOLS = {
     "unetb200_mask_bbox": (_I, [_VP, _I, _I, _I, _VP, _VP]),
     "unetb200_box_sums": (_I, [_VP, _I, _I, _I, C.POINTER(C.c_int32), _I, _VP, _VP]),
     "unetb200_box_sums_ps": (_I, [_VP, _I, _I, _I, _I, C.POINTER(C.c_int32), _I, _VP, _VP]),
+    "unetb200_test_fastdiv": (C.c_uint32, [C.c_uint32, C.c_uint32]),
     "unetb200_enhance_plan": (_I, [C.POINTER(EnhCrop), _I, C.POINTER(_U64), C.POINTER(_U64), C.POINTER(_U64)]),
     "unetb200_enhance_run": (_I, [C.POINTER(EnhCrop), _VP, _I, _VP, _VP, _VP, _VP]),
 }

@@ -1319,6 +1319,15 @@ int unetb200_mask_bbox(const uint8_t* mask, int n_planes, int h, int w, int32_t*
     return 0;
 }
 
+// Host-side check of the kernels' division-by-launch-constant (conv_tc.cuh FastDiv): the quotient the
+// device computes as __umulhi(x, mul) >> shr, evaluated here with the same magic numbers.
+uint32_t unetb200_test_fastdiv(uint32_t d, uint32_t x) {
+    if (d == 0) return 0xffffffffu;
+    const ub::FastDiv f = ub::make_fastdiv(d);
+    if (f.d == 1) return x;
+    return static_cast<uint32_t>((static_cast<uint64_t>(x) * f.mul) >> 32) >> f.shr;
+}
+
 int unetb200_box_sums(const uint8_t* img, int h, int w, int c, const int32_t* boxes_host, int n_boxes,
                       uint64_t* sums_dev, void* stream) {
     return unetb200_box_sums_ps(img, h, w, c, c, boxes_host, n_boxes, sums_dev, stream);
