@@ -205,3 +205,11 @@ def test_fastdiv_magic_numbers(nat):
         for x in xs:
             if 0 <= x < 2 ** 31:
                 assert lib.unetb200_test_fastdiv(d, x) == x // d, (d, x)
+
+
+def test_integration_doc_names_every_symbol():
+    """INTEGRATION.md maps every entry point of include/unetb200.h to the reference code it replaces."""
+    hdr = open(os.path.join(ROOT, "include", "unetb200.h")).read()
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    declared = set(re.findall(r"\b(unetb200_[a-z0-9_]+)\s*\(", hdr))
+    assert not [d for d in sorted(declared) if d not in doc]
