@@ -157,3 +157,37 @@ def test_preprocess_matches_reference_definition():
     assert np.array_equal(t[0].numpy(), ref.transpose(2, 0, 1))
     with pytest.raises(Exception):
         inf.preprocess(np.zeros((4, 4)))     # not a PIL image
+
+
+def test_host_crop_logic_equals_oracle_on_random_masks():
+    """inference.masks_to_crops / boxes_to_crops (host path) against the oracle's restatement of reference
+    inference.py:84-125 on random rectangles, image sizes and near-black content (CPU only)."""
+    import tw_invoice_unet_ocr_llm_b200.inference as inf
+    from oracle.unet_oracle import oracle_crop_boxes
+    rng = np.random.default_rng(17)
+    for trial in range(40):
+        ow, oh = int(rng.integers(20, 2000)), int(rng.integers(20, 1500))
+        frame = rng.integers(0, 256, (oh, ow, 3), dtype=np.uint8)
+        if trial % 4 == 0:
+            frame[:] = rng.integers(0, 6, (oh, ow, 3), dtype=np.uint8)       # means around the `< 3` rejection
+        pil = Image.fromarray(frame)
+        masks, boxes = {}, np.zeros((3, 5), dtype=np.int32)
+        for i, k in enumerate(inf.FIELDS):
+            m = np.zeros((512, 512), dtype=bool)
+            if rng.random() < 0.85:
+                x1, y1 = int(rng.integers(0, 512)), int(rng.integers(0, 512))
+                x2, y2 = int(rng.integers(x1, 512)), int(rng.integers(y1, 512))
+                m[y1:y2 + 1, x1:x2 + 1] = rng.random((y2 - y1 + 1, x2 - x1 + 1)) < 0.5
+                m[y1, x1] = m[y2, x2] = True
+            masks[k] = m
+            ys, xs = np.where(m)
+            boxes[i] = [512, -1, 512, -1, 0] if ys.size == 0 else [xs.min(), xs.max(), ys.min(), ys.max(), ys.size]
+        want = oracle_crop_boxes(masks, ow, oh)
+        for got in (inf.masks_to_crops(pil, masks), inf.boxes_to_crops(pil, boxes)):
+            for k in inf.FIELDS:
+                r = want[k]
+                keep = r is not None and frame[r[1]:r[3], r[0]:r[2]].mean() >= 3
+                assert (got[k] is not None) == keep, (trial, k, r)
+                if keep:
+                    assert got[k].size == (r[2] - r[0], r[3] - r[1])
+                    assert np.array_equal(np.array(got[k]), frame[r[1]:r[3], r[0]:r[2]])
