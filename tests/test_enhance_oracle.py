@@ -149,3 +149,32 @@ def test_c_abi_plan_rejects_bad_crops():
             enhance.plan(sizes, kinds)
     with pytest.raises(ValueError):
         enhance.plan([(4, 4)], ["bogus"])
+
+
+def test_c_abi_plan_windows_of_a_frame():
+    """Crops given as windows of a larger frame (src_stride != 0) keep their src_off, take no room in the
+    packed source buffer, and may use 3- or 4-byte pixels; packed crops are always RGB."""
+    import ctypes as C
+    from tw_invoice_unet_ocr_llm_b200 import _native as nat
+    lib = nat.lib()
+    t = (nat.EnhCrop * 3)()
+    t[0].h, t[0].w, t[0].flags, t[0].clip = 10, 20, 5, 4.0                                   # packed
+    t[1].h, t[1].w, t[1].flags, t[1].clip, t[1].src_stride, t[1].src_pixel_bytes, t[1].src_off = 7, 9, 6, 3.0, 640, 4, 12345 * 4
+    t[2].h, t[2].w, t[2].flags, t[2].clip, t[2].src_stride, t[2].src_off = 5, 5, 1, 4.0, 100, 999   # 3-byte default
+    sb, ob, wb = C.c_uint64(), C.c_uint64(), C.c_uint64()
+    nat.check(lib.unetb200_enhance_plan(t, 3, C.byref(sb), C.byref(ob), C.byref(wb)))
+    assert sb.value == 608                               # only the packed crop: 10*20*3 = 600 -> 16-byte aligned
+    assert (t[0].src_stride, t[0].src_pixel_bytes, t[0].src_off) == (20, 3, 0)
+    assert (t[1].src_stride, t[1].src_pixel_bytes, t[1].src_off) == (640, 4, 12345 * 4)
+    assert (t[2].src_stride, t[2].src_pixel_bytes, t[2].src_off) == (100, 3, 999)
+    assert ob.value == 16 * (200 + 63 + 25)              # 16*h*w is always a multiple of 16
+    for bad in ({"src_stride": 8}, {"src_pixel_bytes": 5}, {"src_pixel_bytes": 4}):      # stride < w, bad size, packed RGBX
+        b = (nat.EnhCrop * 1)()
+        b[0].h, b[0].w, b[0].flags, b[0].clip = 10, 20, 5, 4.0
+        for k, v in bad.items():
+            setattr(b[0], k, v)
+        assert lib.unetb200_enhance_plan(b, 1, C.byref(sb), C.byref(ob), C.byref(wb)) == nat.EINVAL, bad
+    # run() refuses a table that did not go through plan(), without touching the GPU
+    raw = (nat.EnhCrop * 1)()
+    raw[0].h, raw[0].w, raw[0].flags, raw[0].clip = 4, 4, 5, 4.0
+    assert lib.unetb200_enhance_run(raw, C.c_void_p(16), 1, C.c_void_p(16), C.c_void_p(16), C.c_void_p(16), None) == nat.EINVAL
