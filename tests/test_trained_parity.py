@@ -4,66 +4,21 @@ recipe (train.py:18-59 Dice + focal loss, :119-123 AdamW) on synthetic invoices 
 fields, then compares the CUDA forward with the CPU oracle on the trained weights.  Training uses
 plain torch ops (train-mode forward; not the product path) -- it only manufactures a realistic,
 bimodal-logit state_dict in the checkpoint's format."""
-import numpy as np
 import pytest
 import torch
 
 pytestmark = pytest.mark.gpu
 
 
-def _marked_invoices(n, size, seed):
-    """Synthetic invoices with three marked fields and their masks (n,3,size,size)."""
-    from tw_invoice_unet_ocr_llm_b200.synthetic import synthetic_invoices_u8
-    rng = np.random.default_rng(seed)
-    img = synthetic_invoices_u8(n, size, size, seed=seed).astype(np.float32) / 255.0
-    masks = np.zeros((n, 3, size, size), np.float32)
-    s = 1.0            # marks have the same absolute size at every resolution (train at 128, test at 512)
-    for i in range(n):
-        for c in range(3):
-            w, h = int(rng.integers(24, 48) * s), int(rng.integers(8, 14) * s)
-            x, y = int(rng.integers(0, size - w)), int(rng.integers(0, size - h))
-            yy, xx = np.mgrid[0:h, 0:w]
-            if c == 0:
-                patch = np.full((h, w), 0.05)                                  # solid dark bar
-            elif c == 1:
-                patch = 0.5 + 0.45 * (((xx // max(1, int(3 * s))) % 2) * 2 - 1)  # vertical stripes
-            else:
-                patch = 0.5 + 0.45 * ((((xx // max(1, int(4 * s))) + (yy // max(1, int(4 * s)))) % 2) * 2 - 1)  # checker
-            img[i, y:y + h, x:x + w, :] = patch[..., None]
-            masks[i, c, y:y + h, x:x + w] = 1.0
-    x = torch.from_numpy(np.round(img * 255) / 255.0).float().permute(0, 3, 1, 2).contiguous()
-    return x, torch.from_numpy(masks)
-
-
-def _invoice_loss(logits, target):
-    """0.85 * multi-label Dice + 0.15 * focal on sigmoid probabilities (train.py:18-59)."""
-    p = torch.sigmoid(logits)
-    inter = (p * target).sum(dim=(2, 3))
-    dice = 1 - ((2 * inter + 1) / (p.sum(dim=(2, 3)) + target.sum(dim=(2, 3)) + 1)).mean()
-    bce = torch.nn.functional.binary_cross_entropy(p, target, reduction="none")
-    pt = torch.where(target > 0.5, p, 1 - p)
-    focal = (0.25 * (1 - pt) ** 2 * bce).mean()
-    return 0.85 * dice + 0.15 * focal
-
-
 def test_trained_checkpoint_parity(cuda_dev):
     from oracle.unet_oracle import oracle_forward, parity_report
+    from tw_invoice_unet_ocr_llm_b200.synthetic import marked_invoices as _marked_invoices, train_fixture_state
     from tw_invoice_unet_ocr_llm_b200.unet_model import UNet
-    torch.manual_seed(0)
-    model = UNet(3, 3).to(cuda_dev).train()
-    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=1e-4)
-    xs, ms = _marked_invoices(96, 128, seed=300)
-    xs, ms = xs.to(cuda_dev), ms.to(cuda_dev)
-    for step in range(300):
-        idx = torch.randint(0, xs.shape[0], (8,), device=cuda_dev)
-        loss = _invoice_loss(model(xs[idx]), ms[idx])
-        opt.zero_grad(set_to_none=True)
-        loss.backward()
-        opt.step()
-    final_loss = float(loss.detach())
-    model.eval()
-    state = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    state, final_loss = train_fixture_state(cuda_dev, steps=300, seed=0)
     assert len(state) == 136
+    model = UNet(3, 3)
+    model.load_state_dict(state)
+    model = model.to(cuda_dev).eval()
 
     x, gt = _marked_invoices(3, 512, seed=301)           # held-out, at inference.py's native 512x512
     with torch.no_grad():

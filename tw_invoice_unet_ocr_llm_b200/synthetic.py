@@ -108,3 +108,66 @@ def synthetic_crops_u8(sizes, seed: int = 11) -> list:
         page = synthetic_invoices_u8(1, max(64, 2 * h), max(64, 2 * w), seed=seed + i)[0]
         out.append(np.ascontiguousarray(page[:h, :w]))
     return out
+
+
+def marked_invoices(n: int, size: int, seed: int):
+    """Synthetic invoices with three marked fields (solid bar / stripes / checker = the three classes) and their
+    masks: (float32 [n,3,size,size] with values k/255, float32 masks [n,3,size,size]).  Marks have the same
+    absolute size at every resolution, so a model trained at 128x128 segments them at 512x512."""
+    rng = np.random.default_rng(seed)
+    img = synthetic_invoices_u8(n, size, size, seed=seed).astype(np.float32) / 255.0
+    masks = np.zeros((n, 3, size, size), np.float32)
+    for i in range(n):
+        for c in range(3):
+            w, h = int(rng.integers(24, 48)), int(rng.integers(8, 14))
+            x, y = int(rng.integers(0, size - w)), int(rng.integers(0, size - h))
+            yy, xx = np.mgrid[0:h, 0:w]
+            if c == 0:
+                patch = np.full((h, w), 0.05)                                  # solid dark bar
+            elif c == 1:
+                patch = 0.5 + 0.45 * (((xx // 3) % 2) * 2 - 1)                 # vertical stripes
+            else:
+                patch = 0.5 + 0.45 * ((((xx // 4) + (yy // 4)) % 2) * 2 - 1)   # checker
+            img[i, y:y + h, x:x + w, :] = patch[..., None]
+            masks[i, c, y:y + h, x:x + w] = 1.0
+    x = torch.from_numpy(np.round(img * 255) / 255.0).float().permute(0, 3, 1, 2).contiguous()
+    return x, torch.from_numpy(masks)
+
+
+def invoice_loss(logits: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+    """0.85 * multi-label Dice + 0.15 * focal on sigmoid probabilities (the reference's recipe, train.py:18-59)."""
+    p = torch.sigmoid(logits)
+    inter = (p * target).sum(dim=(2, 3))
+    dice = 1 - ((2 * inter + 1) / (p.sum(dim=(2, 3)) + target.sum(dim=(2, 3)) + 1)).mean()
+    bce = torch.nn.functional.binary_cross_entropy(p, target, reduction="none")
+    pt = torch.where(target > 0.5, p, 1 - p)
+    focal = (0.25 * (1 - pt) ** 2 * bce).mean()
+    return 0.85 * dice + 0.15 * focal
+
+
+def train_fixture_state(device, steps: int = 300, seed: int = 0, model_cls=None):
+    """A TRAINED stand-in for ``checkpoints/best_unet_model.pth`` (the real file is a Git-LFS pointer): the
+    UNet trained for ``steps`` AdamW steps (train.py:119-123) with ``invoice_loss`` on ``marked_invoices``.
+    Plain torch train-mode ops -- this manufactures realistic weights (trained BatchNorm statistics, bimodal
+    logits), it is not the product path.  Returns ``(state_dict on CPU, final loss)``."""
+    if model_cls is None:
+        from .unet_model import UNet as model_cls
+    gen_state = torch.random.get_rng_state()
+    try:
+        torch.manual_seed(seed)
+        model = model_cls(3, 3).to(device).train()
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=1e-4)
+        xs, ms = marked_invoices(96, 128, seed=300)
+        xs, ms = xs.to(device), ms.to(device)
+        loss = None
+        for _ in range(steps):
+            idx = torch.randint(0, xs.shape[0], (8,), device=device)
+            loss = invoice_loss(model(xs[idx]), ms[idx])
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            opt.step()
+        model.eval()
+        state = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    finally:
+        torch.random.set_rng_state(gen_state)
+    return state, (float(loss.detach()) if loss is not None else float("nan"))
