@@ -213,3 +213,19 @@ def test_integration_doc_names_every_symbol():
     doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
     declared = set(re.findall(r"\b(unetb200_[a-z0-9_]+)\s*\(", hdr))
     assert not [d for d in sorted(declared) if d not in doc]
+
+
+def test_trained_fixture_generator_produces_the_checkpoint_format():
+    """synthetic.train_fixture_state (tools/make_fixture_checkpoint.py --trained): two steps on the CPU give a
+    state_dict in the checkpoint's exact format (136 keys, fp32 + int64 counters) that loads strictly."""
+    from tw_invoice_unet_ocr_llm_b200.synthetic import invoice_loss, marked_invoices, train_fixture_state
+    from tw_invoice_unet_ocr_llm_b200.unet_model import UNet
+    x, m = marked_invoices(2, 64, seed=5)
+    assert x.shape == (2, 3, 64, 64) and m.shape == (2, 3, 64, 64) and set(m.unique().tolist()) <= {0.0, 1.0}
+    assert torch.equal(x, torch.round(x * 255) / 255)                  # values k/255, like preprocess output
+    assert 0.0 < float(invoice_loss(torch.zeros(2, 3, 64, 64), m)) < 2.0
+    state, loss = train_fixture_state("cpu", steps=2)
+    assert len(state) == 136 and loss == loss
+    res = UNet().load_state_dict(state, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    assert all(v.dtype in (torch.float32, torch.int64) for v in state.values())
