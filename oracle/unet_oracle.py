@@ -23,8 +23,8 @@ Pinning: the reference ships no tests or golden vectors.  
 oracle is pinned instead against outputs of the reference itself, executed in the build
 container from /root/reference by ``tests/golden/make_golden.py``; the resulting
 vectors are committed under ``tests/golden/`` and checked by
-``tests/test_oracle_golden.py`` (and, where /root/reference exists, live against the
-imported reference modules by ``tests/test_oracle_vs_reference.py``).
+``tests/test_oracle_golden.py`` (which also compares live against the imported reference
+modules where /root/reference exists, i.e. in the build container).
 """
 from __future__ import annotations
 
