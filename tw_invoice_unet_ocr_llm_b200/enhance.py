@@ -30,6 +30,7 @@ KINDS = {
     "date": (BLUR | OTSU, 3.0),
 }
 
+
 def _pinned(nbytes: int) -> torch.Tensor:
     """Pinned host buffer from torch's caching host allocator: a block is recycled only after every
     tensor / numpy view of it is gone and the copies queued on it have completed, so results can be
