@@ -109,3 +109,31 @@ def test_gather_masks_gloo_world2(total):
         assert p.exitcode == 0
     assert full.shape == (total, 3, 4, 4)
     assert np.array_equal(full[:, 0, 0, 0], np.arange(total, dtype=np.uint8))
+
+
+def test_multi_gpu_segmenter_returns_boxes_in_order():
+    """return_boxes=True: every shard writes its per-field extents next to its masks, input order kept."""
+    class BoxWorker(FakeWorker):
+        def segment(self, frames, out, boxes_out=None):
+            super().segment(frames, out)
+            if boxes_out is not None:
+                tag = frames.to(torch.int32).sum(dim=(1, 2, 3)) % 1000
+                boxes_out.copy_(tag[:, None, None].expand_as(boxes_out).to(torch.int32))
+    rng = np.random.default_rng(3)
+    frames = rng.integers(0, 256, (11, 8, 8, 3), dtype=np.uint8)
+    seg = MultiGpuSegmenter(None, devices=list(range(4)), worker_factory=BoxWorker)
+    masks, boxes = seg.segment(frames, return_boxes=True)
+    assert masks.shape == (11, 3, 8, 8) and boxes.shape == (11, 3, 5) and boxes.dtype == torch.int32
+    assert np.array_equal(boxes[:, 0, 0].numpy(), frames.astype(np.int64).sum(axis=(1, 2, 3)) % 1000)
+    assert torch.equal(masks, seg.segment(frames))
+
+
+def test_bind_to_gpu_numa_is_harmless_without_nvml():
+    """No NVML / no GPU / one NUMA node: nothing changes and the call reports None."""
+    from tw_invoice_unet_ocr_llm_b200.launcher import bind_to_gpu_numa
+    before = os.sched_getaffinity(0)
+    res = bind_to_gpu_numa(0)
+    after = os.sched_getaffinity(0)
+    assert res is None or set(res) == after
+    if res is None:
+        assert before == after
