@@ -343,7 +343,9 @@ def main():
             tc_flops += fl
             tc_ms += ms
             tc_bytes += by
-        table.append({"layer": l.name.decode(), "kernel": "conv_tc_kernel (tcgen05)" if tensor else "stem_conv_kernel",
+        table.append({"layer": l.name.decode(), "kernel": "conv_tc_kernel (tcgen05)" if tensor else
+                      ("conv_tc_kernel<A_STEM> (tcgen05, in-kernel im2col; HBM / issue bound)"
+                       if eng.get_option("stem_tc") else "stem_conv_kernel (CUDA cores)"),
                       "ms": round(ms, 4), "gflop": round(fl / 1e9, 2), "tflops": round(tf, 1),
                       "algorithmic_gb": round(by / 1e9, 3), "gb_per_s": round(by / 1e9 / (ms * 1e-3), 1) if ms > 0 else 0.0,
                       "frac_of_peak": round(tf / peaks["tflops"], 3)})
