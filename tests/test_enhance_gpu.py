@@ -155,3 +155,34 @@ def test_windows_of_a_device_frame_equal_packed_crops(cuda_dev):
     with pytest.raises(ValueError):
         enhance.enhance_windows(torch.from_numpy(frame).to(cuda_dev), [(0, 0, 641, 10)], ["text"])
     assert enhance.enhance_windows(torch.from_numpy(frame).to(cuda_dev), [], []) == []
+
+
+def test_concurrent_threads(cuda_dev):
+    """Streamlit runs every session in its own thread: concurrent enhance_batch / enhance_for_* calls (shared
+    library state: none; pinned blocks from torch's caching host allocator) give the single-threaded results."""
+    import threading
+    from tw_invoice_unet_ocr_llm_b200 import enhance
+    sizes = [(20 + 3 * i, 60 + 7 * i) for i in range(6)]
+    crops = synthetic_crops_u8(sizes, seed=91)
+    kinds = [("text", "date", "amount")[i % 3] for i in range(len(crops))]
+    want = [_oracle(c, k) for c, k in zip(crops, kinds)]
+    errors = []
+
+    def work(tid):
+        try:
+            for rep in range(6):
+                order = list(range(len(crops)))[tid % 3:] + list(range(len(crops)))[:tid % 3]
+                got = enhance.enhance_batch([crops[i] for i in order], [kinds[i] for i in order])
+                for g, i in zip(got, order):
+                    assert np.array_equal(g, want[i]), (tid, rep, i)
+                one = enhance.enhance_for_date_ocr(Image.fromarray(crops[tid % len(crops)]))
+                assert np.array_equal(np.array(one), oe.enhance_for_date_ocr(crops[tid % len(crops)]))
+        except BaseException as e:      # surfaced below
+            errors.append(e)
+
+    threads = [threading.Thread(target=work, args=(t,)) for t in range(6)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors[0]
