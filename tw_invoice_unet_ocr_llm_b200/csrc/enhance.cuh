@@ -272,7 +272,7 @@ enh_resize_kernel(const unetb200_enh_crop* __restrict__ tab, int n, int total_bl
 __global__ void __launch_bounds__(kEnhThreads)
 enh_lut_kernel(const unetb200_enh_crop* __restrict__ tab, uint8_t* __restrict__ ws) {
     constexpr int kWarps = kEnhThreads / 32;
-    __shared__ int wh[kWarps][256];              // one histogram per warp
+    __shared__ int wh[kWarps][256];              // one histogram per warp (1, 2 or 4 shared ones measured the same: 81 us)
     __shared__ int warp_sum[kWarps];
     const unetb200_enh_crop c = tab[blockIdx.x / (kEnhTiles * kEnhTiles)];
     const int tile = blockIdx.x % (kEnhTiles * kEnhTiles);
