@@ -109,6 +109,14 @@ int unetb200_forward(unetb200_handle_t h, const void* x, int x_fmt, int n, int h
                      void* workspace, uint64_t workspace_bytes, float* logits, uint8_t* mask,
                      const float* logit_thr, void* stream);
 
+/* Same forward with the masks bit-packed: mask_bits uint8 [N, n_classes, H, W/8], bit (x & 7) (LSB first) of
+ * byte x >> 3 of a row is pixel x (numpy: np.unpackbits(bits, axis=-1, bitorder="little")).  The reference keeps
+ * one boolean per pixel (inference.py:75-79); this is the same information in an eighth of the bytes, for
+ * callers that move masks across PCIe (launcher.GpuWorker). */
+int unetb200_forward_bits(unetb200_handle_t h, const void* x, int x_fmt, int n, int height, int width,
+                          void* workspace, uint64_t workspace_bytes, float* logits, uint8_t* mask_bits,
+                          const float* logit_thr, void* stream);
+
 /* Per-layer device times (ms) of the last forward run with option "profile" = 1.
  * Synchronises the stream's events.  `ms` has room for `count` floats. */
 int unetb200_layer_times(unetb200_handle_t h, float* ms, int count);
@@ -125,7 +133,8 @@ int unetb200_last_launch_count(unetb200_handle_t h);
 int unetb200_conv3x3(const void* src0, int c0, const void* src1, int c1, const void* w_packed,
                      const float* bias, int n, int height, int width, int cout, int relu, void* out,
                      void* pool_out, int bn, int amode, int wstat, void* stream);
-/* 3x3 conv (cout = 64) + ReLU with the 1x1 head and threshold fused into the epilogue. */
+/* 3x3 conv (cout = 64) + ReLU with the 1x1 head and threshold fused into the epilogue.  `wstat` as above;
+ * bit 2 makes `mask` the bit-packed [N, n_classes, H, W/8] format of unetb200_forward_bits. */
 int unetb200_conv3x3_head(const void* src0, int c0, const void* w_packed, const float* bias,
                           const float* head_w, const float* head_b, int n_classes, int n, int height,
                           int width, float* logits, uint8_t* mask, const float* logit_thr, int amode,
@@ -171,6 +180,8 @@ int unetb200_resize_bicubic_u8_ps(const uint8_t* src, int n, int h, int w, int c
 /* np.where(mask) min/max of inference.py:85-93: mask uint8 [n_planes,h,w] ->
  * out int32 [n_planes,5] = {xmin, xmax, ymin, ymax, count}; an empty plane gives {w, -1, h, -1, 0}. */
 int unetb200_mask_bbox(const uint8_t* mask, int n_planes, int h, int w, int32_t* out, void* stream);
+/* Same reduction over bit-packed planes (unetb200_forward_bits): bits uint8 [n_planes, h, w/8], w % 32 == 0. */
+int unetb200_mask_bbox_bits(const uint8_t* bits, int n_planes, int h, int w, int32_t* out, void* stream);
 /* Byte sums of n_boxes (<= 16) rectangles {x1, y1, x2, y2} (half-open, host array of 4*n_boxes ints) of one
  * uint8 [h][w][c] device frame -> sums_dev uint64 [n_boxes] (zeroed here): the `np.array(crop).mean() < 3`
  * rejection of inference.py:121-125 as the exact integer test sum < 3 * (x2-x1)*(y2-y1)*c. */

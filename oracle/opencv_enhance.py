@@ -2,7 +2,8 @@
 
 Restates, in numpy, what the reference's ``enhance_for_ocrspace`` (app_camera.py:572-598) and
 ``enhance_for_date_ocr`` (app_camera.py:685-705) compute.  The reference delegates every step to
-OpenCV (third-party, ``opencv-python-headless`` unpinned in requirements.txt; 4.13.0 in this image),
+OpenCV (third-party, pinned ``opencv-python-headless==4.8.1.78`` in the reference's requirements.txt:4,
+absent from /root/reference; this image has 4.13.0),
 so each function below restates the published OpenCV algorithm for 8-bit single-channel images:
 
 =====================  ==========================================  ===============================
@@ -22,7 +23,9 @@ Pinning (tests/test_enhance_oracle.py): every function is compared bit for bit w
 in the test process; ``resize_cubic_x4`` and the two chains are compared with OpenCV's own code path
 (``OPENCV_IPP=disabled``; the wheel in this image otherwise routes ``cv2.resize`` through Intel IPP,
 whose cubic differs from OpenCV's by +-1 on ~5 ppm of the pixels), against golden vectors generated
-by ``tests/golden/make_golden_enhance.py``.
+by ``tests/golden/make_golden_enhance.py``.  Parity with the reference's pinned stock wheel (IPP enabled) is
+therefore NOT bit-exact: ``test_final_images_against_stock_ipp_opencv_are_bounded`` bounds the difference
+of the final (post-CLAHE / post-Otsu) images.
 
 Nothing in the product path imports this module.
 """

@@ -11,6 +11,9 @@ import pytest
 from oracle import opencv_enhance as oe
 from tw_invoice_unet_ocr_llm_b200.synthetic import synthetic_crops_u8
 
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from enhance_common import IPP_BOUNDS, stock_cv2_chain as _stock_cv2_chain  # noqa: E402
+
 HERE = os.path.dirname(os.path.abspath(__file__))
 GOLD = np.load(os.path.join(HERE, "golden", "golden_enhance.npz"))
 
@@ -114,6 +117,27 @@ def test_resize_against_installed_opencv_is_within_one():
         bad += int((d != 0).sum())
         tot += d.size
     assert bad <= 1e-4 * tot
+
+
+def test_final_images_against_stock_ipp_opencv_are_bounded():
+    """app_camera.py:572-598 / 685-705 run with the installed (IPP-enabled) cv2 against the oracle chain:
+    the post-CLAHE / post-Otsu disagreement stays inside IPP_BOUNDS.  With OPENCV_IPP=disabled it is zero
+    (test_golden_chains, test_resize_against_opencv_native_path)."""
+    _cv2()
+    rng = np.random.default_rng(5)
+    sizes = [(int(rng.integers(8, 72)), int(rng.integers(20, 320))) for _ in range(24)]
+    crops = synthetic_crops_u8(sizes, seed=77)
+    for kind, (overall, worst, maxdiff) in IPP_BOUNDS.items():
+        bad = tot = 0
+        for c in crops:
+            want = _stock_cv2_chain(c, kind)
+            got = oe.enhance_for_date_ocr(c) if kind == "date" else oe.enhance_for_ocrspace(c, kind)
+            d = np.abs(want.astype(int) - got.astype(int))
+            assert d.max() <= maxdiff, (kind, c.shape, int(d.max()))
+            assert (d != 0).mean() <= worst, (kind, c.shape, float((d != 0).mean()))
+            bad += int((d != 0).sum())
+            tot += d.size
+        assert bad <= overall * tot, (kind, bad, tot)
 
 
 def test_c_abi_plan_matches_oracle_geometry():

@@ -3,8 +3,10 @@ C ABI, against the CPU fp32 oracle on the same seeded inputs.
 
 Stated tolerance (north_star: "logit max-abs/rel error, >= 99.9 % pixel agreement plus mask
 IoU"), for bf16 storage / fp32 accumulation through 23 layers:
-  * logit max-abs error  <= 0.35   and  max-abs / std(logits) <= 0.25
-  * logit mean-abs error <= 0.04
+  * logit max-abs error  <= 0.25   and  max-abs / std(logits) <= 0.19
+  * logit mean-abs error <= 0.025
+    (about 1.4x what the B200 measures on the calibrated fixture -- 0.07-0.18 / 0.05-0.13 / 0.012-0.019,
+    profiles/r01_parity.txt -- so that a numerics regression is caught, not absorbed)
   * binarised-mask pixel agreement >= 99.9 % at 512x512 (>= 99.7 % on tiny inputs, where a
     handful of near-threshold pixels is already 0.1 %)
   * every pixel with |logit - threshold| > 0.25 agrees
@@ -30,9 +32,9 @@ def model(fixture_state, cuda_dev):
 
 
 def _check(rep, min_agree):
-    assert rep["max_abs"] <= 0.35, rep
-    assert rep["max_abs_over_std"] <= 0.25, rep
-    assert rep["mean_abs"] <= 0.04, rep
+    assert rep["max_abs"] <= 0.25, rep
+    assert rep["max_abs_over_std"] <= 0.19, rep
+    assert rep["mean_abs"] <= 0.025, rep
     assert rep["agreement"] >= min_agree, rep
     assert rep["agreement_outside_0.25"] == 1.0, rep
     assert min(rep["iou"]) >= 0.95, rep
@@ -78,11 +80,25 @@ def test_logits_1024_nonsquare(model, fixture_state, cuda_dev):
     _check(rep, 0.999)
 
 
-def test_batch64_properties(model, cuda_dev):
-    """BASELINE.json configs[1] at full size (64 x 3 x 512 x 512), through size-independent
-    properties: eight distinct frames tiled 8x must give eight identical groups of logits (images
-    are independent and every tile/CTA assignment must produce the same bits), and the masks must
-    equal logits > threshold."""
+def test_logits_1024_square_batch(model, fixture_state, cuda_dev):
+    """BASELINE.json configs[3] as named (1024 x 1024), two images of the batch-16 bench shape against the
+    oracle (2 x 1.5 TFLOP on the host cores: a few seconds)."""
+    from oracle.unet_oracle import oracle_forward, parity_report
+    from tw_invoice_unet_ocr_llm_b200.synthetic import synthetic_invoices
+    x = synthetic_invoices(2, 1024, 1024, seed=54)
+    with torch.no_grad():
+        z = model(x.to(cuda_dev))
+    rep = parity_report(oracle_forward(fixture_state, x), z)
+    print(f"parity 2x1024x1024: {rep}")
+    _check(rep, 0.999)
+
+
+def test_batch64_properties(model, fixture_state, cuda_dev):
+    """BASELINE.json configs[1] at full size (64 x 3 x 512 x 512): the first eight images of the batch-64
+    run against the oracle (the stated tolerance), and through size-independent properties: eight distinct
+    frames tiled 8x must give eight identical groups of logits (images are independent and every tile/CTA
+    assignment must produce the same bits), and the masks must equal logits > threshold."""
+    from oracle.unet_oracle import oracle_forward, parity_report
     from tw_invoice_unet_ocr_llm_b200.synthetic import synthetic_invoices
     base = synthetic_invoices(8, 512, 512, seed=52)
     x = torch.cat([base] * 8).to(cuda_dev)
@@ -97,6 +113,9 @@ def test_batch64_properties(model, cuda_dev):
     t = torch.tensor(logit_thresholds(thr), dtype=torch.float32, device=cuda_dev).view(1, 3, 1, 1)
     assert torch.equal(m, (z > t).to(torch.uint8))
     assert torch.isfinite(z).all()
+    rep = parity_report(oracle_forward(fixture_state, base), z[:8])
+    print(f"parity 8x512x512 inside the batch-64 forward: {rep}")
+    _check(rep, 0.999)
 
 
 @pytest.mark.parametrize("amode", [int(v) for v in os.environ.get("UNETB200_TEST_AMODES", "0,1,2").split(",")])

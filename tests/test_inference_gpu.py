@@ -209,6 +209,62 @@ def test_launcher_single_gpu_matches_engine(fixture_state, cuda_dev):
     assert torch.equal(out, m.cpu())
 
 
+def test_packed_masks_equal_byte_masks(fixture_state, cuda_dev):
+    """unetb200_forward_bits: one bit per pixel, LSB first == the uint8 masks of unetb200_forward, through the
+    engine (odd tile counts, partial tiles) and through a packed launcher worker with boxes."""
+    from tw_invoice_unet_ocr_llm_b200.engine import Engine, unpack_mask_bits
+    from tw_invoice_unet_ocr_llm_b200.launcher import MultiGpuSegmenter
+    from tw_invoice_unet_ocr_llm_b200.synthetic import synthetic_invoices_u8
+    eng = Engine(fixture_state, cuda_dev)
+    thr = [0.25, 0.40, 0.30]
+    for n, h, w, seed in ((3, 48, 80, 90), (2, 128, 160, 91), (1, 512, 512, 92)):
+        x = torch.from_numpy(synthetic_invoices_u8(n, h, w, seed=seed)).to(cuda_dev)
+        z, m = eng.run(x, thresholds=thr)
+        z2, b = eng.run(x, thresholds=thr, mask_bits=True)
+        torch.cuda.synchronize()
+        assert b.shape == (n, 3, h, w // 8) and b.dtype == torch.uint8
+        assert torch.equal(z, z2)
+        assert torch.equal(unpack_mask_bits(b), m)
+        assert np.array_equal(unpack_mask_bits(b.cpu().numpy()), m.cpu().numpy())
+    frames = synthetic_invoices_u8(7, 128, 160, seed=84)
+    plain = MultiGpuSegmenter(fixture_state, devices=["cuda:0"], chunk=3)
+    packed = MultiGpuSegmenter(fixture_state, devices=["cuda:0"], chunk=3, packed=True)
+    m0, b0 = plain.segment(frames, return_boxes=True)
+    m1, b1 = packed.segment(frames, return_boxes=True)
+    assert m1.shape == (7, 3, 128, 20)
+    assert torch.equal(unpack_mask_bits(m1), m0) and torch.equal(b0, b1)
+
+
+def test_engine_streams_do_not_share_scratch(fixture_state, cuda_dev):
+    """Forwards enqueued from two CUDA streams may overlap on the device: each stream gets its own workspace,
+    so concurrent forwards of different inputs give the answers of the serial runs."""
+    from tw_invoice_unet_ocr_llm_b200.engine import Engine
+    from tw_invoice_unet_ocr_llm_b200.synthetic import synthetic_invoices_u8
+    eng = Engine(fixture_state, cuda_dev)
+    xs = [torch.from_numpy(synthetic_invoices_u8(4, 256, 256, seed=95 + i)).to(cuda_dev) for i in range(2)]
+    want = []
+    for x in xs:
+        z, _ = eng.run(x)
+        torch.cuda.synchronize()
+        want.append(z.clone())
+    streams = [torch.cuda.Stream(cuda_dev) for _ in range(2)]
+    for rep in range(3):
+        got = []
+        for x, st in zip(xs, streams):
+            st.wait_stream(torch.cuda.current_stream(cuda_dev))
+            with torch.cuda.stream(st):
+                got.append(eng.run(x)[0])
+        torch.cuda.synchronize()
+        for g, w_ in zip(got, want):
+            assert torch.equal(g, w_)
+    assert len(eng._ws) >= 2
+    with pytest.raises(RuntimeError):
+        eng.run(xs[0], logits_out=torch.empty((4, 3, 256, 128), device=cuda_dev))       # wrong shape
+    with pytest.raises(RuntimeError):
+        eng.run(xs[0], thresholds=[0.25, 0.4, 0.3],
+                mask_out=torch.empty((4, 3, 256, 512), dtype=torch.uint8, device=cuda_dev)[..., ::2])   # not contiguous
+
+
 def test_concurrent_run_unet_threads(checkpoint, cuda_dev):
     """Streamlit runs each session in its own thread of one process and they share the cached model
     (SURVEY.md 8b "Threading"): concurrent run_unet calls must give the single-threaded answers."""

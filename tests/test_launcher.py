@@ -8,7 +8,7 @@ import pytest
 import torch
 import torch.multiprocessing as mp
 
-from tw_invoice_unet_ocr_llm_b200.launcher import (MultiGpuSegmenter, chunk_bounds, gather_masks,
+from tw_invoice_unet_ocr_llm_b200.launcher import (HostGather, MultiGpuSegmenter, chunk_bounds, gather_masks,
                                                    shard_bounds)
 
 
@@ -68,6 +68,46 @@ def test_worker_error_propagates():
         seg.segment(np.zeros((4, 16, 16, 3), dtype=np.uint8))
 
 
+def test_failed_worker_shard_is_requeued_on_survivors():
+    """SURVEY section 5 (failure handling): a worker that raises loses nothing -- its shard is split over the
+    workers that succeeded; the output is complete, in order, and the failure is counted."""
+    class Flaky(FakeWorker):
+        def segment(self, frames, out):
+            if self.dev == 1:
+                raise RuntimeError("device 1 lost")
+            super().segment(frames, out)
+    rng = np.random.default_rng(8)
+    frames = rng.integers(0, 256, (13, 16, 16, 3), dtype=np.uint8)
+    seg = MultiGpuSegmenter(None, devices=[0, 1, 2], worker_factory=Flaky)
+    out = seg.segment(frames)
+    expect = (frames.astype(np.int64).sum(axis=(1, 2)) % 251).astype(np.uint8)
+    assert np.array_equal(out[:, :, 0, 0].numpy(), expect)
+    assert seg.failures == [0, 1, 0]
+    assert sum(sum(w.seen) for w in seg.workers) == 13           # every frame segmented exactly once
+    assert seg.workers[1].seen == []
+
+
+def test_packed_segmenter_allocates_bit_planes():
+    class PackedFake:
+        def __init__(self, dev):
+            self.dev = dev
+
+        def segment(self, frames, out):
+            out.fill_(0xA5)
+    seg = MultiGpuSegmenter(None, devices=[0, 1], worker_factory=PackedFake, packed=True)
+    out = seg.segment(np.zeros((5, 16, 32, 3), dtype=np.uint8))
+    assert out.shape == (5, 3, 16, 4) and bool((out == 0xA5).all())
+
+
+def test_unpack_mask_bits_matches_numpy():
+    from tw_invoice_unet_ocr_llm_b200.engine import unpack_mask_bits
+    rng = np.random.default_rng(4)
+    planes = rng.integers(0, 2, (2, 3, 8, 32), dtype=np.uint8)
+    bits = np.packbits(planes, axis=-1, bitorder="little")
+    assert np.array_equal(unpack_mask_bits(bits), planes)
+    assert torch.equal(unpack_mask_bits(torch.from_numpy(bits)), torch.from_numpy(planes))
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -91,6 +131,42 @@ def _gloo_rank(rank, world, port, total, q):
             assert full is None
     finally:
         dist.destroy_process_group()
+
+
+def _gloo_rank_shm(rank, world, port, total, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        hg = HostGather(total, (3, 4, 2), pin=False)
+        lo, hi = shard_bounds(total, world, rank)
+        assert hg.local().shape == (hi - lo, 3, 4, 2)
+        hg.local().copy_(torch.arange(lo, hi, dtype=torch.uint8).view(-1, 1, 1, 1).expand(-1, 3, 4, 2))
+        hg.wait()
+        if rank == 0:
+            q.put(hg.full().numpy().copy())
+        hg.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("total", [7, 8])
+def test_host_gather_shared_block_gloo_world2(total):
+    """HostGather: every rank writes its shard into one shared host block in place (the device->host copy
+    target of bench.py's sharded run); rank 0 reads the whole batch in input order."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gloo_rank_shm, args=(r, 2, port, total, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    full = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert full.shape == (total, 3, 4, 2)
+    assert np.array_equal(full[:, 0, 0, 0], np.arange(total, dtype=np.uint8))
 
 
 @pytest.mark.parametrize("total", [7, 8])

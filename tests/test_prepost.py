@@ -83,6 +83,24 @@ def test_gpu_mask_bbox_bit_exact(cuda_dev):
 
 
 @pytest.mark.gpu
+def test_gpu_mask_bbox_bits_equals_byte_masks(cuda_dev):
+    """The reduction over bit-packed planes (unetb200_forward_bits output) == the one over byte planes."""
+    from tw_invoice_unet_ocr_llm_b200 import prepost
+    rng = np.random.default_rng(19)
+    m = np.zeros((2, 3, 128, 160), np.uint8)
+    m[0, 0, 10:30, 33:97] = 1
+    m[0, 1] = rng.random((128, 160)) < 0.002
+    m[0, 2, 127, 159] = 1
+    m[1, 0, 0, 0] = 1
+    m[1, 1] = 1
+    bits = np.packbits(m, axis=-1, bitorder="little")
+    got = prepost.mask_bbox_bits(torch.from_numpy(bits).to(cuda_dev)).cpu()
+    want = prepost.mask_bbox(torch.from_numpy(m).to(cuda_dev)).cpu()
+    assert torch.equal(got, want)
+    assert list(got[1, 2]) == [160, -1, 128, -1, 0]
+
+
+@pytest.mark.gpu
 def test_gpu_box_sums_exact(cuda_dev):
     """unetb200_box_sums == numpy sums of the same rectangles (unaligned starts, 1-pixel boxes, the
     whole frame), for 3- and 4-channel frames."""

@@ -65,6 +65,7 @@ SYMBOLS = {
     "unetb200_get_option": (_I, [_VP, C.c_char_p, C.POINTER(_I)]),
     "unetb200_workspace_bytes": (_U64, [_VP, _I, _I, _I]),
     "unetb200_forward": (_I, [_VP, _VP, _I, _I, _I, _I, _VP, _U64, _VP, _VP, C.POINTER(_F), _VP]),
+    "unetb200_forward_bits": (_I, [_VP, _VP, _I, _I, _I, _I, _VP, _U64, _VP, _VP, C.POINTER(_F), _VP]),
     "unetb200_layer_times": (_I, [_VP, C.POINTER(_F), _I]),
     "unetb200_last_launch_count": (_I, [_VP]),
     "unetb200_conv3x3": (_I, [_VP, _I, _VP, _I, _VP, _VP, _I, _I, _I, _I, _I, _VP, _VP, _I, _I, _I, _VP]),
@@ -81,6 +82,7 @@ SYMBOLS = {
     "unetb200_resize_bicubic_u8": (_I, [_VP, _I, _I, _I, _I, _VP, _VP, _I, _VP, _VP, _I, _VP, _VP, _I, _I, _VP]),
     "unetb200_resize_bicubic_u8_ps": (_I, [_VP, _I, _I, _I, _I, _I, _VP, _VP, _I, _VP, _VP, _I, _VP, _VP, _I, _I, _VP]),
     "unetb200_mask_bbox": (_I, [_VP, _I, _I, _I, _VP, _VP]),
+    "unetb200_mask_bbox_bits": (_I, [_VP, _I, _I, _I, _VP, _VP]),
     "unetb200_box_sums": (_I, [_VP, _I, _I, _I, C.POINTER(C.c_int32), _I, _VP, _VP]),
     "unetb200_box_sums_ps": (_I, [_VP, _I, _I, _I, _I, C.POINTER(C.c_int32), _I, _VP, _VP]),
     "unetb200_test_fastdiv": (C.c_uint32, [C.c_uint32, C.c_uint32]),

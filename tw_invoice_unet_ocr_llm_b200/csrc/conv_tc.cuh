@@ -108,7 +108,8 @@ struct ConvParams {
     const float* head_w;     // [ncls][64] fp32      (EPI_HEAD)
     const float* head_b;     // [ncls]               (EPI_HEAD)
     float* logits;           // [N][ncls][H][W] fp32 (EPI_HEAD, nullable)
-    uint8_t* mask;           // [N][ncls][H][W] u8   (EPI_HEAD, nullable)
+    uint8_t* mask;           // [N][ncls][H][W] u8, or [N][ncls][H][W/8] bits when mask_bits (EPI_HEAD, nullable)
+    int mask_bits;           // 1 = one bit per pixel: bit (x & 7) of byte x >> 3 of each row, LSB first
     float thr[kMaxClasses];  // logit-space thresholds
     int* dbg;                // watchdog record (nullable)
     int C0, C1;              // channels of source 0 / 1 (multiples of 64; C1 may be 0)
@@ -759,14 +760,28 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
                 __syncwarp();
                 if (lane == 0) release_acc(acc);
                 const int y = y0 + (row >> 3), x = x0 + (row & 7);
-                if (valid && y < p.H && x < p.W) {
+                const bool inside = valid && y < p.H && x < p.W;
+                if (inside) {
 #pragma unroll
                     for (int c = 0; c < NC; ++c) {
                         if (c < p.ncls) {
                             const size_t o = ((static_cast<size_t>(n) * p.ncls + c) * p.H + y) * p.W + x;
                             if (p.logits) p.logits[o] = z[c];
-                            if (p.mask) p.mask[o] = z[c] > p.thr[c] ? 1 : 0;
+                            if (p.mask && !p.mask_bits) p.mask[o] = z[c] > p.thr[c] ? 1 : 0;
                         }
+                    }
+                }
+                if (p.mask && p.mask_bits) {
+                    // one bit per pixel (inference.py:75-79 keeps a boolean per pixel): the warp's 32 pixels are
+                    // 4 tile rows x 8 columns, x0 is a multiple of 8 and W of 16, so byte r of the ballot is
+                    // exactly byte x0 / 8 of image row y0 + 4q + r.  Lanes 0..3 store one byte each.
+#pragma unroll
+                    for (int c = 0; c < NC; ++c) {
+                        const uint32_t bits = __ballot_sync(0xffffffffu, inside && z[c] > p.thr[c]);
+                        const int yr = y0 + 4 * q + lane;
+                        if (c < p.ncls && lane < 4 && valid && yr < p.H && x0 < p.W)
+                            p.mask[((static_cast<size_t>(n) * p.ncls + c) * p.H + yr) * (p.W >> 3) + (x0 >> 3)] =
+                                static_cast<uint8_t>(bits >> (8 * lane));
                     }
                 }
             }

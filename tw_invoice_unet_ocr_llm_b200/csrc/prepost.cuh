@@ -121,6 +121,45 @@ __global__ void __launch_bounds__(256) mask_bbox_kernel(const uint8_t* __restric
     }
 }
 
+// Same reduction over bit-packed planes [h][w/8] (bit x & 7 of byte x >> 3 = pixel x; w % 32 == 0): one 32-pixel
+// word per thread and step, extents from ffs / clz, count from popc.
+__global__ void __launch_bounds__(256) mask_bbox_bits_kernel(const uint8_t* __restrict__ bits, int h, int w,
+                                                             int32_t* __restrict__ out) {
+    const int wpr = w >> 5;                                   // words per row
+    const uint32_t* m = reinterpret_cast<const uint32_t*>(bits + static_cast<size_t>(blockIdx.x) * h * (w >> 3));
+    int xmin = w, xmax = -1, ymin = h, ymax = -1, cnt = 0;
+    for (int i = threadIdx.x; i < h * wpr; i += blockDim.x) {
+        const uint32_t v = __ldg(m + i);                      // little-endian: bit b of the word = pixel 32*wx + b
+        if (v == 0) continue;
+        const int y = i / wpr, x0 = (i - y * wpr) << 5;
+        xmin = min(xmin, x0 + __ffs(v) - 1);
+        xmax = max(xmax, x0 + 31 - __clz(v));
+        ymin = min(ymin, y); ymax = max(ymax, y);
+        cnt += __popc(v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        xmin = min(xmin, __shfl_xor_sync(0xffffffffu, xmin, o));
+        xmax = max(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
+        ymin = min(ymin, __shfl_xor_sync(0xffffffffu, ymin, o));
+        ymax = max(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    }
+    __shared__ int s[8][5];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { s[warp][0] = xmin; s[warp][1] = xmax; s[warp][2] = ymin; s[warp][3] = ymax; s[warp][4] = cnt; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < 8; ++i) {
+            xmin = min(xmin, s[i][0]); xmax = max(xmax, s[i][1]);
+            ymin = min(ymin, s[i][2]); ymax = max(ymax, s[i][3]);
+            cnt += s[i][4];
+        }
+        int32_t* o = out + static_cast<size_t>(blockIdx.x) * 5;
+        o[0] = xmin; o[1] = xmax; o[2] = ymin; o[3] = ymax; o[4] = cnt;
+    }
+}
+
 // Byte sums of up to kMaxBoxes rectangles [x1, x2) x [y1, y2) of one uint8 [h][w][c] frame: the
 // `np.array(crop).mean() < 3` rejection of inference.py:121-125 as an integer test (sum < 3 * count)
 // on the frame that is already on the device.  grid = (row chunks, boxes); sums must start at zero.

@@ -9,11 +9,14 @@
 namespace ub {
 
 // ---------------------------------------------------------------------------
-// Debug / watchdog: every mbarrier wait is bounded so that a protocol bug
-// traps (context error -> host sees a failure) instead of hanging the GPU.
+// Watchdog: every mbarrier wait is bounded so that a protocol bug traps (context error -> host sees a
+// failure, unetb200_last_error names the wait site) instead of hanging the GPU.  The bound is far above
+// any legitimate wait: under programmatic dependent launch the next layer's MMA / epilogue warps sit in
+// these waits while their producer blocks in griddepcontrol.wait for the WHOLE previous grid, and tools
+// (cuda-gdb, MPS time slicing) stretch that further.  -DUB_WAIT_TIMEOUT_CYCLES=0 compiles the check out.
 // ---------------------------------------------------------------------------
 #ifndef UB_WAIT_TIMEOUT_CYCLES
-#define UB_WAIT_TIMEOUT_CYCLES (4000000000LL)   // ~2 s at 2 GHz
+#define UB_WAIT_TIMEOUT_CYCLES (40000000000LL)   // ~20 s at 2 GHz
 #endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -88,7 +91,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag
     long long t0 = clock64();
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if ((++spins & 0x3ff) == 0 && clock64() - t0 > UB_WAIT_TIMEOUT_CYCLES) {
+        if (UB_WAIT_TIMEOUT_CYCLES > 0 && (++spins & 0x3ff) == 0 && clock64() - t0 > UB_WAIT_TIMEOUT_CYCLES) {
             if (dbg) {
                 dbg[0] = 0xDEAD;
                 dbg[1] = tag;

@@ -343,6 +343,7 @@ struct ConvDesc {
     int ncls = 0;
     float* logits = nullptr;
     uint8_t* mask = nullptr;
+    int mask_bits = 0;          // 1 = mask is bit-packed [N][ncls][H][W/8]
     int bn = 128, amode = ub::A_COL3;
     int wstat = 1;              // allow weight-stationary mode when it fits
     int pf_items = 0;           // L2 prefetch distance (activation ring items)
@@ -505,6 +506,7 @@ int build_conv_step(const ConvDesc& d, int num_sms, Step* st) {
     p.head_b = d.head_b;
     p.logits = d.logits;
     p.mask = d.mask;
+    p.mask_bits = d.mask_bits;
     p.dbg = d.dbg;
     p.C0 = d.c0;
     p.C1 = d.c1;
@@ -646,7 +648,7 @@ int check_sm100() {
     return 0;
 }
 
-typedef std::tuple<const void*, int, int, int, int, void*, float*, uint8_t*> PlanKey;
+typedef std::tuple<const void*, int, int, int, int, void*, float*, uint8_t*, int> PlanKey;
 
 struct Plan {
     std::vector<Step> steps;
@@ -711,7 +713,7 @@ WsLayout ws_layout(int n, int h, int w, int bw) {
 }
 
 int build_plan(unetb200_handle_t h, const void* x, int x_fmt, int n, int H, int W, void* ws,
-               float* logits, uint8_t* mask, Plan* plan) {
+               float* logits, uint8_t* mask, int mask_bits, Plan* plan) {
     const int bw = h->arch.base_width;
     const WsLayout L = ws_layout(n, H, W, bw);
     char* base = static_cast<char*>(ws);
@@ -795,7 +797,7 @@ int build_plan(unetb200_handle_t h, const void* x, int x_fmt, int n, int H, int 
             d.w = Wp(21); d.bias = Bp(21);
             d.n = n; d.h = H; d.wd = W; d.cout = bw; d.relu = 1; d.taps = 9; d.epi = ub::EPI_HEAD;
             d.head_w = reinterpret_cast<const float*>(Wp(22)); d.head_b = Bp(22);
-            d.ncls = h->arch.n_classes; d.logits = logits; d.mask = mask;
+            d.ncls = h->arch.n_classes; d.logits = logits; d.mask = mask; d.mask_bits = mask_bits;
             d.bn = 64; d.amode = h->amode; d.wstat = h->wstat; d.pf_items = h->pf_items; d.epi2 = h->epi2; d.min_na = h->min_na; d.pair = h->pair >= 1; d.dbg = h->dbg;
             Step st;
             if ((rc = build_conv_step(d, h->num_sms, &st))) return rc;
@@ -1008,9 +1010,9 @@ uint64_t unetb200_workspace_bytes(unetb200_handle_t h, int n, int height, int wi
     return ws_layout(n, height, width, h->arch.base_width).total;
 }
 
-int unetb200_forward(unetb200_handle_t h, const void* x, int x_fmt, int n, int height, int width,
-                     void* workspace, uint64_t workspace_bytes, float* logits, uint8_t* mask,
-                     const float* logit_thr, void* stream) {
+static int forward_impl(unetb200_handle_t h, const void* x, int x_fmt, int n, int height, int width,
+                        void* workspace, uint64_t workspace_bytes, float* logits, uint8_t* mask, int mask_bits,
+                        const float* logit_thr, void* stream) {
     if (!h) return fail(UNETB200_EINVAL, "handle is NULL");
     if (!x || !workspace) return fail(UNETB200_EINVAL, "x/workspace pointer is NULL");
     if (n <= 0 || height <= 0 || width <= 0) return fail(UNETB200_EINVAL, "empty input");
@@ -1027,14 +1029,31 @@ int unetb200_forward(unetb200_handle_t h, const void* x, int x_fmt, int n, int h
         return fail(UNETB200_EINVAL, "workspace must be 1024-byte aligned");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     std::lock_guard<std::mutex> g(h->mu);
-    int dev = -1;
-    UB_CUDA(cudaGetDevice(&dev));
-    if (dev != h->device) UB_CUDA(cudaSetDevice(h->device));
-    PlanKey key(x, x_fmt, n, height, width, workspace, logits, mask);
+    if (h->dbg && h->dbg[0] == 0xDEAD) {
+        // a kernel of an earlier forward ran into the bounded mbarrier wait (ptx.cuh) and trapped: the CUDA
+        // context is gone; say where instead of failing with a bare "unspecified launch failure"
+        char buf[200];
+        snprintf(buf, sizeof buf, "an earlier launch trapped in its mbarrier watchdog (wait site %d, block %d, "
+                 "thread %d, parity %d): the CUDA context of this process is unusable",
+                 h->dbg[1], h->dbg[2], h->dbg[3], h->dbg[4]);
+        return fail(UNETB200_ECUDA, buf);
+    }
+    // run on the handle's device and hand the caller's current device back on every exit path
+    struct DeviceGuard {
+        int prev = -1;
+        bool switched = false;
+        ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+    } guard;
+    UB_CUDA(cudaGetDevice(&guard.prev));
+    if (guard.prev != h->device) {
+        UB_CUDA(cudaSetDevice(h->device));
+        guard.switched = true;
+    }
+    PlanKey key(x, x_fmt, n, height, width, workspace, logits, mask, mask_bits);
     auto it = h->plans.find(key);
     if (it == h->plans.end()) {
         Plan plan;
-        int rc = build_plan(h, x, x_fmt, n, height, width, workspace, logits, mask, &plan);
+        int rc = build_plan(h, x, x_fmt, n, height, width, workspace, logits, mask, mask_bits, &plan);
         if (rc) return rc;
         if (h->plans.size() > 64) h->plans.clear();
         it = h->plans.emplace(key, std::move(plan)).first;
@@ -1065,6 +1084,19 @@ int unetb200_forward(unetb200_handle_t h, const void* x, int x_fmt, int n, int h
     h->last_launches = launches;
     h->timed = prof;
     return 0;
+}
+
+int unetb200_forward(unetb200_handle_t h, const void* x, int x_fmt, int n, int height, int width,
+                     void* workspace, uint64_t workspace_bytes, float* logits, uint8_t* mask,
+                     const float* logit_thr, void* stream) {
+    return forward_impl(h, x, x_fmt, n, height, width, workspace, workspace_bytes, logits, mask, 0, logit_thr, stream);
+}
+
+int unetb200_forward_bits(unetb200_handle_t h, const void* x, int x_fmt, int n, int height, int width,
+                          void* workspace, uint64_t workspace_bytes, float* logits, uint8_t* mask_bits,
+                          const float* logit_thr, void* stream) {
+    return forward_impl(h, x, x_fmt, n, height, width, workspace, workspace_bytes, logits, mask_bits, 1, logit_thr,
+                        stream);
 }
 
 int unetb200_layer_times(unetb200_handle_t h, float* ms, int count) {
@@ -1130,7 +1162,7 @@ int unetb200_conv3x3_head(const void* src0, int c0, const void* w_packed, const 
     d.src0 = src0; d.c0 = c0; d.w = w_packed; d.bias = bias; d.n = n; d.h = height; d.wd = width;
     d.cout = 64; d.relu = 1; d.taps = 9; d.epi = ub::EPI_HEAD; d.head_w = head_w; d.head_b = head_b;
     d.ncls = n_classes; d.logits = logits; d.mask = mask; d.bn = 64; d.amode = amode;
-    d.wstat = wstat & 1; d.pair = (wstat >> 1) & 1; d.dbg = g_hook_dbg();
+    d.wstat = wstat & 1; d.pair = (wstat >> 1) & 1; d.mask_bits = (wstat >> 2) & 1; d.dbg = g_hook_dbg();
     int sms = 0;
     if ((rc = device_num_sms(&sms))) return rc;
     Step st;
@@ -1315,6 +1347,14 @@ int unetb200_resize_bicubic_u8_ps(const uint8_t* src, int n, int h, int w, int c
 int unetb200_mask_bbox(const uint8_t* mask, int n_planes, int h, int w, int32_t* out, void* stream) {
     if (!mask || !out || n_planes <= 0 || h <= 0 || w <= 0) return fail(UNETB200_EINVAL, "mask_bbox: bad argument");
     ub::mask_bbox_kernel<<<n_planes, 256, 0, static_cast<cudaStream_t>(stream)>>>(mask, h, w, out);
+    UB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int unetb200_mask_bbox_bits(const uint8_t* bits, int n_planes, int h, int w, int32_t* out, void* stream) {
+    if (!bits || !out || n_planes <= 0 || h <= 0 || w <= 0 || (w & 31) || (reinterpret_cast<uintptr_t>(bits) & 3))
+        return fail(UNETB200_EINVAL, "mask_bbox_bits: bad argument (w must be a multiple of 32, bits 4-byte aligned)");
+    ub::mask_bbox_bits_kernel<<<n_planes, 256, 0, static_cast<cudaStream_t>(stream)>>>(bits, h, w, out);
     UB_CUDA(cudaGetLastError());
     return 0;
 }

@@ -24,6 +24,18 @@ def logit_thresholds(probs: Sequence[float]) -> list[float]:
     return [math.log(t / (1.0 - t)) for t in probs]
 
 
+def unpack_mask_bits(bits, width: Optional[int] = None):
+    """Bit-packed masks (``Engine.run(mask_bits=True)``: uint8 ``[..., H, W/8]``, LSB first) -> uint8 0/1
+    ``[..., H, W]``.  Accepts a numpy array or a (CPU or CUDA) tensor and returns the same kind."""
+    if isinstance(bits, torch.Tensor):
+        shifts = torch.arange(8, dtype=torch.uint8, device=bits.device)
+        out = ((bits.unsqueeze(-1) >> shifts) & 1).reshape(*bits.shape[:-1], bits.shape[-1] * 8)
+        return out if width is None else out[..., :width]
+    import numpy as np
+    out = np.unpackbits(np.ascontiguousarray(bits), axis=-1, bitorder="little")
+    return out if width is None else out[..., :width]
+
+
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
@@ -44,7 +56,9 @@ class Engine:
         self.layers = nat.layer_table(self.arch)
         self.n_channels, self.n_classes = n_channels, n_classes
         self._lock = threading.Lock()
-        self._ws: Optional[torch.Tensor] = None
+        # one scratch region PER CUDA STREAM: forwards enqueued on different streams may overlap on the
+        # device, so they must never share activations (the lock below only serialises the enqueue)
+        self._ws: "dict[int, torch.Tensor]" = {}
         self._handle = C.c_void_p()
         with torch.cuda.device(self.device):
             nbytes = int(self._lib.unetb200_packed_bytes(C.byref(self.arch)))
@@ -97,24 +111,43 @@ class Engine:
     def workspace_bytes(self, n: int, h: int, w: int) -> int:
         return int(self._lib.unetb200_workspace_bytes(self._handle, n, h, w))
 
-    def _workspace(self, n: int, h: int, w: int):
-        """(pointer, bytes) of a 1024-byte aligned scratch region big enough for this shape."""
+    MAX_STREAM_WORKSPACES = 4
+
+    def _workspace(self, n: int, h: int, w: int, stream: int):
+        """(pointer, bytes) of a 1024-byte aligned scratch region big enough for this shape, private to
+        the CUDA stream ``stream`` (the raw ``cudaStream_t`` value).  A region is allocated, grown and
+        dropped only while its own stream is current, so torch's stream-ordered caching allocator never
+        hands its memory to work that could overlap a forward still running on it."""
         need = self.workspace_bytes(n, h, w)
-        if self._ws is None or self._ws.numel() < need + 1024:
-            self._ws = None
-            self._ws = torch.empty(need + 1024, dtype=torch.uint8, device=self.device)
-        ptr = (self._ws.data_ptr() + 1023) & ~1023          # small torch blocks are only 512-byte aligned
-        return ptr, self._ws.numel() - (ptr - self._ws.data_ptr())
+        ws = self._ws.get(stream)
+        if ws is None or ws.numel() < need + 1024:
+            self._ws.pop(stream, None)
+            ws = None                                        # release before growing
+            if len(self._ws) >= self.MAX_STREAM_WORKSPACES:  # oldest stream's region goes back to ITS pool
+                self._ws.pop(next(iter(self._ws)))
+            ws = self._ws[stream] = torch.empty(need + 1024, dtype=torch.uint8, device=self.device)
+        ptr = (ws.data_ptr() + 1023) & ~1023                 # small torch blocks are only 512-byte aligned
+        return ptr, ws.numel() - (ptr - ws.data_ptr())
+
+    def _check_out(self, t: torch.Tensor, what: str, shape, dtype) -> None:
+        if not isinstance(t, torch.Tensor) or t.device != self.device or t.dtype != dtype \
+                or tuple(t.shape) != tuple(shape) or not t.is_contiguous():
+            raise RuntimeError(f"{what} must be a contiguous {dtype} tensor of shape {tuple(shape)} on {self.device}, "
+                               f"got {getattr(t, 'dtype', type(t))} {tuple(getattr(t, 'shape', ()))} on "
+                               f"{getattr(t, 'device', None)} (contiguous={getattr(t, 'is_contiguous', lambda: None)()})")
 
     # ------------------------------------------------------------------ forward
     def run(self, x: torch.Tensor, *, want_logits: bool = True,
             thresholds: Optional[Sequence[float]] = None,
-            logits_out: Optional[torch.Tensor] = None, mask_out: Optional[torch.Tensor] = None):
+            logits_out: Optional[torch.Tensor] = None, mask_out: Optional[torch.Tensor] = None,
+            mask_bits: bool = False):
         """Enqueue one forward on the current stream.
 
         ``x``: float32 ``[N,C,H,W]`` (values as ``inference.preprocess`` makes them) or uint8
         ``[N,H,W,C]`` raw pixels.  Returns ``(logits | None, mask | None)``; ``mask`` is uint8
-        ``[N,n_classes,H,W]`` with 1 where ``sigmoid(logit) > thresholds[c]``.
+        ``[N,n_classes,H,W]`` with 1 where ``sigmoid(logit) > thresholds[c]``, or, with ``mask_bits``,
+        the same booleans packed eight to a byte: uint8 ``[N,n_classes,H,W/8]``, pixel ``x`` = bit ``x & 7``
+        (LSB first) of byte ``x >> 3`` (:func:`unpack_mask_bits` / ``np.unpackbits(bitorder="little")``).
         """
         if x.device != self.device:
             raise RuntimeError(f"input is on {x.device}, engine is on {self.device}")
@@ -135,21 +168,28 @@ class Engine:
             raise RuntimeError(f"H and W must be divisible by 16, got {h}x{w}")
         x = x.contiguous()
         thr = None
+        out_shape = (n, self.n_classes, h, w)
+        mask_shape = (n, self.n_classes, h, w // 8) if mask_bits else out_shape
+        if logits_out is not None:
+            self._check_out(logits_out, "logits_out", out_shape, torch.float32)
+        if mask_out is not None:
+            self._check_out(mask_out, "mask_out", mask_shape, torch.uint8)
         with self._lock, torch.cuda.device(self.device):
-            ws_ptr, ws_bytes = self._workspace(n, h, w)
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            ws_ptr, ws_bytes = self._workspace(n, h, w, stream)
             logits = None
             if want_logits:
                 logits = logits_out if logits_out is not None else torch.empty(
-                    (n, self.n_classes, h, w), dtype=torch.float32, device=self.device)
+                    out_shape, dtype=torch.float32, device=self.device)
             mask = None
             if thresholds is not None:
                 if len(thresholds) != self.n_classes:
                     raise RuntimeError("one threshold per class is required")
                 thr = (C.c_float * self.n_classes)(*logit_thresholds(thresholds))
                 mask = mask_out if mask_out is not None else torch.empty(
-                    (n, self.n_classes, h, w), dtype=torch.uint8, device=self.device)
-            stream = torch.cuda.current_stream(self.device).cuda_stream
-            nat.check(self._lib.unetb200_forward(
+                    mask_shape, dtype=torch.uint8, device=self.device)
+            fwd = self._lib.unetb200_forward_bits if mask_bits else self._lib.unetb200_forward
+            nat.check(fwd(
                 self._handle, x.data_ptr(), fmt, n, h, w, ws_ptr, ws_bytes,
                 _ptr(logits), _ptr(mask), thr, stream))
         return logits, mask

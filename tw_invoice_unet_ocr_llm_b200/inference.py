@@ -46,7 +46,10 @@ def load_model(checkpoint_path: str):
     """Build ``UNet(3, 3)``, strictly load the state_dict, ``eval()`` (reference :17-24).
 
     The result is cached per (real path, mtime, size, device): the reference re-reads the
-    124 MB checkpoint on every call, which costs ~1 s.
+    124 MB checkpoint on every call, which costs ~1 s.  Unlike the reference, which returns a fresh
+    module per call, the returned instance is therefore SHARED with later ``run_unet`` calls of the same
+    checkpoint: treat it as read-only (``copy.deepcopy`` it before fine-tuning or weight surgery; the packed
+    replica is never copied along).
     """
     st = os.stat(checkpoint_path)
     key = (os.path.realpath(checkpoint_path), st.st_mtime_ns, st.st_size, DEVICE)

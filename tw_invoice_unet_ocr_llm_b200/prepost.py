@@ -98,6 +98,22 @@ def mask_bbox(mask: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def mask_bbox_bits(bits: torch.Tensor) -> torch.Tensor:
+    """Bit-packed masks uint8 ``[N, C, H, W/8]`` (``Engine.run(mask_bits=True)``) -> int32 ``[N, C, 5]`` as
+    :func:`mask_bbox`.  ``W`` must be a multiple of 32.  Enqueued on the current stream."""
+    if bits.dtype != torch.uint8 or bits.dim() != 4 or not bits.is_cuda:
+        raise RuntimeError("mask_bbox_bits expects a CUDA uint8 [N,C,H,W/8] tensor")
+    bits = bits.contiguous()
+    n, c, h, wb = bits.shape
+    if wb % 4:
+        raise RuntimeError("mask_bbox_bits needs a mask width that is a multiple of 32")
+    out = torch.empty((n, c, 5), dtype=torch.int32, device=bits.device)
+    with torch.cuda.device(bits.device):
+        nat.check(nat.lib().unetb200_mask_bbox_bits(bits.data_ptr(), n * c, h, wb * 8, out.data_ptr(),
+                                                    torch.cuda.current_stream(bits.device).cuda_stream))
+    return out
+
+
 def box_sums(frame: torch.Tensor, rects, channels: int = None) -> torch.Tensor:
     """uint8 ``[H, W, C]`` frame on a CUDA device + up to 16 half-open rectangles ``(x1, y1, x2, y2)``
     -> int64 ``[n]`` byte sums on the device (the ``np.array(crop).mean() < 3`` test of reference

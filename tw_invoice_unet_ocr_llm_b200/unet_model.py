@@ -92,6 +92,16 @@ class UNet(nn.Module):
         state["_engine_key"] = None
         return state
 
+    def invalidate_engine(self):
+        """Drop the packed replica so that the next eval forward re-folds and re-packs the weights.
+
+        The replica is rebuilt automatically after ``load_state_dict``, ``.to()`` / ``.cuda()`` / ``.half()``,
+        ``train()`` and any in-place update autograd can see (the key below tracks every tensor's storage
+        pointer and version counter).  Writes that bypass the version counter -- ``param.data.copy_()``,
+        EMA updates through ``.data``, manual weight surgery on ``.data`` -- are invisible to it: call this
+        method after them."""
+        self._drop_engine()
+
     def _weights_key(self):
         return tuple((t.data_ptr(), t._version) for t in itertools.chain(self.parameters(), self.buffers()))
 
