@@ -3,11 +3,19 @@
 fixture best_unet_model.pth, batch 64 x 3 x 512 x 512, bf16 tensor-core forward on B200.
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU forward (oracle port)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU forward (oracle/_ref)
 
 One process per GPU (torchrun for N > 1); images are independent, so ranks shard the batch
 with no data-path collective ("scaling": "weak": 64 images per GPU per step).  Rank 0 prints
-ONE JSON line.  See DESIGN.md "Measurement" for what each field means.
+ONE JSON line.  Besides the headline (`value`, `e2e`, `roofline`, `cpu_baseline`) the line carries:
+  sharded_512      BASELINE.json configs[2] as written: 512 pinned frames sharded 512/N per GPU in chunks of
+                   64 -> all masks in ONE host array (launcher.HostGather), wall clock, strong scaling
+  shard_bitident   every rank segments rank 0's first 8 frames; the mask hashes must agree across ranks
+  launcher_threads the same 512 frames through launcher.MultiGpuSegmenter (one process, one thread per GPU)
+  hires_1024       configs[3]: 16 x 3 x 1024 x 1024, img/s and per-layer GB/s of the HBM-bound layers
+  run_unet_batch_1080p  the reference-facing batched entry on 64 PIL 1920x1080 frames
+  latency_b1       configs[4]: batch-1 forward + threshold, run_unet on a 1080p frame
+See DESIGN.md "Measurement" for what each field means.
 """
 from __future__ import annotations
 
@@ -137,44 +145,78 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_forward_rate(state, n_images: int, warmup: int, batch: int = 1):
-    """images/s of the oracle's fp32 CPU forward (the reference's algorithm on the host cores)."""
+def cpu_forward(state):
+    """(callable x -> logits, kind): the UNMODIFIED reference module `unet_model.UNet` (reference
+    unet_model.py:23-86, vendored to oracle/_ref/ by oracle/make_ref.sh; kind "reference") run in eval mode under
+    no_grad on the host cores, exactly like inference.py:66-67; the oracle port (kind "port") only when the
+    reference modules are absent."""
     import torch
+    from oracle.reference_modules import reference_unet_model
+    mod = reference_unet_model()
+    if mod is not None:
+        model = mod.UNet(n_channels=3, n_classes=3)
+        model.load_state_dict(state)
+        model.eval()
+
+        def fwd(x):
+            with torch.no_grad():
+                return model(x)
+        return fwd, "reference"
     from oracle.unet_oracle import oracle_forward
+    return (lambda x: oracle_forward(state, x)), "port"
+
+
+def cpu_forward_rate(state, n_images: int, warmup: int, batch: int = 1, size: int = 512):
+    """images/s of the reference's fp32 CPU forward on all host cores -> (rate, cores, step times, kind)."""
+    import torch
     from tw_invoice_unet_ocr_llm_b200.synthetic import synthetic_invoices
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    x = synthetic_invoices(batch, 512, 512, seed=42)
+    fwd, kind = cpu_forward(state)
+    x = synthetic_invoices(batch, size, size, seed=42)
     for _ in range(warmup):
-        oracle_forward(state, x)
+        fwd(x)
     times = []
     for _ in range(max(1, n_images // batch)):
         t0 = time.perf_counter()
-        oracle_forward(state, x)
+        fwd(x)
         times.append(time.perf_counter() - t0)
-    return batch / statistics.median(times), cores, times
+    return batch / statistics.median(times), cores, times, kind
+
+
+def workload_config(batch: int, size: int, world: int) -> dict:
+    """The `config` object, identical for both arms (the reference arm times a bounded sample of it)."""
+    named = {512: "configs[1]", 1024: "configs[3]"}.get(size, "configs[1]-shaped")
+    return {"workload": f"{named}: fixture best_unet_model.pth (seeded, same 136-key fp32 format), "
+                        f"batch {batch} x 3x{size}x{size} synthetic invoices per GPU",
+            "batch_per_gpu": batch, "image": f"3x{size}x{size}",
+            "parallelism": f"dp{world} (batch sharding, no collective)",
+            "gflop_per_image": GFLOP_PER_IMAGE_512 * (size * size) / (512 * 512)}
 
 
 def run_reference(args, rank, world):
-    """`--impl reference`: the reference's own CPU implementation of the path.  The reference is
-    pure Python/PyTorch and cannot travel to the GPU box, so this times the oracle port (the same
-    torch.nn.functional CPU kernels, called functionally) on all host cores; rank 0 only."""
+    """`--impl reference`: the reference's own CPU implementation of the path -- the unmodified
+    `unet_model.UNet` from oracle/_ref/ (copied there from the reference checkout by oracle/make_ref.sh; it
+    travels to the GPU box with the snapshot), eval mode, fp32, all host cores; rank 0 only.  Same `config`
+    as the CUDA arm; every step is a bounded sample (2 images) of that arm's batch-64 step -- the CPU's
+    images/s does not depend on the batch size, its step would just take 32x longer."""
     if rank != 0:
         return
     from tw_invoice_unet_ocr_llm_b200.synthetic import make_fixture_state
     state = make_fixture_state()
     per_step = 2                                     # bounded sample: 2 of the 64 images per step
-    rate, cores, times = cpu_forward_rate(state, per_step * args.steps, max(1, args.warmup), batch=per_step)
+    rate, cores, times, kind = cpu_forward_rate(state, per_step * args.steps, max(1, args.warmup), batch=per_step,
+                                                size=args.size)
     ms = 1e3 * statistics.median(times)
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[1] shape on the CPU path: fixture best_unet_model.pth, 3x512x512 "
-                               f"invoices, fp32 torch CPU forward, {per_step} images per step (bounded sample "
-                               "of the batch-64 step)", "image": "3x512x512", "batch_per_step": per_step},
-        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} steps x {per_step} images, median step"},
+        "config": workload_config(args.batch, args.size, world),
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": f"{args.steps} steps x {per_step} images of the batch-{args.batch} step "
+                                   f"(fp32 torch CPU forward of {'the reference module' if kind == 'reference' else 'the oracle port'}), "
+                                   "median step"},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -236,7 +278,7 @@ def main():
     import torch.distributed as dist
     from tw_invoice_unet_ocr_llm_b200 import _native as nat
     from tw_invoice_unet_ocr_llm_b200.launcher import GpuWorker
-    from tw_invoice_unet_ocr_llm_b200.synthetic import make_fixture_state, synthetic_invoices_u8
+    from tw_invoice_unet_ocr_llm_b200.synthetic import make_fixture_state, synthetic_invoices, synthetic_invoices_u8
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA (B200) device: there is no CPU path for --impl b200")
@@ -250,10 +292,18 @@ def main():
         numa_cores = bind_to_gpu_numa(local_rank)
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's version banner must not land on stdout
         dist.init_process_group("nccl", device_id=dev)
+    # host-side rendezvous for the sections where GPUs must stay idle while a rank waits (an NCCL barrier
+    # parks a spinning kernel on every waiting GPU)
+    host_group = dist.new_group(backend="gloo") if world > 1 else None
+
+    def host_barrier():
+        if world > 1:
+            dist.barrier(group=host_group)
 
     B, S = args.batch, args.size
     state = make_fixture_state()
-    worker = GpuWorker(state, dev, chunk=min(B, args.e2e_chunk))   # public multi-GPU launcher building block
+    # public multi-GPU launcher building block; masks leave the GPU bit-packed (1 bit per pixel)
+    worker = GpuWorker(state, dev, chunk=min(B, args.e2e_chunk), packed=True)
     eng = worker.engine
     thr = [0.25, 0.40, 0.30]
 
@@ -328,7 +378,7 @@ def main():
     layer_ms = [a / args.steps for a in acc]
     layers = eng.layers
     peaks = read_peaks()
-    table, tc_flops, tc_ms, tc_bytes = [], 0.0, 0.0, 0.0
+    table, tc_flops, tc_ms, tc_bytes, n_tc = [], 0.0, 0.0, 0.0, 0
     for i, l in enumerate(layers):
         if l.kind == nat.HEAD:
             continue                                  # fused into conv1.net.3
@@ -339,10 +389,11 @@ def main():
         tf = fl / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
         tensor = l.kind in (nat.CONV3X3, nat.CONVT2X2)
         by = layer_bytes(l, S, S) * B + l.w_bytes
-        if tensor:
+        if tensor and ms > 0:
             tc_flops += fl
             tc_ms += ms
             tc_bytes += by
+            n_tc += 1
         table.append({"layer": l.name.decode(), "kernel": "conv_tc_kernel (tcgen05)" if tensor else
                       ("conv_tc_kernel<A_STEM> (tcgen05, in-kernel im2col; HBM / issue bound)"
                        if eng.get_option("stem_tc") else "stem_conv_kernel (CUDA cores)"),
@@ -351,14 +402,18 @@ def main():
                       "frac_of_peak": round(tf / peaks["tflops"], 3)})
     achieved = tc_flops / (tc_ms * 1e-3) / 1e12
     traffic, traffic_src = ncu_traffic_bytes() if (B == 64 and S == 512) else (None, None)
+    if traffic is not None and launches_per_step != 22:
+        traffic = None          # the committed capture describes the 22-launch plan only
     roofline = {
-        "bound": "tensor", "kernel": "conv_tc_kernel<BN,TAPS,AMODE,EPI> (21 launches per step: 17 conv3x3 + 4 convT)",
+        "bound": "tensor", "kernel": f"tcgen05 implicit-GEMM conv kernels ({n_tc} launches per step: 3x3 convs + 2x2 up-convs)",
         "achieved": round(achieved, 1), "peak": peaks["tflops"], "unit": "TFLOP/s",
         "frac": round(achieved / peaks["tflops"], 4), "traffic": traffic,
-        "traffic_note": (f"DRAM read+write bytes of the same 21 launches of one step, ncu --set full ({traffic_src}); "
-                         f"algorithmic bytes of those launches: {tc_bytes / 1e9:.2f} GB per step") if traffic else None,
+        "traffic_note": (f"STATIC, not measured in this run: DRAM read+write bytes of the same launches of one step "
+                         f"from the committed ncu --set full capture profiles/{traffic_src}; "
+                         f"algorithmic bytes of those launches: {tc_bytes / 1e9:.2f} GB per step") if traffic else
+                        f"no committed ncu capture for this configuration; algorithmic bytes {tc_bytes / 1e9:.2f} GB per step",
         "peak_source": peaks["source"],
-        "how": "sum of algorithmic conv FLOPs of the 21 tcgen05 launches / sum of their CUDA-event durations "
+        "how": "sum of algorithmic conv FLOPs of the tcgen05 launches / sum of their CUDA-event durations "
                "(events recorded between launches on the launching stream, averaged over the K steps)",
         "share_of_step": round(tc_ms / sum(layer_ms), 4),
     }
@@ -368,12 +423,12 @@ def main():
 
     # ---------------- end to end through the public launcher API: pinned host frames in, host masks out
     frames_host = torch.from_numpy(frames_u8).pin_memory()
-    masks_host = torch.empty((B, 3, S, S), dtype=torch.uint8).pin_memory()
+    masks_host = torch.empty((B, 3, S, S // 8), dtype=torch.uint8).pin_memory()     # 1 bit per pixel
 
     # Steady-state serving loop: every step uploads its own 64 frames and downloads its own masks
     # (all inside the timed region); the launcher double-buffers, so step k+1's upload overlaps
     # step k's forward.  Alternating host mask buffers stand in for the consumer of step k.
-    masks_alt = torch.empty((B, 3, S, S), dtype=torch.uint8).pin_memory()
+    masks_alt = torch.empty_like(masks_host).pin_memory()
 
     def e2e_run(k):
         for i in range(k):
@@ -386,8 +441,136 @@ def main():
     e2e = {"value": world * B / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms,
            "h2d_bytes_per_step": int(frames_host.numel()), "d2h_bytes_per_step": int(masks_host.numel()),
            "chunk": worker.chunk,
-           "api": "tw_invoice_unet_ocr_llm_b200.launcher.GpuWorker.segment_async + synchronize (pinned uint8 frames -> "
-                  "pinned uint8 masks, double-buffered across steps)"}
+           "api": "tw_invoice_unet_ocr_llm_b200.launcher.GpuWorker(packed=True).segment_async + synchronize (pinned "
+                  "uint8 frames -> pinned bit-packed masks [B,3,H,W/8], double-buffered across steps)"}
+
+    # ---------------- BASELINE.json configs[2] as written (SURVEY 8d "Config 3"): 512 synthetic frames, 512/N per
+    # GPU in chunks of 64; wall clock from "frames in pinned host memory" to "all masks in ONE host array";
+    # strong scaling (total work fixed).  The gather is launcher.HostGather: a shared pinned host block that every
+    # rank's device->host copies write in place (no collective, no extra copy).
+    import hashlib
+    from tw_invoice_unet_ocr_llm_b200.launcher import HostGather, MultiGpuSegmenter, shard_bounds
+    TOTAL = 512
+    sharded = bitident = threads_res = None
+    if not args.no_extras and S % 32 == 0:
+        base0 = synthetic_invoices_u8(8, S, S, seed=7)                 # the same 8 frames on every rank
+        lo, hi = shard_bounds(TOTAL, world, rank)
+        shard_frames = torch.empty((hi - lo, S, S, 3), dtype=torch.uint8).pin_memory()
+        for i in range(hi - lo):
+            shard_frames[i] = torch.from_numpy(base0[(lo + i) % 8])
+        item = (3, S, S // 8)
+        hg = HostGather(TOTAL, item, group=host_group) if world > 1 else None
+        out_local = hg.local() if hg is not None else torch.empty((TOTAL, *item), dtype=torch.uint8).pin_memory()
+        walls = []
+        for rep in range(4):                                          # first pass untimed
+            torch.cuda.synchronize(dev)
+            host_barrier()
+            t0 = time.perf_counter()
+            worker.segment_async(shard_frames, out_local)
+            worker.synchronize()
+            host_barrier()
+            if rep:
+                walls.append(time.perf_counter() - t0)
+        wall = statistics.median(walls)
+        # bit identity across GPUs: every rank segments the SAME 8 frames; 64-bit hashes of the packed masks
+        # must agree, and every gathered row g must equal row g % 8 of rank 0's own result
+        eight = torch.empty((8, *item), dtype=torch.uint8).pin_memory()
+        worker.segment(torch.from_numpy(base0).pin_memory(), eight)
+        digest = int.from_bytes(hashlib.blake2b(eight.numpy().tobytes(), digest_size=8).digest(), "little", signed=True)
+        hashes = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+        if world > 1:
+            dist.all_gather(hashes, torch.tensor([digest], dtype=torch.int64), group=host_group)
+        else:
+            hashes = [torch.tensor([digest])]
+        if rank == 0:
+            full = hg.full() if hg is not None else out_local
+            rows_ok = all(torch.equal(full[g], eight[g % 8]) for g in range(TOTAL))
+            bitident = bool(rows_ok and all(int(h.item()) == digest for h in hashes))
+            sharded = {"images": TOTAL, "per_gpu": hi - lo, "chunk": worker.chunk, "wall_ms": wall * 1e3,
+                       "value": TOTAL / wall, "unit": UNIT, "scaling": "strong",
+                       "h2d_bytes": TOTAL * S * S * 3, "d2h_bytes": TOTAL * 3 * S * S // 8,
+                       "gather": ("launcher.HostGather: one POSIX shared-memory block, cudaHostRegister'ed in every rank "
+                                  f"(pinned={hg.pinned}); each GPU's D2H writes its shard in place") if hg is not None
+                                 else "single process: masks land in one pinned array",
+                       "what": "wall clock (time.perf_counter between host barriers, median of 3 after 1 warm-up pass) from "
+                               "frames in pinned host memory to all bit-packed masks in one host array",
+                       "rows_equal_rank0_reference": rows_ok}
+        if hg is not None:
+            hg.close()
+        del shard_frames, out_local
+
+        # the same job through the one-process launcher (Python threads, one per GPU): rank 0 drives all N GPUs
+        # while the other ranks wait on the host (their GPUs idle)
+        if rank == 0:
+            try:
+                seg = MultiGpuSegmenter(state, devices=[f"cuda:{i}" for i in range(world)], packed=True)
+                frames512 = torch.empty((TOTAL, S, S, 3), dtype=torch.uint8).pin_memory()
+                for i in range(TOTAL):
+                    frames512[i] = torch.from_numpy(base0[i % 8])
+                out512 = torch.empty((TOTAL, *item), dtype=torch.uint8).pin_memory()
+                tw = []
+                for rep in range(4):
+                    t0 = time.perf_counter()
+                    seg.segment(frames512, out512)
+                    if rep:
+                        tw.append(time.perf_counter() - t0)
+                w2 = statistics.median(tw)
+                same = all(torch.equal(out512[g], eight[g % 8]) for g in range(TOTAL))
+                threads_res = {"images": TOTAL, "wall_ms": w2 * 1e3, "value": TOTAL / w2, "unit": UNIT,
+                               "ratio_to_torchrun": (TOTAL / w2) / (TOTAL / wall), "rows_equal_rank0_reference": same,
+                               "api": "launcher.MultiGpuSegmenter(packed=True).segment: one process, one worker thread per GPU"}
+                del seg, frames512, out512
+            except Exception as e:          # informational
+                threads_res = {"error": repr(e)}
+            torch.cuda.set_device(dev)
+        host_barrier()
+
+    # ---------------- BASELINE.json configs[3]: 16 x 3 x 1024 x 1024 (rank 0): img/s and the HBM-bound layers
+    hires = None
+    if rank == 0 and not args.no_extras and S == 512:
+        try:
+            HB, HS = 16, 1024
+            xh = synthetic_invoices(2, HS, HS, seed=54).repeat(HB // 2, 1, 1, 1).to(dev)
+            lh = torch.empty((HB, 3, HS, HS), dtype=torch.float32, device=dev)
+            mh = torch.empty((HB, 3, HS, HS), dtype=torch.uint8, device=dev)
+            run_h = lambda: eng.run(xh, want_logits=True, thresholds=thr, logits_out=lh, mask_out=mh)
+            for _ in range(3):
+                run_h()
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                run_h()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            ms_h = e0.elapsed_time(e1) / 5
+            eng.set_option("profile", 1)
+            run_h()
+            acc_h = None
+            for _ in range(3):
+                run_h()
+                t = eng.layer_times_ms()
+                acc_h = t if acc_h is None else [a + b for a, b in zip(acc_h, t)]
+            eng.set_option("profile", 0)
+            rows = {}
+            for i, l in enumerate(layers):
+                nm = l.name.decode()
+                if nm in ("down1.net.0", "down1.net.3", "up1", "up2", "conv1.net.0", "conv1.net.3") and acc_h[i] > 0:
+                    by = layer_bytes(l, HS, HS) * HB + l.w_bytes
+                    fl = layer_flops(l, HS, HS) * HB
+                    ms = acc_h[i] / 3
+                    rows[nm] = {"ms": round(ms, 4), "gb_per_s": round(by / 1e9 / (ms * 1e-3), 1),
+                                "frac_of_hbm_peak": round(by / 1e9 / (ms * 1e-3) / peaks["hbm_gbs"], 3),
+                                "tflops": round(fl / (ms * 1e-3) / 1e12, 1)}
+            hires = {"workload": "configs[3]: batch 16 x 3x1024x1024, fp32 NCHW input resident, fp32 logits + uint8 masks out",
+                     "value": HB / (ms_h / 1e3), "unit": UNIT, "ms_per_step": ms_h,
+                     "achieved_tflops_whole_step": HB / (ms_h / 1e3) * GFLOP_PER_IMAGE_512 * 4 / 1e3,
+                     "hbm_peak_gbs": peaks["hbm_gbs"], "layers": rows,
+                     "how": "5 forwards under CUDA events after 3 warm-ups; per-layer: events between launches (PDL off), 3 forwards"}
+            del xh, lh, mh
+        except Exception as e:              # informational
+            hires = {"error": repr(e)}
+            eng.set_option("profile", 0)
 
     # ---------------- batch-1 latency (BASELINE.json configs[4]): one resident 3x512x512 frame ->
     # logits + masks, synchronised per call; p50/p95 over 200 calls (rank 0, informational)
@@ -459,6 +642,24 @@ def main():
                         ts.append((time.perf_counter() - t0) * 1e3)
                 ts.sort()
                 res["with_crop_enhancement"] = {"p50_ms": ts[len(ts) // 2], "p95_ms": ts[int(len(ts) * 0.95)]}
+                # the reference-facing batched entry point on 64 frames (4 distinct 1080p frames x 16)
+                try:
+                    four = synthetic_invoices_u8(4, 1080, 1920, seed=12)
+                    pils = [Image.fromarray(four[i % 4]) for i in range(64)]
+                    inf.run_unet_batch(pils, ckpt)
+                    tb = []
+                    for _ in range(3):
+                        t0 = time.perf_counter()
+                        outb = inf.run_unet_batch(pils, ckpt)
+                        tb.append(time.perf_counter() - t0)
+                    wb = statistics.median(tb)
+                    res["run_unet_batch_1080p"] = {
+                        "images": 64, "wall_ms": wb * 1e3, "value": 64 / wb, "unit": UNIT,
+                        "crops_per_image": sum(c is not None for c in outb[0][1].values()),
+                        "api": "inference.run_unet_batch(list of 64 PIL RGB 1920x1080 frames, checkpoint): masks + crops"}
+                    del pils, outb
+                except Exception as e:
+                    res["run_unet_batch_1080p"] = {"error": repr(e)}
                 # the same sequence with the reference's cv2 calls on the host for the enhancement
                 # (this fixture's crops cover most of the frame: ~90 Mpixel of enhanced output per call)
                 try:
@@ -499,25 +700,26 @@ def main():
     # ---------------- CPU baseline (rank 0, N = 1 only): the oracle port on the host cores
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        rate, cores, times = cpu_forward_rate(state, 8, 2, batch=1)
-        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{len(times)} single-image 3x512x512 fp32 forwards of the oracle after 2 warm-ups, median "
-                         f"{statistics.median(times):.3f} s"}
+        rate, cores, times, kind = cpu_forward_rate(state, 8, 2, batch=1, size=S)
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": kind,
+               "sample": f"{len(times)} single-image 3x{S}x{S} fp32 forwards of "
+                         f"{'the unmodified reference UNet (oracle/_ref)' if kind == 'reference' else 'the oracle port'} "
+                         f"after 2 warm-ups, median {statistics.median(times):.3f} s"}
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"configs[1]: fixture best_unet_model.pth (seeded, same 136-key fp32 format), "
-                                   f"batch {B} x 3x{S}x{S} synthetic invoices per GPU, bf16 NHWC tensor-core forward, "
-                                   "fp32 NCHW input resident in HBM, outputs fp32 logits + uint8 masks",
-                       "numa_bound_cores_rank0": len(numa_cores) if numa_cores else None,
-                       "batch_per_gpu": B, "image": f"3x{S}x{S}", "parallelism": f"dp{world} (batch sharding, no collective)",
-                       "l2": "no flush needed: per-step working set (~9 GB of activations, 201 MB input) exceeds the 126 MB L2",
-                       "gflop_per_image": GFLOP_PER_IMAGE_512 * (S * S) / (512 * 512),
-                       "achieved_tflops_whole_step": value / world * GFLOP_PER_IMAGE_512 * (S * S) / (512 * 512) / 1e3},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "latency_b1": lat, "enhance": enh, "clocks": clocks,
+            "config": workload_config(B, S, world),
+            "notes": {"forward": "bf16 NHWC tensor-core forward, fp32 NCHW input resident in HBM, outputs fp32 logits + uint8 masks",
+                      "l2": "no flush needed: per-step working set (~9 GB of activations, 201 MB input) exceeds the 126 MB L2",
+                      "numa_bound_cores_rank0": len(numa_cores) if numa_cores else None,
+                      "achieved_tflops_whole_step": value / world * GFLOP_PER_IMAGE_512 * (S * S) / (512 * 512) / 1e3},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "sharded_512": sharded, "shard_bitident": bitident,
+            "launcher_threads": threads_res, "hires_1024": hires,
+            "run_unet_batch_1080p": (lat or {}).get("run_unet_1080p", {}).get("run_unet_batch_1080p") if lat else None,
+            "latency_b1": lat, "enhance": enh, "clocks": clocks,
             "gpu_launches": launches_per_step * args.steps,
         }
         emit(line)

@@ -66,6 +66,10 @@ typedef struct {
 typedef struct unetb200_handle_s* unetb200_handle_t;
 
 int unetb200_abi_version(void);
+/* Compile-time switches of this build: UNETB200_BUILD_TEST_VARIANTS = the measured-and-rejected kernel variants
+ * (A_COL3 staging, the patch stem) are compiled in (-DUNETB200_TEST_VARIANTS); production builds return 0. */
+#define UNETB200_BUILD_TEST_VARIANTS 1
+int unetb200_build_flags(void);
 const char* unetb200_last_error(void);
 
 /* ---- packed weights: layout + device-side fold/pack (replaces nothing in the

@@ -123,7 +123,10 @@ def test_amodes_agree(model, cuda_dev, amode):
     """The three activation-staging strategies feed the same tiles to the same MMAs.  A_TAP
     and A_HALO also accumulate the nine taps in the same order -> bit-identical logits;
     A_COL3 walks the taps column-major, so it differs by fp32 accumulation order only."""
+    from tw_invoice_unet_ocr_llm_b200 import _native as nat
     from tw_invoice_unet_ocr_llm_b200.synthetic import synthetic_invoices
+    if amode == 1 and not nat.has_test_variants():
+        pytest.skip("A_COL3 is compiled only with UNETB200_TEST_VARIANTS=1")
     x = synthetic_invoices(2, 64, 96, seed=46).to(cuda_dev)
     eng = model.engine(cuda_dev)
     keep = eng.get_option("amode")
@@ -211,16 +214,20 @@ def test_stem_variants_agree(model, cuda_dev):
     x = synthetic_invoices(2, 64, 96, seed=53).to(cuda_dev)
     eng = model.engine(cuda_dev)
     keep = eng.get_option("stem_tc")
+    from tw_invoice_unet_ocr_llm_b200 import _native as nat
+    variants = (0, 1, 2) if nat.has_test_variants() else (0, 1)     # 2 = patch stem, test builds only
     z = {}
     try:
-        for v in (0, 1, 2):
+        for v in variants:
             eng.set_option("stem_tc", v)
             z[v], _ = eng.run(x)
         torch.cuda.synchronize()
     finally:
         eng.set_option("stem_tc", keep)
-    assert (z[1] - z[2]).abs().max().item() < 0.15  # same products, different fp32 summation order
-    assert (z[0] - z[2]).abs().max().item() < 0.15
+    assert (z[0] - z[1]).abs().max().item() < 0.15
+    if 2 in z:
+        assert (z[1] - z[2]).abs().max().item() < 0.15  # same products, different fp32 summation order
+        assert (z[0] - z[2]).abs().max().item() < 0.15
 
 
 def test_u8_input_and_masks(model, fixture_state, cuda_dev):

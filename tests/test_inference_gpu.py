@@ -181,18 +181,30 @@ def test_load_model_is_cached_and_strict(checkpoint, cuda_dev):
     assert next(m1.parameters()).is_cuda
 
 
-def test_run_unet_batch_equals_single(checkpoint, cuda_dev):
+def test_run_unet_batch_equals_single(checkpoint, cuda_dev, monkeypatch):
+    """The pipelined batch entry point (two staging buffers, chunks of MAX_CHUNK, crops on host threads) returns
+    what run_unet returns image by image: masks, crop presence, crop pixels -- across chunk boundaries, for
+    frames of different sizes, a non-RGB mode (host PIL path) and a near-black frame (crops rejected)."""
     from tw_invoice_unet_ocr_llm_b200 import inference as inf
     from tw_invoice_unet_ocr_llm_b200.synthetic import synthetic_invoices_u8
-    frames = synthetic_invoices_u8(3, 300, 400, seed=78)
-    pils = [Image.fromarray(f) for f in frames]
-    batch = inf.run_unet_batch(pils, checkpoint)
-    assert len(batch) == 3
-    for pil, (bm, bc) in zip(pils, batch):
-        sm, sc = inf.run_unet(pil, checkpoint)
-        for k in inf.FIELDS:
-            assert np.array_equal(bm[k], sm[k])
-            assert (bc[k] is None) == (sc[k] is None)
+    pils = [Image.fromarray(f) for f in synthetic_invoices_u8(3, 300, 400, seed=78)]
+    pils += [Image.fromarray(f) for f in synthetic_invoices_u8(2, 480, 640, seed=79)]
+    pils.append(pils[0].convert("RGBA"))
+    pils.append(Image.fromarray((synthetic_invoices_u8(1, 300, 400, seed=80)[0] // 128).astype(np.uint8)))   # near black
+    monkeypatch.setattr(inf, "MAX_CHUNK", 3)
+    for rep in range(2):                              # second pass reuses the staging buffers
+        batch = inf.run_unet_batch(pils, checkpoint)
+        assert len(batch) == len(pils)
+        for pil, (bm, bc) in zip(pils, batch):
+            sm, sc = inf.run_unet(pil, checkpoint)
+            assert list(bm) == inf.FIELDS and list(bc) == inf.FIELDS
+            for k in inf.FIELDS:
+                assert bm[k].dtype == np.bool_ and bm[k].shape == (512, 512)
+                assert np.array_equal(bm[k], sm[k])
+                assert (bc[k] is None) == (sc[k] is None)
+                if bc[k] is not None:
+                    assert bc[k].size == sc[k].size and np.array_equal(np.asarray(bc[k]), np.asarray(sc[k]))
+    assert all(c is None for c in batch[-1][1].values())
     assert inf.run_unet_batch([], checkpoint) == []
 
 

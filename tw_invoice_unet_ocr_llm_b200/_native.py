@@ -54,6 +54,7 @@ class EnhCrop(C.Structure):
 _VP, _I, _U64, _F = C.c_void_p, C.c_int, C.c_uint64, C.c_float
 SYMBOLS = {
     "unetb200_abi_version": (_I, []),
+    "unetb200_build_flags": (_I, []),
     "unetb200_last_error": (C.c_char_p, []),
     "unetb200_num_layers": (_I, [C.POINTER(Arch)]),
     "unetb200_layer_info": (_I, [C.POINTER(Arch), _I, C.POINTER(Layer)]),
@@ -120,6 +121,11 @@ def lib() -> C.CDLL:
                 fn.argtypes = args
             _lib = handle
     return _lib
+
+
+def has_test_variants() -> bool:
+    """True when the library was built with -DUNETB200_TEST_VARIANTS (A_COL3 staging, patch stem)."""
+    return bool(lib().unetb200_build_flags() & 1)
 
 
 def last_error() -> str:

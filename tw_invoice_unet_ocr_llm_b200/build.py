@@ -35,11 +35,17 @@ def up_to_date() -> bool:
     return all(os.path.getmtime(s) <= t for s in sources())
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile every CUDA source into the shared library; returns its path."""
-    if not force and up_to_date():
+def build(force: bool = False, verbose: bool = False, out: str = OUT, defines=()) -> str:
+    """Compile every CUDA source into the shared library; returns its path.  ``UNETB200_TEST_VARIANTS=1`` in the
+    environment (or ``defines=["UNETB200_TEST_VARIANTS"]``) also compiles the measured-and-rejected kernel
+    variants the cross-check tests can exercise (A_COL3 staging, the patch stem)."""
+    defines = list(defines)
+    if os.environ.get("UNETB200_TEST_VARIANTS") == "1" and "UNETB200_TEST_VARIANTS" not in defines:
+        defines.append("UNETB200_TEST_VARIANTS")
+    if out == OUT and not defines and not force and up_to_date():
         return OUT
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", OUT + ".tmp", *sorted(glob.glob(os.path.join(CSRC, "*.cu")))]
+    cmd = [_nvcc(), *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-o", out + ".tmp",
+           *sorted(glob.glob(os.path.join(CSRC, "*.cu")))]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     res = subprocess.run(cmd, capture_output=True, text=True)
@@ -47,8 +53,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
     if verbose:
         sys.stderr.write(res.stderr)
-    os.replace(OUT + ".tmp", OUT)
-    return OUT
+    os.replace(out + ".tmp", out)
+    return out
 
 
 if __name__ == "__main__":

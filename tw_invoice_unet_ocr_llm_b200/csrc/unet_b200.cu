@@ -231,11 +231,16 @@ ConvLaunch conv3_pick_epi(int epi) {
     }
 }
 
+// Production staging is A_HALO; A_TAP (the canonical per-tap staging) stays in every build as its cross-check.
+// A_COL3 and the patch stem (A_STEMP) are measured-and-rejected alternatives: compiled only with
+// -DUNETB200_TEST_VARIANTS (UNETB200_TEST_VARIANTS=1 python -m tw_invoice_unet_ocr_llm_b200.build).
 template <int BN>
 ConvLaunch conv3_pick_amode(int amode, int epi) {
     switch (amode) {
         case ub::A_TAP: return conv3_pick_epi<BN, ub::A_TAP>(epi);
+#ifdef UNETB200_TEST_VARIANTS
         case ub::A_COL3: return conv3_pick_epi<BN, ub::A_COL3>(epi);
+#endif
         case ub::A_HALO: return conv3_pick_epi<BN, ub::A_HALO>(epi);
         default: return ConvLaunch();
     }
@@ -251,6 +256,7 @@ ConvLaunch stem_inst() {
     return l;
 }
 
+#ifdef UNETB200_TEST_VARIANTS
 template <int CIN>
 ConvLaunch stemp_inst() {
     ConvLaunch l;
@@ -260,14 +266,17 @@ ConvLaunch stemp_inst() {
     l.b_tap = ub::ConvCfg<64, 9, ub::A_STEMP>::B_TAP;
     return l;
 }
+#endif
 
 ConvLaunch pick_conv(int taps, int bn, int amode, int epi, int stem_cin = 0, int ncls = 0, bool pair = false) {
     if (amode == ub::A_STEMP) {
+#ifdef UNETB200_TEST_VARIANTS
         switch (stem_cin) {
             case 1: return stemp_inst<1>();
             case 3: return stemp_inst<3>();
             case 4: return stemp_inst<4>();
         }
+#endif
         return ConvLaunch();
     }
     if (pair && amode != ub::A_STEM && amode != ub::A_STEMP && (taps == 1 || amode == ub::A_HALO)) {
@@ -301,7 +310,9 @@ ConvLaunch pick_conv(int taps, int bn, int amode, int epi, int stem_cin = 0, int
         const bool three = ncls == 3;
         switch (amode) {
             case ub::A_TAP: return three ? conv_inst<64, 9, ub::A_TAP, ub::EPI_HEAD, 3>() : conv_inst<64, 9, ub::A_TAP, ub::EPI_HEAD>();
+#ifdef UNETB200_TEST_VARIANTS
             case ub::A_COL3: return three ? conv_inst<64, 9, ub::A_COL3, ub::EPI_HEAD, 3>() : conv_inst<64, 9, ub::A_COL3, ub::EPI_HEAD>();
+#endif
             case ub::A_HALO: return three ? conv_inst<64, 9, ub::A_HALO, ub::EPI_HEAD, 3>() : conv_inst<64, 9, ub::A_HALO, ub::EPI_HEAD>();
         }
         return ConvLaunch();
@@ -451,7 +462,9 @@ int build_conv_step(const ConvDesc& d, int num_sms, Step* st) {
         return fail(UNETB200_EINVAL, "fused head needs cout == 64");
     st->kind = 1;
     st->conv = pick_conv(d.taps, bn, d.amode, d.epi, d.stem_cin, d.ncls, d.pair != 0);
-    if (!st->conv.fn) return fail(UNETB200_EINVAL, "conv: no kernel for this configuration");
+    if (!st->conv.fn)
+        return fail(UNETB200_EINVAL, "conv: no kernel for this configuration (A_COL3 and the patch stem exist only in "
+                                     "builds with -DUNETB200_TEST_VARIANTS)");
     ub::ConvParams& p = st->cp;
     memset(&p, 0, sizeof p);
     int boxW = 8, boxH = 16;
@@ -814,6 +827,13 @@ int build_plan(unetb200_handle_t h, const void* x, int x_fmt, int n, int H, int 
 extern "C" {
 
 int unetb200_abi_version(void) { return UNETB200_ABI_VERSION; }
+int unetb200_build_flags(void) {
+#ifdef UNETB200_TEST_VARIANTS
+    return UNETB200_BUILD_TEST_VARIANTS;
+#else
+    return 0;
+#endif
+}
 const char* unetb200_last_error(void) { return g_err.c_str(); }
 
 int unetb200_num_layers(const unetb200_arch_t* arch) {

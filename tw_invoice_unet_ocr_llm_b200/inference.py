@@ -241,35 +241,120 @@ def _gpu_resizable(pil_img: Image.Image) -> bool:
     return pil_img.mode == "RGB" and pil_img.size[0] > 0 and pil_img.size[1] > 0
 
 
+_pool = None
+_batch_stage: Dict[tuple, list] = {}      # (thread, slot) -> [pinned flat buffer, event of its last upload]
+
+
+def _worker_pool():
+    """Host threads for the byte work of the batched entry point (staging copies, PIL crops); both release
+    the GIL, so a few threads keep one GPU fed."""
+    global _pool
+    if _pool is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _pool = ThreadPoolExecutor(max_workers=max(2, min(8, (os.cpu_count() or 4) // 2)),
+                                   thread_name_prefix="unetb200-host")
+    return _pool
+
+
+def _stage_buffer(slot: int, nbytes: int):
+    """Pinned flat staging buffer ``slot`` (0 / 1, alternating chunks) of this thread, at least ``nbytes``
+    long, free to overwrite: its previous uploads have completed."""
+    key = (threading.get_ident(), slot)
+    ent = _batch_stage.get(key)
+    if ent is not None and ent[1] is not None:
+        ent[1].synchronize()
+    if ent is None or ent[0].numel() < nbytes:
+        if len(_batch_stage) > 8:
+            _batch_stage.clear()
+        ent = _batch_stage[key] = [torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8).pin_memory(), None]
+    return ent
+
+
 def _segment_images(eng, pil_imgs: Sequence[Image.Image]):
-    """Images -> (uint8 masks (B, 3, 512, 512), per-image crops).  Per chunk of ``MAX_CHUNK`` images:
-    plain RGB frames are uploaded raw and resized on the GPU straight into their slot of the batch
-    tensor (other modes: the reference's PIL calls on the host), one forward, one mask -> box reduction,
-    one download; the uploaded frames stay on the device for the near-black crop test."""
+    """Images -> (uint8 0/1 masks (B, 3, 512, 512) on the host, per-image crops), pipelined.
+
+    Per chunk of ``MAX_CHUNK`` images: host threads copy the frames (Pillow's own RGBX buffers where they can
+    be exported without a repack) into one of two pinned staging buffers while the previous chunk is in
+    flight; every frame is uploaded asynchronously and resized on the GPU straight into its slot of the batch
+    tensor (other PIL modes: the reference's PIL calls on the host); one forward, one mask -> box reduction,
+    asynchronous downloads into pinned memory.  Nothing waits for the GPU until every chunk is enqueued; then,
+    chunk by chunk: rectangles on the host (reference :95-112), the near-black test for all rectangles of the
+    chunk on the device frames (one sync), and the ``PIL.crop`` calls on the host threads."""
     from . import prepost
     _require_cuda()
     thr = [THRESHOLDS[f] for f in FIELDS]
-    masks = np.empty((len(pil_imgs), len(FIELDS), IMG_SIZE, IMG_SIZE), dtype=np.uint8)
-    crops = []
-    for lo in range(0, len(pil_imgs), MAX_CHUNK):
+    n_img = len(pil_imgs)
+    masks = torch.empty((n_img, len(FIELDS), IMG_SIZE, IMG_SIZE), dtype=torch.uint8).pin_memory()
+    boxes_host = torch.empty((n_img, len(FIELDS), 5), dtype=torch.int32).pin_memory()
+    pool = _worker_pool()
+    stream = torch.cuda.current_stream()
+    chunks = []                                    # (lo, images, device frames, event after the downloads)
+    for ci, lo in enumerate(range(0, n_img, MAX_CHUNK)):
         chunk = pil_imgs[lo:lo + MAX_CHUNK]
+        views = [_rgb_host_view(im) if _gpu_resizable(im) else None for im in chunk]
+        offs, total = [], 0
+        for v in views:
+            offs.append(total)
+            if v is not None:
+                total += (v.size + 255) & ~255
+        ent = _stage_buffer(ci & 1, total)
+        flat = ent[0]
+        flat_np = flat.numpy()
+
+        def fill(i):
+            v = views[i]
+            np.copyto(flat_np[offs[i]:offs[i] + v.size].reshape(v.shape), v)
+
+        futs = [pool.submit(fill, i) if v is not None else None for i, v in enumerate(views)]
         x = torch.empty((len(chunk), IMG_SIZE, IMG_SIZE, 3), dtype=torch.uint8, device=DEVICE)
         frames = []
-        for i, im in enumerate(chunk):
-            if _gpu_resizable(im):
-                # fresh device copy per image (the pinned staging buffer is reused after the copy lands)
-                f = _upload_rgb(im, wait=True)
-                prepost.resize_u8(f, IMG_SIZE, IMG_SIZE, out=x[i:i + 1], channels=3)
-                frames.append(f[0])
+        for i, (im, v) in enumerate(zip(chunk, views)):
+            if v is not None:
+                futs[i].result()
+                f = flat[offs[i]:offs[i] + v.size].view(v.shape).to(DEVICE, non_blocking=True)
+                prepost.resize_u8(f[None], IMG_SIZE, IMG_SIZE, out=x[i:i + 1], channels=3)
+                frames.append(f)
             else:
                 x[i].copy_(torch.from_numpy(_resized_rgb_u8(im.resize((IMG_SIZE, IMG_SIZE)))))
                 frames.append(None)
+        ent[1] = torch.cuda.Event()
+        ent[1].record(stream)                      # this staging buffer is reusable once its uploads are done
         _, mask = eng.run(x, want_logits=False, thresholds=thr)
-        boxes = prepost.mask_bbox(mask).cpu().numpy()
-        masks[lo:lo + len(chunk)] = mask.cpu().numpy()
-        for im, bx, f in zip(chunk, boxes, frames):
-            crops.append(boxes_to_crops(im, bx, f))
-    return masks, crops
+        masks[lo:lo + len(chunk)].copy_(mask, non_blocking=True)
+        boxes_host[lo:lo + len(chunk)].copy_(prepost.mask_bbox(mask), non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(stream)
+        chunks.append((lo, chunk, frames, done))
+
+    crops: list = [None] * n_img
+    bx_all = boxes_host.numpy()
+    for lo, chunk, frames, done in chunks:
+        done.synchronize()
+        rects = [[_crop_rect(im.size, _extent(bx_all[lo + i, k])) for k in range(len(FIELDS))]
+                 for i, im in enumerate(chunk)]
+        sums = []
+        for i, f in enumerate(frames):             # near-black sums of every live rectangle, enqueued together
+            live = [r for r in rects[i] if r is not None]
+            sums.append(prepost.box_sums(f, live, channels=3) if (f is not None and live) else None)
+        sums_host = [None if t is None else t.cpu().tolist() for t in sums]      # first .cpu() waits for all
+
+        def cut(i):
+            im, out, tot = chunk[i], {}, (list(sums_host[i]) if sums_host[i] is not None else None)
+            for key, r in zip(FIELDS, rects[i]):
+                if r is None:
+                    out[key] = None
+                elif tot is None:                  # frame not on the device: the host test of the reference
+                    c = im.crop(r)
+                    arr = np.array(c)
+                    out[key] = None if (arr.size == 0 or arr.mean() < 3) else c
+                else:
+                    total = tot.pop(0)
+                    out[key] = None if total < 3 * (r[2] - r[0]) * (r[3] - r[1]) * 3 else im.crop(r)
+            return out
+
+        for i, res in enumerate(pool.map(cut, range(len(chunk)))):
+            crops[lo + i] = res
+    return masks.numpy(), crops
 
 
 def run_unet(pil_img: Image.Image, checkpoint_path: str):
@@ -341,4 +426,5 @@ def run_unet_batch(pil_imgs: Sequence[Image.Image], checkpoint_path: str
     _require_cuda()
     _, eng = _cached_engine(checkpoint_path)
     m, crops = _segment_images(eng, list(pil_imgs))
-    return [({f: m[b, i] != 0 for i, f in enumerate(FIELDS)}, crops[b]) for b in range(len(pil_imgs))]
+    mb = m.view(np.bool_)          # the kernel writes exactly 0 / 1: the boolean planes without another pass
+    return [({f: mb[b, i] for i, f in enumerate(FIELDS)}, crops[b]) for b in range(len(pil_imgs))]
