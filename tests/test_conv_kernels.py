@@ -109,6 +109,69 @@ def test_conv3x3_two_sources_and_pool(cuda_dev, amode, pair):
     assert torch.equal(_to_nchw_f32(pool), F.max_pool2d(_to_nchw_f32(out), 2))
 
 
+A_ROW = 5      # conv_row.cuh: the row-stacked kernel of the 64-output-channel convs
+
+
+@pytest.mark.parametrize("cin,n,h,w", [
+    (64, 2, 32, 24),        # one K slice, one x tile (partial: 24 of 128 pixels)
+    (128, 1, 32, 32),       # two K slices (conv1.net.0's depth)
+    (128, 1, 20, 12),       # partial tiles in both directions
+    (64, 3, 2, 2),          # smaller than one tile in both directions, H not a multiple of 4
+    (64, 1, 8, 300),        # three x tiles, the last one partial
+    (64, 2, 6, 130),        # H = 6: second row block half empty; x tile boundary at 128
+    (128, 1, 64, 256),      # many tiles per CTA: accumulator / ring wrap-around
+])
+def test_conv3x3_row_kernel(cuda_dev, cin, n, h, w):
+    """The row-stacked 64-channel conv (N = 192 UMMAs over the three ky taps) against F.conv2d, and bit for
+    bit against the tap-per-UMMA kernel (same K order per output element)."""
+    nat = _nat()
+    cout = 64
+    g = torch.Generator(device="cpu").manual_seed(cin * 3 + h + w)
+    x = torch.randn((n, cin, h, w), generator=g).to(cuda_dev)
+    wt = (torch.randn((cout, cin, 3, 3), generator=g) / (3.0 * cin ** 0.5)).to(cuda_dev)
+    b = torch.randn((cout,), generator=g).to(cuda_dev)
+    xb, wb = _nhwc_bf16(x), _pack3x3(wt)
+    outs = {}
+    for amode in (A_ROW, 2):
+        out = torch.full((n, h, w, cout), float("nan"), dtype=torch.bfloat16, device=cuda_dev)
+        nat.check(nat.lib().unetb200_conv3x3(xb.data_ptr(), cin, None, 0, wb.data_ptr(), b.data_ptr(),
+                                             n, h, w, cout, 1, out.data_ptr(), None, 64, amode, 1, None))
+        torch.cuda.synchronize()
+        outs[amode] = out
+    ref = F.relu(F.conv2d(_to_nchw_f32(xb), wb.float().reshape(3, 3, cout, cin).permute(2, 3, 0, 1), b, padding=1))
+    _close(_to_nchw_f32(outs[A_ROW]), ref, "row-stacked conv3x3")
+    assert torch.equal(outs[A_ROW], outs[2]), "row-stacked kernel differs from the tap-per-UMMA kernel"
+
+
+@pytest.mark.parametrize("n,h,w", [(2, 32, 16), (1, 64, 384), (3, 4, 258)])
+def test_conv3x3_row_two_sources_and_pool(cuda_dev, n, h, w):
+    """Row kernel: cat([up, skip]) as two K ranges (conv1.net.0) and the fused 2x2 max-pool (down1.net.3)."""
+    nat = _nat()
+    c0, c1, cout = 64, 64, 64
+    g = torch.Generator(device="cpu").manual_seed(7 + w)
+    x0 = torch.randn((n, c0, h, w), generator=g).to(cuda_dev)
+    x1 = torch.randn((n, c1, h, w), generator=g).to(cuda_dev)
+    wt = (torch.randn((cout, c0 + c1, 3, 3), generator=g) / (3.0 * (c0 + c1) ** 0.5)).to(cuda_dev)
+    b = torch.randn((cout,), generator=g).to(cuda_dev)
+    x0b, x1b, wb = _nhwc_bf16(x0), _nhwc_bf16(x1), _pack3x3(wt)
+    out = torch.full((n, h, w, cout), float("nan"), dtype=torch.bfloat16, device=cuda_dev)
+    pool = torch.full((n, h // 2, w // 2, cout), float("nan"), dtype=torch.bfloat16, device=cuda_dev)
+    nat.check(nat.lib().unetb200_conv3x3(x0b.data_ptr(), c0, x1b.data_ptr(), c1, wb.data_ptr(),
+                                         b.data_ptr(), n, h, w, cout, 1, out.data_ptr(),
+                                         pool.data_ptr(), 64, A_ROW, 1, None))
+    torch.cuda.synchronize()
+    xin = torch.cat([_to_nchw_f32(x0b), _to_nchw_f32(x1b)], dim=1)
+    ref = F.relu(F.conv2d(xin, wb.float().reshape(3, 3, cout, c0 + c1).permute(2, 3, 0, 1), b, padding=1))
+    _close(_to_nchw_f32(out), ref, "row kernel, two sources")
+    assert torch.equal(_to_nchw_f32(pool), F.max_pool2d(_to_nchw_f32(out), 2))
+    # without the pool output the plain-store epilogue must give the same tensor
+    out2 = torch.full_like(out, float("nan"))
+    nat.check(nat.lib().unetb200_conv3x3(x0b.data_ptr(), c0, x1b.data_ptr(), c1, wb.data_ptr(),
+                                         b.data_ptr(), n, h, w, cout, 1, out2.data_ptr(), None, 64, A_ROW, 1, None))
+    torch.cuda.synchronize()
+    assert torch.equal(out, out2)
+
+
 @pytest.mark.parametrize("pair", [0, 1])
 @pytest.mark.parametrize("cin,cout,bn", [(128, 64, 128), (256, 128, 64), (128, 64, 256)])
 def test_convt2x2(cuda_dev, cin, cout, bn, pair):
@@ -201,7 +264,7 @@ def test_stem_tensor_core(cuda_dev, fmt, n, h, w, variant):
 
 
 @pytest.mark.parametrize("pair", [0, 1])
-@pytest.mark.parametrize("amode", AMODES)
+@pytest.mark.parametrize("amode", AMODES + [5])
 def test_conv3x3_head(cuda_dev, amode, pair):
     """conv1.net.3 + out_conv 1x1 + logit-space threshold in one kernel (unet_model.py:86,
     inference.py:72-79)."""
@@ -209,7 +272,7 @@ def test_conv3x3_head(cuda_dev, amode, pair):
     if pair and amode != 2:
         pytest.skip("CTA-pair kernels are instantiated for A_HALO only")
     _need_variant(amode)
-    n, h, w, ncls = 2, 32, 32, 3
+    n, h, w, ncls = (2, 32, 32, 3) if amode != 5 else (2, 24, 176, 3)     # row kernel: two x tiles, the second partial
     g = torch.Generator(device="cpu").manual_seed(3)
     x = torch.randn((n, 64, h, w), generator=g).to(cuda_dev)
     wt = (torch.randn((64, 64, 3, 3), generator=g) / 24.0).to(cuda_dev)
@@ -230,3 +293,11 @@ def test_conv3x3_head(cuda_dev, amode, pair):
     assert err < 2e-3, f"fused head logits max err {err}"
     thr_t = torch.tensor(list(thr), device=cuda_dev).view(1, ncls, 1, 1)
     assert torch.equal(mask, (logits > thr_t).to(torch.uint8)), "mask != (logits > thr)"
+    # bit-packed masks (flag bit 2): pixel x = bit x & 7 of byte x >> 3
+    bits = torch.full((n, ncls, h, w // 8), 0xAA, dtype=torch.uint8, device=cuda_dev)
+    nat.check(nat.lib().unetb200_conv3x3_head(xb.data_ptr(), 64, wb.data_ptr(), b.data_ptr(),
+                                              hw.data_ptr(), hb.data_ptr(), ncls, n, h, w,
+                                              None, bits.data_ptr(), thr, amode, 1 | (pair << 1) | 4, None))
+    torch.cuda.synchronize()
+    from tw_invoice_unet_ocr_llm_b200.engine import unpack_mask_bits
+    assert torch.equal(unpack_mask_bits(bits), mask), "bit-packed mask != byte mask"

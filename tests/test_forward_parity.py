@@ -180,6 +180,29 @@ def test_cta_pairs_identical(model, cuda_dev):
     assert torch.equal(z0, z1)
 
 
+def test_row_kernel_forward_identical(model, cuda_dev):
+    """The three 64-channel 3x3 convs (down1.net.3 + pool, conv1.net.0, conv1.net.3 + head) on the row-stacked
+    kernel accumulate every output element in the same K order as the tap-per-UMMA kernel: bit-identical
+    logits and masks, for each subset of the layers."""
+    from tw_invoice_unet_ocr_llm_b200.synthetic import synthetic_invoices
+    eng = model.engine(cuda_dev)
+    keep = eng.get_option("row64")
+    thr = [0.25, 0.40, 0.30]
+    try:
+        for n, h, w in [(2, 64, 96), (1, 512, 512), (3, 48, 272)]:
+            x = synthetic_invoices(n, h, w, seed=57).to(cuda_dev)
+            res = {}
+            for mode in (0, 1, 2, 3):
+                eng.set_option("row64", mode)
+                res[mode] = eng.run(x, thresholds=thr)
+            torch.cuda.synchronize()
+            for mode in (1, 2, 3):
+                assert torch.equal(res[0][0], res[mode][0]), (n, h, w, mode)
+                assert torch.equal(res[0][1], res[mode][1]), (n, h, w, mode)
+    finally:
+        eng.set_option("row64", keep)
+
+
 def test_fill_sms_policy_identical(model, cuda_dev):
     """Small batches narrow the column block of the deep layers so their tiles cover the SMs (batch-1
     latency); every output element still accumulates over K in the same order: bit-identical logits, and

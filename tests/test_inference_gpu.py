@@ -192,8 +192,8 @@ def test_run_unet_batch_equals_single(checkpoint, cuda_dev, monkeypatch):
     pils.append(pils[0].convert("RGBA"))
     pils.append(Image.fromarray((synthetic_invoices_u8(1, 300, 400, seed=80)[0] // 128).astype(np.uint8)))   # near black
     monkeypatch.setattr(inf, "MAX_CHUNK", 3)
-    for rep in range(2):                              # second pass reuses the staging buffers
-        batch = inf.run_unet_batch(pils, checkpoint)
+    for rep in range(3):                              # later passes reuse the staging buffers; last one: crop views
+        batch = inf.run_unet_batch(pils, checkpoint, crop_views=rep == 2)
         assert len(batch) == len(pils)
         for pil, (bm, bc) in zip(pils, batch):
             sm, sc = inf.run_unet(pil, checkpoint)
@@ -203,7 +203,8 @@ def test_run_unet_batch_equals_single(checkpoint, cuda_dev, monkeypatch):
                 assert np.array_equal(bm[k], sm[k])
                 assert (bc[k] is None) == (sc[k] is None)
                 if bc[k] is not None:
-                    assert bc[k].size == sc[k].size and np.array_equal(np.asarray(bc[k]), np.asarray(sc[k]))
+                    assert bc[k].mode == sc[k].mode and bc[k].size == sc[k].size
+                    assert np.array_equal(np.asarray(bc[k]), np.asarray(sc[k])) and bc[k].tobytes() == sc[k].tobytes()
     assert all(c is None for c in batch[-1][1].values())
     assert inf.run_unet_batch([], checkpoint) == []
 

@@ -68,7 +68,7 @@
 namespace ub {
 
 enum : int { EPI_STORE = 0, EPI_STORE_POOL = 1, EPI_HEAD = 2, EPI_UPSAMPLE = 3 };
-enum : int { A_TAP = 0, A_COL3 = 1, A_HALO = 2, A_STEM = 3, A_STEMP = 4 };
+enum : int { A_TAP = 0, A_COL3 = 1, A_HALO = 2, A_STEM = 3, A_STEMP = 4, A_ROW = 5 /* conv_row.cuh */ };
 
 constexpr int kMaxClasses = 8;
 
@@ -131,6 +131,11 @@ struct ConvParams {
     const void* stem_x;      // A_STEM / A_STEMP: network input (format stem_fmt), see stem.cuh
     int stem_fmt;
     const void* stem_w;      // A_STEMP: weights already in the smem tile layout (pack.cuh), 9 x 4096 B
+    // conv_row.cuh: the layer's 64 bias values and the 1x1 head as KERNEL PARAMETERS, so the epilogue reads them
+    // as constant-bank operands of its FADD / FFMA instead of through shared-memory loads
+    float bias_c[64];
+    float head_wc[kMaxClasses * 64];
+    float head_bc[kMaxClasses];
 };
 
 template <int BN, int TAPS, int AMODE, bool PAIR = false>
@@ -153,7 +158,7 @@ constexpr int kOutStage = 16384;      // 128 pixels x 64 channels bf16
 constexpr int kPoolStage = 4096;      // 32 pixels x 64 channels bf16
 constexpr int kMaxRing = 8;           // upper bound on na and (non-stationary) nb
 constexpr int kBarBytes = 1024;
-constexpr int kStaticSmem = 4096 + kMaxClasses * 64 * 4 + 64;   // s_bias + s_head_w + s_head_b
+constexpr int kStaticSmem = 4096 + 64;   // s_bias (+ margin)
 constexpr int kSmemLimit = 232448;    // 227 KB per CTA on sm_100
 
 // X: A_STEM -> n_channels of the network input; EPI_HEAD -> n_classes (0 = generic, up to 8).
@@ -189,8 +194,6 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));   // generic view of smem_base
 
     __shared__ __align__(16) float s_bias[1024];
-    __shared__ __align__(16) float s_head_w[kMaxClasses * 64];
-    __shared__ float s_head_b[kMaxClasses];
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -218,11 +221,6 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
     }
     if (warp == 2) {
         if (PAIR) tmem_alloc_pair<Cfg::TMEM_COLS>(s_tmem_ptr); else tmem_alloc<Cfg::TMEM_COLS>(s_tmem_ptr);
-    }
-    if (EPI == EPI_HEAD) {
-        for (int i = threadIdx.x; i < kMaxClasses * 64; i += blockDim.x)
-            s_head_w[i] = i < p.ncls * 64 ? p.head_w[i] : 0.f;
-        if (threadIdx.x < kMaxClasses) s_head_b[threadIdx.x] = threadIdx.x < p.ncls ? p.head_b[threadIdx.x] : 0.f;
     }
     for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) s_bias[i] = p.bias[i];
     tc_fence_before();
@@ -689,7 +687,7 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
         // BN == 64 launches (one 64-column chunk per tile, in production a single column block): the
         // chunk's 64 bias values live in registers and are reloaded only when the channel offset
         // changes (the thin-K epilogues stalled on their shared-memory loads)
-        constexpr bool kBiasRegs = BN == 64 && AMODE != A_STEM && AMODE != A_STEMP;   // (the 640-thread stem has 102 registers per thread)
+        constexpr bool kBiasRegs = BN == 64 && AMODE != A_STEM && AMODE != A_STEMP && EPI != EPI_HEAD;   // (the 640-thread stem has 102 registers per thread; the head reads its bias as kernel parameters)
         float bias_r[kBiasRegs ? 64 : 1];
         int bias_ch0 = -1;
         auto load_bias = [&](int ch0) {
@@ -720,13 +718,13 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
             const uint32_t t_addr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
 
             if (EPI == EPI_HEAD) {
-                load_bias(0);
-                // out_conv 1x1 (unet_model.py:86) from the fp32 accumulators, NC classes at once;
-                // s_head_w rows past n_classes are zero so the generic variant needs no predicates
+                // out_conv 1x1 (unet_model.py:86) from the fp32 accumulators, NC classes at once.  Bias and head
+                // weights are kernel parameters (ConvParams::bias_c / head_wc / head_bc, zero past n_classes): every
+                // use below is a constant-bank operand -- no registers, no shared-memory loads in the FFMA stream
                 constexpr int NC = X > 0 ? X : kMaxClasses;
                 float z[NC];
 #pragma unroll
-                for (int c = 0; c < NC; ++c) z[c] = s_head_b[c];
+                for (int c = 0; c < NC; ++c) z[c] = p.head_bc[c];
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
                     uint32_t v[32];
@@ -734,12 +732,10 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
                     tmem_ld_wait();
 #pragma unroll
                     for (int i = 0; i < 32; i += 4) {
-                        const float4 b4 = make_float4(bias_r[half * 32 + i], bias_r[half * 32 + i + 1],
-                                                      bias_r[half * 32 + i + 2], bias_r[half * 32 + i + 3]);
-                        float f0 = __uint_as_float(v[i + 0]) + b4.x;
-                        float f1 = __uint_as_float(v[i + 1]) + b4.y;
-                        float f2 = __uint_as_float(v[i + 2]) + b4.z;
-                        float f3 = __uint_as_float(v[i + 3]) + b4.w;
+                        float f0 = __uint_as_float(v[i + 0]) + p.bias_c[half * 32 + i];
+                        float f1 = __uint_as_float(v[i + 1]) + p.bias_c[half * 32 + i + 1];
+                        float f2 = __uint_as_float(v[i + 2]) + p.bias_c[half * 32 + i + 2];
+                        float f3 = __uint_as_float(v[i + 3]) + p.bias_c[half * 32 + i + 3];
                         if (p.relu) {
                             f0 = fmaxf(f0, 0.f);
                             f1 = fmaxf(f1, 0.f);
@@ -748,11 +744,11 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
                         }
 #pragma unroll
                         for (int c = 0; c < NC; ++c) {
-                            const float4 w4 = *reinterpret_cast<const float4*>(s_head_w + c * 64 + half * 32 + i);
-                            z[c] = fmaf(f0, w4.x, z[c]);
-                            z[c] = fmaf(f1, w4.y, z[c]);
-                            z[c] = fmaf(f2, w4.z, z[c]);
-                            z[c] = fmaf(f3, w4.w, z[c]);
+                            const int k0 = c * 64 + half * 32 + i;
+                            z[c] = fmaf(f0, p.head_wc[k0], z[c]);
+                            z[c] = fmaf(f1, p.head_wc[k0 + 1], z[c]);
+                            z[c] = fmaf(f2, p.head_wc[k0 + 2], z[c]);
+                            z[c] = fmaf(f3, p.head_wc[k0 + 3], z[c]);
                         }
                     }
                 }

@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "conv_tc.cuh"
+#include "conv_row.cuh"
 #include "errors.h"
 #include "pack.cuh"
 #include "prepost.cuh"
@@ -197,6 +198,7 @@ struct ConvLaunch {
     int b_tap = 0, tpb = 1;         // bytes of one tap's weight tile, taps per stage (= per TMA box)
     int smem = 0;                   // dynamic shared memory of this launch (set by plan_smem)
     bool pair = false;              // launched as clusters of 2 CTAs (cta_group::2)
+    bool row = false;               // conv_row_kernel (conv_row.cuh): 4 x 128 tiles, ky taps stacked along N
 };
 
 template <int BN, int TAPS, int AMODE, int EPI, int X = 0, bool PAIR = false>
@@ -420,7 +422,94 @@ int plan_smem(ConvLaunch* cl, ub::ConvParams* p, int taps, int n_cs, int n_block
     return 0;
 }
 
+// Row-stacked kernel for the 64-output-channel 3x3 convs (conv_row.cuh).
+int build_row_step(const ConvDesc& d, int num_sms, Step* st) {
+    if (d.taps != 9 || d.cout != 64) return fail(UNETB200_EINVAL, "row kernel: 3x3 conv with 64 output channels only");
+    if (d.c0 <= 0 || d.c0 % 64 || d.c1 % 64 || d.c1 < 0)
+        return fail(UNETB200_EINVAL, "conv: source channels must be multiples of 64");
+    const int n_cs = (d.c0 + d.c1) / 64;
+    st->kind = 1;
+    ConvLaunch& cl = st->conv;
+    cl = ConvLaunch();
+    cl.row = true;
+    switch (d.epi) {
+        case ub::EPI_STORE: cl.fn = ub::conv_row_kernel<ub::EPI_STORE>; break;
+        case ub::EPI_STORE_POOL: cl.fn = ub::conv_row_kernel<ub::EPI_STORE_POOL>; break;
+        case ub::EPI_HEAD: cl.fn = d.ncls == 3 ? ub::conv_row_kernel<ub::EPI_HEAD, 3> : ub::conv_row_kernel<ub::EPI_HEAD, 0>; break;
+        default: return fail(UNETB200_EINVAL, "row kernel: unsupported epilogue");
+    }
+    ub::ConvParams& p = st->cp;
+    memset(&p, 0, sizeof p);
+    int rc;
+    if ((rc = make_act_map(&p.tmA0, d.src0, d.c0, d.wd, d.h, d.n, ub::kRowW + 2, 1))) return rc;
+    if (d.c1 > 0) {
+        if ((rc = make_act_map(&p.tmA1, d.src1, d.c1, d.wd, d.h, d.n, ub::kRowW + 2, 1))) return rc;
+    } else {
+        p.tmA1 = p.tmA0;
+    }
+    if ((rc = make_w_map(&p.tmB, d.w, d.c0 + d.c1, 64, 9, 64, 1))) return rc;
+    if (d.epi != ub::EPI_HEAD) {
+        if ((rc = make_act_map(&p.tmOut[0], d.out, 64, d.wd, d.h, d.n, 32, 1))) return rc;   // one warp's 32 pixels of a row
+        for (int i = 1; i < 4; ++i) p.tmOut[i] = p.tmOut[0];
+    }
+    if (d.epi == ub::EPI_STORE_POOL) {
+        if (!d.pool) return fail(UNETB200_EINVAL, "pool output missing");
+        if ((rc = make_act_map(&p.tmPool, d.pool, 64, d.wd / 2, d.h / 2, d.n, 16, 1))) return rc;
+    } else {
+        p.tmPool = p.tmA0;
+    }
+    p.bias = d.bias; p.head_w = d.head_w; p.head_b = d.head_b; p.logits = d.logits; p.mask = d.mask;
+    p.mask_bits = d.mask_bits; p.dbg = d.dbg;
+    // bias / head weights travel as kernel parameters (constant bank): one small synchronous read-back per plan
+    UB_CUDA(cudaMemcpy(p.bias_c, d.bias, sizeof p.bias_c, cudaMemcpyDeviceToHost));
+    if (d.epi == ub::EPI_HEAD) {
+        if (!d.head_w || !d.head_b || d.ncls < 1 || d.ncls > ub::kMaxClasses)
+            return fail(UNETB200_EINVAL, "row kernel: head weights missing");
+        UB_CUDA(cudaMemcpy(p.head_wc, d.head_w, sizeof(float) * 64 * d.ncls, cudaMemcpyDeviceToHost));
+        UB_CUDA(cudaMemcpy(p.head_bc, d.head_b, sizeof(float) * d.ncls, cudaMemcpyDeviceToHost));
+    }
+    p.C0 = d.c0; p.C1 = d.c1; p.H = d.h; p.W = d.wd; p.NIMG = d.n; p.Cout = 64;
+    p.tiles_x = (d.wd + ub::kRowW - 1) / ub::kRowW;
+    p.tiles_y = (d.h + ub::kRowR - 1) / ub::kRowR;
+    p.n_blocks = 1;
+    const long long total = 1LL * p.tiles_x * p.tiles_y * d.n;
+    if (total > 0x7fffffffLL) return fail(UNETB200_EINVAL, "conv: too many tiles");
+    p.total_tiles = static_cast<int>(total);
+    p.relu = d.relu; p.ncls = d.ncls; p.wstat = 1;
+    // shared memory: [A ring][resident weights][row staging][pool staging][barriers]
+    const int budget = ub::kSmemLimit - ub::kRowStatic - 1024 /*alignment slack*/ - ub::kBarBytes;
+    const int slab = n_cs * 9 * ub::kRowBBlock;
+    int n_epi = 2, n_out = 0, pool_bytes = 0;
+    if (d.epi == ub::EPI_STORE) n_out = 2;
+    if (d.epi == ub::EPI_STORE_POOL) { n_out = 2; pool_bytes = 8192; }          // two rows + one pooled row per group
+    auto staging = [&]() { return n_epi * (n_out * ub::kOutStage + pool_bytes); };
+    // prefer activation ring depth over staging: at least 4 halo rows in flight
+    while (d.epi == ub::EPI_STORE && (budget - slab - staging()) / ub::kRowAStage < 4 && (n_out > 1 || n_epi > 1)) {
+        if (n_out > 1) n_out = 1; else n_epi = 1;
+    }
+    while (d.epi == ub::EPI_STORE_POOL && (budget - slab - staging()) / ub::kRowAStage < 4 && n_epi > 1) n_epi = 1;
+    int na = (budget - slab - staging()) / ub::kRowAStage;
+    if (na > ub::kMaxRing) na = ub::kMaxRing;
+    if (na < 2) return fail(UNETB200_EINVAL, "row kernel: shared memory plan does not fit");
+    p.na = na; p.nb = n_cs * 9; p.n_out = n_out ? n_out : 1; p.n_epi = n_epi;
+    p.off_b = na * ub::kRowAStage;
+    p.off_out = p.off_b + slab;
+    p.off_pool = p.off_out + n_epi * n_out * ub::kOutStage;
+    p.off_bar = p.off_pool + n_epi * pool_bytes;
+    cl.smem = p.off_bar + ub::kBarBytes + 1024;
+    cl.a_stage = ub::kRowAStage; cl.b_tap = ub::kRowBBlock; cl.b_stage = ub::kRowBBlock;
+    p.fd_tpi = ub::make_fastdiv(static_cast<uint32_t>(p.tiles_x * p.tiles_y));
+    p.fd_tx = ub::make_fastdiv(static_cast<uint32_t>(p.tiles_x));
+    p.fd_nb = ub::make_fastdiv(1u);
+    p.fd_na = ub::make_fastdiv(static_cast<uint32_t>(na));
+    p.fd_nout = ub::make_fastdiv(static_cast<uint32_t>(p.n_out));
+    st->grid = dim3(static_cast<unsigned>(total < num_sms ? total : num_sms));
+    st->block = dim3(384);
+    return 0;
+}
+
 int build_conv_step(const ConvDesc& d, int num_sms, Step* st) {
+    if (d.amode == ub::A_ROW) return build_row_step(d, num_sms, st);
     const bool stemp = d.amode == ub::A_STEMP;
     const bool stem = d.amode == ub::A_STEM || stemp;
     if (d.c0 <= 0 || d.c0 % 64 || d.c1 % 64 || d.c1 < 0)
@@ -517,6 +606,15 @@ int build_conv_step(const ConvDesc& d, int num_sms, Step* st) {
     p.bias = d.bias;
     p.head_w = d.head_w;
     p.head_b = d.head_b;
+    if (d.epi == ub::EPI_HEAD) {
+        // the head epilogue reads bias and 1x1 weights as kernel parameters (constant bank): one small
+        // synchronous read-back per plan
+        if (!d.head_w || !d.head_b || d.ncls < 1 || d.ncls > ub::kMaxClasses)
+            return fail(UNETB200_EINVAL, "fused head: weights missing");
+        UB_CUDA(cudaMemcpy(p.bias_c, d.bias, sizeof p.bias_c, cudaMemcpyDeviceToHost));
+        UB_CUDA(cudaMemcpy(p.head_wc, d.head_w, sizeof(float) * 64 * d.ncls, cudaMemcpyDeviceToHost));
+        UB_CUDA(cudaMemcpy(p.head_bc, d.head_b, sizeof(float) * d.ncls, cudaMemcpyDeviceToHost));
+    }
     p.logits = d.logits;
     p.mask = d.mask;
     p.mask_bits = d.mask_bits;
@@ -569,7 +667,7 @@ int launch_step(Step& st, cudaStream_t stream) {
             if (it == configured.end() || !(it->second & (1 << dev))) {
                 UB_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(st.conv.fn),
                                              cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             ub::kSmemLimit - ub::kStaticSmem));
+                                             ub::kSmemLimit - (st.conv.row ? ub::kRowStatic : ub::kStaticSmem)));
                 configured[reinterpret_cast<const void*>(st.conv.fn)] |= (1 << dev);
             }
         }
@@ -687,6 +785,7 @@ struct unetb200_handle_s {
     int pair = 2;               // CTA pairs (cta_group::2): 0 = never, 1 = wherever instantiated, 2 = where measured faster
     int pdl = 1;                // programmatic dependent launch between the layers of one forward
     int fill_sms = 1;           // narrow the column block of launches whose tiles do not cover the SMs (small batches)
+    int row64 = 0;              // 64-output-channel 3x3 convs on the row-stacked kernel (conv_row.cuh)
     int profile = 0;
     int* dbg = nullptr;         // pinned, device-visible watchdog record
     std::map<PlanKey, Plan> plans;
@@ -743,6 +842,7 @@ int build_plan(unetb200_handle_t h, const void* x, int x_fmt, int n, int H, int 
         d.relu = 1; d.taps = 9; d.epi = pool ? ub::EPI_STORE_POOL : ub::EPI_STORE;
         d.out = out; d.pool = pool;
         d.bn = h->bn_max; d.amode = h->amode; d.wstat = h->wstat; d.pf_items = h->pf_items; d.epi2 = h->epi2; d.min_na = h->min_na; d.dbg = h->dbg; d.fill_sms = h->fill_sms;
+        if (d.cout == 64 && (h->row64 & (c1 > 0 ? 2 : 1))) d.amode = ub::A_ROW;   // bit 0: one-slice layers, bit 1: conv1.net.0
         // measured on B200 (profiles/): CTA pairs win or tie on every 3x3 conv, lose slightly on the up-convs
         d.pair = h->pair >= 1;
         Step st;
@@ -811,7 +911,7 @@ int build_plan(unetb200_handle_t h, const void* x, int x_fmt, int n, int H, int 
             d.n = n; d.h = H; d.wd = W; d.cout = bw; d.relu = 1; d.taps = 9; d.epi = ub::EPI_HEAD;
             d.head_w = reinterpret_cast<const float*>(Wp(22)); d.head_b = Bp(22);
             d.ncls = h->arch.n_classes; d.logits = logits; d.mask = mask; d.mask_bits = mask_bits;
-            d.bn = 64; d.amode = h->amode; d.wstat = h->wstat; d.pf_items = h->pf_items; d.epi2 = h->epi2; d.min_na = h->min_na; d.pair = h->pair >= 1; d.dbg = h->dbg;
+            d.bn = 64; d.amode = (h->row64 & 1) ? ub::A_ROW : h->amode; d.wstat = h->wstat; d.pf_items = h->pf_items; d.epi2 = h->epi2; d.min_na = h->min_na; d.pair = h->pair >= 1; d.dbg = h->dbg;
             Step st;
             if ((rc = build_conv_step(d, h->num_sms, &st))) return rc;
             st.layer = 21;
@@ -953,6 +1053,8 @@ int unetb200_create(const unetb200_arch_t* arch, const void* blob_dev, uint64_t 
     if (env) h->pf_items = atoi(env);
     env = getenv("UNETB200_STEM_TC");
     if (env) h->stem_tc = atoi(env);
+    env = getenv("UNETB200_ROW64");
+    if (env) h->row64 = atoi(env) & 3;
     *out = h;
     return 0;
 }
@@ -997,6 +1099,9 @@ int unetb200_set_option(unetb200_handle_t h, const char* key, int value) {
     } else if (k == "fill_sms") {
         if (value < 0 || value > 2) return fail(UNETB200_EINVAL, "fill_sms must be 0, 1 or 2");
         h->fill_sms = value;                 // 2 = also the up-convs (measured: no gain at batch 1-4)
+    } else if (k == "row64") {
+        if (value < 0 || value > 3) return fail(UNETB200_EINVAL, "row64 must be 0..3 (bit 0: Cin = 64 layers, bit 1: conv1.net.0)");
+        h->row64 = value;
     } else if (k == "profile") {
         h->profile = value ? 1 : 0;
     } else {
@@ -1019,6 +1124,7 @@ int unetb200_get_option(unetb200_handle_t h, const char* key, int* value) {
     else if (k == "pair") *value = h->pair;
     else if (k == "pdl") *value = h->pdl;
     else if (k == "fill_sms") *value = h->fill_sms;
+    else if (k == "row64") *value = h->row64;
     else if (k == "profile") *value = h->profile;
     else if (k == "num_sms") *value = h->num_sms;
     else return fail(UNETB200_EINVAL, "unknown option " + k);

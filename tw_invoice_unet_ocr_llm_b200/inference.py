@@ -242,7 +242,10 @@ def _gpu_resizable(pil_img: Image.Image) -> bool:
 
 
 _pool = None
-_batch_stage: Dict[tuple, list] = {}      # (thread, slot) -> [pinned flat buffer, event of its last upload]
+_batch_state: Dict[tuple, dict] = {}      # (thread, device) -> staging ring + side streams of the batched entry point
+_TRACE = None             # set to a list to collect (label, seconds since call start) marks of the batched entry point
+PIPE_GROUP = 16           # images per pipeline stage of the batched entry point (one forward each)
+STAGE_SLOTS = 3           # pinned staging buffers in flight (fill / upload / reuse)
 
 
 def _worker_pool():
@@ -256,104 +259,184 @@ def _worker_pool():
     return _pool
 
 
-def _stage_buffer(slot: int, nbytes: int):
-    """Pinned flat staging buffer ``slot`` (0 / 1, alternating chunks) of this thread, at least ``nbytes``
-    long, free to overwrite: its previous uploads have completed."""
-    key = (threading.get_ident(), slot)
-    ent = _batch_stage.get(key)
-    if ent is not None and ent[1] is not None:
-        ent[1].synchronize()
-    if ent is None or ent[0].numel() < nbytes:
-        if len(_batch_stage) > 8:
-            _batch_stage.clear()
-        ent = _batch_stage[key] = [torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8).pin_memory(), None]
-    return ent
+def _batch_ctx(dev_index: int) -> dict:
+    key = (threading.get_ident(), dev_index)
+    ctx = _batch_state.get(key)
+    if ctx is None:
+        if len(_batch_state) > 8:
+            _batch_state.clear()
+        ctx = _batch_state[key] = {
+            "up": torch.cuda.Stream(dev_index),        # host -> device copies + resize
+            "post": torch.cuda.Stream(dev_index),      # near-black sums of finished groups
+            "slots": [{"buf": None, "free": None} for _ in range(STAGE_SLOTS)],
+        }
+    return ctx
 
 
-def _segment_images(eng, pil_imgs: Sequence[Image.Image]):
-    """Images -> (uint8 0/1 masks (B, 3, 512, 512) on the host, per-image crops), pipelined.
+def _crop_fast(pil_img: Image.Image, view: Optional[np.ndarray], r, share: bool) -> Image.Image:
+    """``pil_img.crop(r)`` for an RGB image whose pixels are visible as ``view`` (the zero-copy ``(H, W, 4)``
+    RGBX export of :func:`_rgb_host_view`): same mode, size and pixels, built without holding the GIL --
+    ``PIL.Image.crop`` copies under the GIL, which serialises the host threads of the batched entry point.
+    ``share=False``: numpy copies the window (GIL released) and Pillow maps the copy; ``share=True``: Pillow
+    maps the window of the SOURCE image in place (no copy; the crop is read-only and aliases ``pil_img``).
+    Anything unexpected falls back to ``pil_img.crop``."""
+    try:
+        if view is None or view.ndim != 3 or view.shape[2] != 4 or pil_img.mode != "RGB":
+            return pil_img.crop(r)
+        x1, y1, x2, y2 = r
+        h, w = view.shape[:2]
+        if share and not (y2 == h and x1 > 0):       # (the mapped window must end inside the buffer)
+            buf, off, stride = view.reshape(-1), (y1 * w + x1) * 4, w * 4
+        else:
+            buf, off, stride = np.ascontiguousarray(view[y1:y2, x1:x2]).reshape(-1), 0, (x2 - x1) * 4
+        core = Image.core.map_buffer(buf, (x2 - x1, y2 - y1), "raw", off, ("RGB", stride, 1))
+        im = Image.new("RGB", (0, 0))._new(core)
+        im.readonly = 1                                # Pillow copies on the first write
+        return im
+    except Exception:
+        return pil_img.crop(r)
 
-    Per chunk of ``MAX_CHUNK`` images: host threads copy the frames (Pillow's own RGBX buffers where they can
-    be exported without a repack) into one of two pinned staging buffers while the previous chunk is in
-    flight; every frame is uploaded asynchronously and resized on the GPU straight into its slot of the batch
-    tensor (other PIL modes: the reference's PIL calls on the host); one forward, one mask -> box reduction,
-    asynchronous downloads into pinned memory.  Nothing waits for the GPU until every chunk is enqueued; then,
-    chunk by chunk: rectangles on the host (reference :95-112), the near-black test for all rectangles of the
-    chunk on the device frames (one sync), and the ``PIL.crop`` calls on the host threads."""
+
+def _segment_images(eng, pil_imgs: Sequence[Image.Image], crop_views: bool = False):
+    """Images -> (uint8 0/1 masks (B, 3, 512, 512) on the host, per-image crops), as a pipeline of groups of
+    ``PIPE_GROUP`` images (at most ``MAX_CHUNK`` per forward):
+
+    * host threads copy each group's frames (Pillow's own RGBX buffers where they can be exported without a
+      repack) into one of ``STAGE_SLOTS`` pinned staging buffers -- a buffer is refilled as soon as the uploads
+      that read it have completed;
+    * an upload stream moves every frame to the device and resizes it on the GPU straight into its slot of the
+      group's batch tensor (other PIL modes: the reference's PIL calls on the host), so the copies of group g+1
+      overlap the forward of group g on the caller's stream; masks and their boxes come back asynchronously
+      into pinned memory;
+    * as soon as a group's boxes have landed, a host thread computes the crop rectangles (reference :95-112),
+      runs the near-black test of ALL its rectangles on the device frames (a side stream, one sync) and fans the
+      ``PIL.crop`` calls out to the pool.
+
+    The caller's thread never waits for the GPU before the last group is enqueued."""
     from . import prepost
     _require_cuda()
     thr = [THRESHOLDS[f] for f in FIELDS]
     n_img = len(pil_imgs)
-    masks = torch.empty((n_img, len(FIELDS), IMG_SIZE, IMG_SIZE), dtype=torch.uint8).pin_memory()
-    boxes_host = torch.empty((n_img, len(FIELDS), 5), dtype=torch.int32).pin_memory()
+    group = max(1, min(MAX_CHUNK, PIPE_GROUP))
+    dev_index = torch.cuda.current_device()
+    ctx = _batch_ctx(dev_index)
+    up, post = ctx["up"], ctx["post"]
+    masks = torch.empty((n_img, len(FIELDS), IMG_SIZE, IMG_SIZE), dtype=torch.uint8, pin_memory=True)
+    boxes_host = torch.empty((n_img, len(FIELDS), 5), dtype=torch.int32, pin_memory=True)
+    bx_all = boxes_host.numpy()
     pool = _worker_pool()
-    stream = torch.cuda.current_stream()
-    chunks = []                                    # (lo, images, device frames, event after the downloads)
-    for ci, lo in enumerate(range(0, n_img, MAX_CHUNK)):
-        chunk = pil_imgs[lo:lo + MAX_CHUNK]
-        views = [_rgb_host_view(im) if _gpu_resizable(im) else None for im in chunk]
+    main = torch.cuda.current_stream()
+    spans = [(lo, min(lo + group, n_img)) for lo in range(0, n_img, group)]
+    import time as _time
+    _t0 = _time.perf_counter()
+
+    def mark(label):
+        if _TRACE is not None:
+            _TRACE.append((label, _time.perf_counter() - _t0))
+    views = [_rgb_host_view(im) if _gpu_resizable(im) else None for im in pil_imgs]
+    mark("views")
+
+    def plan(g):
+        lo, hi = spans[g]
         offs, total = [], 0
-        for v in views:
+        for v in views[lo:hi]:
             offs.append(total)
             if v is not None:
                 total += (v.size + 255) & ~255
-        ent = _stage_buffer(ci & 1, total)
-        flat = ent[0]
-        flat_np = flat.numpy()
+        return offs, total
 
-        def fill(i):
-            v = views[i]
-            np.copyto(flat_np[offs[i]:offs[i] + v.size].reshape(v.shape), v)
+    def fill_one(g, i, off, flat_np):
+        v = views[spans[g][0] + i]
+        np.copyto(flat_np[off:off + v.size].reshape(v.shape), v)
 
-        futs = [pool.submit(fill, i) if v is not None else None for i, v in enumerate(views)]
-        x = torch.empty((len(chunk), IMG_SIZE, IMG_SIZE, 3), dtype=torch.uint8, device=DEVICE)
-        frames = []
-        for i, (im, v) in enumerate(zip(chunk, views)):
-            if v is not None:
-                futs[i].result()
-                f = flat[offs[i]:offs[i] + v.size].view(v.shape).to(DEVICE, non_blocking=True)
-                prepost.resize_u8(f[None], IMG_SIZE, IMG_SIZE, out=x[i:i + 1], channels=3)
-                frames.append(f)
+    def start_fill(g):
+        """Reserve group g's slot (worker thread waits for it to be free), then one copy task per frame."""
+        def reserve():
+            offs, total = plan(g)
+            slot = ctx["slots"][g % STAGE_SLOTS]
+            if slot["free"] is not None:
+                slot["free"].synchronize()
+            if slot["buf"] is None or slot["buf"].numel() < total:
+                slot["buf"] = torch.empty(max(total, 1 << 20), dtype=torch.uint8, pin_memory=True)
+            flat_np = slot["buf"].numpy()
+            lo, hi = spans[g]
+            futs = [pool.submit(fill_one, g, i, offs[i], flat_np) if views[lo + i] is not None else None
+                    for i in range(hi - lo)]
+            return slot, offs, futs
+        return pool.submit(reserve)
+
+    def cut(idx, rects, tot):
+        im, view = pil_imgs[idx], views[idx]
+        out = {}
+        for key, r in zip(FIELDS, rects):
+            if r is None:
+                out[key] = None
+            elif tot is None:                          # frame not on the device: the host test of the reference
+                c = im.crop(r)
+                arr = np.array(c)
+                out[key] = None if (arr.size == 0 or arr.mean() < 3) else c
             else:
-                x[i].copy_(torch.from_numpy(_resized_rgb_u8(im.resize((IMG_SIZE, IMG_SIZE)))))
-                frames.append(None)
-        ent[1] = torch.cuda.Event()
-        ent[1].record(stream)                      # this staging buffer is reusable once its uploads are done
-        _, mask = eng.run(x, want_logits=False, thresholds=thr)
-        masks[lo:lo + len(chunk)].copy_(mask, non_blocking=True)
-        boxes_host[lo:lo + len(chunk)].copy_(prepost.mask_bbox(mask), non_blocking=True)
-        done = torch.cuda.Event()
-        done.record(stream)
-        chunks.append((lo, chunk, frames, done))
+                total = tot.pop(0)
+                out[key] = None if total < 3 * (r[2] - r[0]) * (r[3] - r[1]) * 3 else _crop_fast(im, view, r, crop_views)
+        return out
 
-    crops: list = [None] * n_img
-    bx_all = boxes_host.numpy()
-    for lo, chunk, frames, done in chunks:
+    def finish(g, frames, done):
+        """(worker thread) boxes of group g -> rectangles -> near-black sums on the device -> crop tasks."""
+        torch.cuda.set_device(dev_index)
+        lo, hi = spans[g]
         done.synchronize()
-        rects = [[_crop_rect(im.size, _extent(bx_all[lo + i, k])) for k in range(len(FIELDS))]
-                 for i, im in enumerate(chunk)]
-        sums = []
-        for i, f in enumerate(frames):             # near-black sums of every live rectangle, enqueued together
-            live = [r for r in rects[i] if r is not None]
-            sums.append(prepost.box_sums(f, live, channels=3) if (f is not None and live) else None)
-        sums_host = [None if t is None else t.cpu().tolist() for t in sums]      # first .cpu() waits for all
+        rects = [[_crop_rect(pil_imgs[i].size, _extent(bx_all[i, k])) for k in range(len(FIELDS))]
+                 for i in range(lo, hi)]
+        with torch.cuda.stream(post):
+            sums = []
+            for f, rs in zip(frames, rects):
+                live = [r for r in rs if r is not None]
+                sums.append(prepost.box_sums(f, live, channels=3) if (f is not None and live) else None)
+            sums_host = [None if t is None else t.cpu().tolist() for t in sums]
+        return [pool.submit(cut, lo + i, rects[i], sums_host[i]) for i in range(hi - lo)]
 
-        def cut(i):
-            im, out, tot = chunk[i], {}, (list(sums_host[i]) if sums_host[i] is not None else None)
-            for key, r in zip(FIELDS, rects[i]):
-                if r is None:
-                    out[key] = None
-                elif tot is None:                  # frame not on the device: the host test of the reference
-                    c = im.crop(r)
-                    arr = np.array(c)
-                    out[key] = None if (arr.size == 0 or arr.mean() < 3) else c
+    fills = {g: start_fill(g) for g in range(min(STAGE_SLOTS, len(spans)))}
+    posts = []
+    for g, (lo, hi) in enumerate(spans):
+        slot, offs, futs = fills.pop(g).result()
+        mark(f"g{g} reserved")
+        flat = slot["buf"]
+        x = torch.empty((hi - lo, IMG_SIZE, IMG_SIZE, 3), dtype=torch.uint8, device=DEVICE)
+        frames = []
+        up.wait_stream(main)                           # x's memory is free on the caller's stream
+        with torch.cuda.stream(up):
+            for i in range(hi - lo):
+                im, v = pil_imgs[lo + i], views[lo + i]
+                if v is not None:
+                    futs[i].result()
+                    f = flat[offs[i]:offs[i] + v.size].view(v.shape).to(DEVICE, non_blocking=True)
+                    prepost.resize_u8(f[None], IMG_SIZE, IMG_SIZE, out=x[i:i + 1], channels=3)
+                    frames.append(f)
                 else:
-                    total = tot.pop(0)
-                    out[key] = None if total < 3 * (r[2] - r[0]) * (r[3] - r[1]) * 3 else im.crop(r)
-            return out
-
-        for i, res in enumerate(pool.map(cut, range(len(chunk)))):
-            crops[lo + i] = res
+                    x[i].copy_(torch.from_numpy(_resized_rgb_u8(im.resize((IMG_SIZE, IMG_SIZE)))))
+                    frames.append(None)
+            slot["free"] = torch.cuda.Event()
+            slot["free"].record(up)
+        mark(f"g{g} uploaded")
+        if g + STAGE_SLOTS < len(spans):
+            fills[g + STAGE_SLOTS] = start_fill(g + STAGE_SLOTS)
+        main.wait_stream(up)
+        _, mask = eng.run(x, want_logits=False, thresholds=thr)
+        masks[lo:hi].copy_(mask, non_blocking=True)
+        boxes_host[lo:hi].copy_(prepost.mask_bbox(mask), non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(main)
+        posts.append(pool.submit(finish, g, frames, done))
+        del frames
+        mark(f"g{g} enqueued")
+    crops: list = []
+    for g, p_ in enumerate(posts):
+        futs = p_.result()
+        mark(f"g{g} boxes+sums")
+        crops += [f.result() for f in futs]
+        mark(f"g{g} crops")
+    main.synchronize()
+    mark("done")
     return masks.numpy(), crops
 
 
@@ -418,13 +501,16 @@ def run_unet_enhanced(pil_img: Image.Image, checkpoint_path: str):
     return masks, crops, {f: Image.fromarray(done[f]) if f in done else None for f in FIELDS}
 
 
-def run_unet_batch(pil_imgs: Sequence[Image.Image], checkpoint_path: str
+def run_unet_batch(pil_imgs: Sequence[Image.Image], checkpoint_path: str, crop_views: bool = False
                    ) -> List[Tuple[Dict[str, np.ndarray], Dict[str, Optional[Image.Image]]]]:
-    """``run_unet`` for many images with one batched forward per 64 images (new entry point)."""
+    """``run_unet`` for many images as one pipeline (new entry point): ``[(masks, crops), ...]`` in input order,
+    each pair exactly what ``run_unet`` returns for that image.  ``crop_views=True`` returns the crops of RGB
+    inputs as read-only windows INTO the input images (no pixel copy; they alias ``pil_imgs[i]`` and keep it
+    alive) instead of independent copies."""
     if len(pil_imgs) == 0:
         return []
     _require_cuda()
     _, eng = _cached_engine(checkpoint_path)
-    m, crops = _segment_images(eng, list(pil_imgs))
+    m, crops = _segment_images(eng, list(pil_imgs), crop_views=crop_views)
     mb = m.view(np.bool_)          # the kernel writes exactly 0 / 1: the boolean planes without another pass
     return [({f: mb[b, i] for i, f in enumerate(FIELDS)}, crops[b]) for b in range(len(pil_imgs))]
