@@ -342,6 +342,15 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
         const int grp = (threadIdx.x - 384) >> 7;                // producer group: takes tiles it % 2 == grp
         const int r = (threadIdx.x - 384) & 127;
         float* s_patch = reinterpret_cast<float*>(smem_gen + p.off_patch) + grp * 2 * PE;
+        // uint8 ingest: k / 255.0f (inference.py:36, IEEE division) for all 256 byte values, once per CTA and
+        // producer group -- a table look-up per pixel byte instead of a division (the kernel is issue-bound:
+        // the division made the uint8 path 0.4 ms per batch-64 step slower than the float path)
+        float* s_lut = reinterpret_cast<float*>(smem_gen + p.off_patch) + 4 * PE + grp * 256;
+        if (p.stem_fmt != 0) {
+            s_lut[r] = __fdiv_rn(static_cast<float>(r), 255.0f);
+            s_lut[r + 128] = __fdiv_rn(static_cast<float>(r + 128), 255.0f);
+            named_bar_sync(9 + grp, 128);
+        }
         const int hh = r >> 3, ww = r & 7;
         // patch elements this thread fetches, fixed for the whole kernel: (ci, dy, dx) packed
         int ecode[NL];
@@ -351,51 +360,59 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
             const int ci = e / 180, rem = e - ci * 180;
             ecode[i] = e < PE ? ((ci << 16) | ((rem / 10) << 8) | (rem % 10)) : -1;
         }
-        auto fetch = [&](int t, float (&regs)[NL]) {
+        // fetch keeps the RAW loaded words (float bits, or the pixel byte) in registers: nothing may depend on a
+        // load before publish(), one tile of work later, or the global-load latency lands in the producer's
+        // critical path (converting the bytes inside fetch made the uint8 ingest 0.4 ms per step slower)
+        auto fetch = [&](int t, uint32_t (&regs)[NL]) {
             int n, rr, ty_, tx_;
             fdivmod(static_cast<uint32_t>(t), p.fd_tpi, n, rr);
             fdivmod(static_cast<uint32_t>(rr), p.fd_tx, ty_, tx_);
             const int y0 = ty_ * 16 - 1, x0 = tx_ * 8 - 1;
 #pragma unroll
             for (int i = 0; i < NL; ++i) {
-                float v = 0.f;
+                uint32_t v = 0u;                                 // zero padding: 0.0f, or byte 0 -> 0 / 255
                 if (ecode[i] >= 0) {
                     const int ci = ecode[i] >> 16;
                     const int y = y0 + ((ecode[i] >> 8) & 0xff), x = x0 + (ecode[i] & 0xff);
                     if (y >= 0 && y < p.H && x >= 0 && x < p.W) {
                         if (p.stem_fmt == 0) {
-                            v = __ldg(static_cast<const float*>(p.stem_x) +
-                                      ((static_cast<size_t>(n) * CI + ci) * p.H + y) * p.W + x);
+                            v = __float_as_uint(__ldg(static_cast<const float*>(p.stem_x) +
+                                                      ((static_cast<size_t>(n) * CI + ci) * p.H + y) * p.W + x));
                         } else {
-                            const uint8_t u = __ldg(static_cast<const uint8_t*>(p.stem_x) +
-                                                    ((static_cast<size_t>(n) * p.H + y) * p.W + x) * CI + ci);
-                            v = __fdiv_rn(static_cast<float>(u), 255.0f);   // inference.py:36 (`/ 255.0`)
+                            v = __ldg(static_cast<const uint8_t*>(p.stem_x) +
+                                      ((static_cast<size_t>(n) * p.H + y) * p.W + x) * CI + ci);
                         }
                     }
                 }
                 regs[i] = v;
             }
         };
-        auto publish = [&](int buf, const float (&regs)[NL]) {
+        auto publish = [&](int buf, const uint32_t (&regs)[NL]) {
 #pragma unroll
             for (int i = 0; i < NL; ++i) {
                 const int e = r + i * 128;
-                if (e < PE) s_patch[buf * PE + e] = regs[i];
+                if (e < PE)                                      // byte -> s_lut[byte] == byte / 255.0f (inference.py:36)
+                    s_patch[buf * PE + e] = p.stem_fmt == 0 ? __uint_as_float(regs[i]) : s_lut[regs[i]];
             }
         };
-        float regs[NL];
+        // Two register sets: the loads of tile t + 2 are issued before tile t is built and are first touched when
+        // tile t + 1 has been built, so a global load has two tiles of work (not one) to come back.
+        uint32_t regs_a[NL], regs_b[NL];
         pdl_wait();
         const int stride = 2 * static_cast<int>(gridDim.x);
         int it = 0;                                              // this group's tile counter
         int t = static_cast<int>(blockIdx.x) + grp * static_cast<int>(gridDim.x);
         if (t < p.total_tiles) {
-            fetch(t, regs);
-            publish(0, regs);
+            fetch(t, regs_a);
+            publish(0, regs_a);
         }
+        if (t + stride < p.total_tiles) fetch(t + stride, regs_b);
         named_bar_sync(9 + grp, 128);
-        for (; t < p.total_tiles; t += stride, ++it) {
+        // one tile: prefetch tile t + 2 into `rf` (free: its tile is in the patch already), build the A rows of
+        // tile t from patch buffer it & 1, publish tile t + 1 (loaded one iteration ago, in `rp`) into the other
+        auto tile_step = [&](uint32_t (&rf)[NL], const uint32_t (&rp)[NL]) {
             const int tn = t + stride;
-            if (tn < p.total_tiles) fetch(tn, regs);             // global loads in flight during the build
+            if (tn + stride < p.total_tiles) fetch(tn + stride, rf);
             const float* pt = s_patch + (it & 1) * PE;
             uint32_t hi[16], lo[16];                             // 32 bf16 each, zero padded past KS
 #pragma unroll
@@ -431,8 +448,14 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
                 fence_proxy_async_smem();
                 mbar_arrive(bar_a_full + 8 * sa);
             }
-            if (tn < p.total_tiles) publish((it + 1) & 1, regs);
+            if (tn < p.total_tiles) publish((it + 1) & 1, rp);
             named_bar_sync(9 + grp, 128);
+            t = tn;
+            ++it;
+        };
+        while (t < p.total_tiles) {
+            tile_step(regs_a, regs_b);
+            if (t < p.total_tiles) tile_step(regs_b, regs_a);
         }
     } else if (warp == 0) {
         // ===================== TMA producer: activations ======================

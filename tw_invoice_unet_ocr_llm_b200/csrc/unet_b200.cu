@@ -636,7 +636,7 @@ int build_conv_step(const ConvDesc& d, int num_sms, Step* st) {
     p.pf_items = d.pf_items;
     if ((rc = plan_smem(&st->conv, &p, d.taps == 9 ? 9 : 1, cin / 64, p.n_blocks, bn,
                         d.epi == ub::EPI_STORE_POOL, d.epi != ub::EPI_HEAD, stem ? 1 : d.wstat,
-                        (stem && !stemp) ? 4 * d.stem_cin * 180 * 4 : 0, d.epi2, d.min_na)))
+                        (stem && !stemp) ? 4 * d.stem_cin * 180 * 4 + 2 * 1024 /* patches + /255 tables */ : 0, d.epi2, d.min_na)))
         return rc;
     p.fd_tpi = ub::make_fastdiv(static_cast<uint32_t>(p.tiles_x * p.tiles_y));
     p.fd_tx = ub::make_fastdiv(static_cast<uint32_t>(p.tiles_x));
