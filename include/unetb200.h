@@ -43,7 +43,8 @@ enum {
 };
 
 /* A-operand staging strategy of the tensor-core conv kernel (see csrc/conv_tc.cuh) */
-enum { UNETB200_A_TAP = 0, UNETB200_A_COL3 = 1, UNETB200_A_HALO = 2 };
+enum { UNETB200_A_TAP = 0, UNETB200_A_COL3 = 1, UNETB200_A_HALO = 2,
+       UNETB200_A_ROW = 5 /* single-kernel hooks only: the row-stacked kernel (cout == 64) */ };
 
 /* UNet(n_channels, n_classes) of reference unet_model.py:24; base_width is the 64 of :29. */
 typedef struct {
@@ -94,7 +95,9 @@ int unetb200_create(const unetb200_arch_t* arch, const void* blob_dev, uint64_t 
 int unetb200_destroy(unetb200_handle_t h);
 
 /* options: "amode" (UNETB200_A_*), "bn_max" (64/128/256), "wstat" (0/1), "stem_tc" (first conv: 0 CUDA cores / 1 tensor cores + im2col / 2 tensor cores, implicit GEMM), "pair" (0 never / 1 everywhere / 2 auto),
- * "pdl" (0/1 programmatic dependent launch), "epi2" (two epilogue groups: 0 never / 1 weight-stationary launches / 2 always), "pf_items" (0..64), "profile" (0/1) */
+ * "pdl" (0/1 programmatic dependent launch), "epi2" (two epilogue groups: 0 never / 1 weight-stationary launches / 2 always), "pf_items" (0..64), "profile" (0/1),
+ * "row64" (64-output-channel 3x3 convs on the row-stacked kernel csrc/conv_row.cuh: bit 0 = down1.net.3 and conv1.net.3, bit 1 = conv1.net.0; default 2; results are bit-identical either way),
+ * "fill_sms" (0/1/2 small-batch column-block policy), "min_na" (2..8) */
 int unetb200_set_option(unetb200_handle_t h, const char* key, int value);
 int unetb200_get_option(unetb200_handle_t h, const char* key, int* value);
 

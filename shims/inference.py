@@ -8,4 +8,4 @@ if _ROOT not in sys.path:
     sys.path.insert(0, _ROOT)
 
 from tw_invoice_unet_ocr_llm_b200.inference import (  # noqa: E402,F401
-    DEVICE, FIELDS, IMG_SIZE, THRESHOLDS, load_model, preprocess, run_unet, run_unet_batch)
+    DEVICE, FIELDS, IMG_SIZE, THRESHOLDS, load_model, preprocess, run_unet, run_unet_batch, run_unet_enhanced)

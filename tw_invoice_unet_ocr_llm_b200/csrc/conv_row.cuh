@@ -30,7 +30,8 @@
 //   warp 1 : MMA issuer          warp 2 : TMEM allocator (2 accumulators x 4 rows x 64 columns; handing the rows
 //            over one by one -- row barriers instead of tile barriers -- was measured 10 % SLOWER)
 //   warp 3 : weights, once: the whole [slice][kx][ky = 2,1,0][64][64] slab stays resident
-//   warps 4-7, 8-11 : two epilogue groups on alternate tiles; a warp owns 32 pixels of every output row.
+//   warps 4-7, 8-11 : two epilogue groups, each draining half of the rows of EVERY tile; a warp owns 32 pixels
+//                     of its rows.
 #pragma once
 #include "conv_tc.cuh"
 
@@ -80,7 +81,7 @@ __global__ void __launch_bounds__(384, 1) conv_row_kernel(const __grid_constant_
         mbar_init(bar_b_full, 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(bar_t_full + 8 * i, 1);
-            mbar_init(bar_t_empty + 8 * i, 4);       // one arrive per epilogue warp
+            mbar_init(bar_t_empty + 8 * i, 4 * p.n_epi);   // one arrive per active epilogue warp
         }
         mbar_fence_init();
     }
@@ -191,14 +192,18 @@ __global__ void __launch_bounds__(384, 1) conv_row_kernel(const __grid_constant_
         }
     } else if (warp >= 4) {
         // ============================= epilogue ===============================
-        const int eg = (warp - 4) >> 2;         // epilogue group: takes tiles tile_it % n_epi == eg
+        // Both epilogue groups work on EVERY tile, half of its rows each (group 0: rows 0-1, group 1: rows 2-3):
+        // with only two accumulators in TMEM the UMMAs of tile t + 2 wait for tile t to be drained, so what
+        // counts is the drain LATENCY of one tile, not the throughput of two tiles drained side by side
+        // (alternate tiles per group, the conv_tc.cuh scheme, left the MMA warp waiting ~20 % of the time).
+        const int eg = (warp - 4) >> 2;         // epilogue group
         const int q = warp & 3;                 // TMEM lane quarter = pixels 32q .. 32q + 31 of the tile row
-        const int estep = p.n_epi;
-        uint32_t tile_it = eg, chunk_it = 0;
+        const int j_lo = p.n_epi == 2 ? eg * (R / 2) : 0;
+        const int j_hi = p.n_epi == 2 ? j_lo + R / 2 : R;
+        uint32_t tile_it = 0, chunk_it = 0;
         // bias and head weights are kernel parameters (ConvParams::bias_c / head_wc): with the loops below fully
         // unrolled every use is a constant-bank operand, no registers and no shared-memory loads
-        for (int t = eg < estep ? first_tile + eg * tile_stride : p.total_tiles; t < p.total_tiles;
-             t += estep * tile_stride, tile_it += estep) {
+        for (int t = eg < p.n_epi ? first_tile : p.total_tiles; t < p.total_tiles; t += tile_stride, ++tile_it) {
             int n, y0, x0;
             decode(t, n, y0, x0);
             const uint32_t acc = tile_it & 1, acc_ph = (tile_it >> 1) & 1;
@@ -206,8 +211,8 @@ __global__ void __launch_bounds__(384, 1) conv_row_kernel(const __grid_constant_
             tc_fence_after();
             const uint32_t t_addr = tmem_base + acc * (R * 64) + (static_cast<uint32_t>(q * 32) << 16);
             auto row_ready = [&](int) {};            // (accumulators are handed over per tile, see the header)
-            auto row_done = [&](int j) {             // last row read: the accumulator goes back to the MMA warp
-                if (j == R - 1) {
+            auto row_done = [&](int j) {             // this warp's last row read: its share of the accumulator is free
+                if (j == j_hi - 1) {
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar_t_empty + 8 * acc);
@@ -219,7 +224,7 @@ __global__ void __launch_bounds__(384, 1) conv_row_kernel(const __grid_constant_
             if (EPI == EPI_HEAD) {
                 constexpr int NC = X > 0 ? X : kMaxClasses;
 #pragma unroll 1
-                for (int j = 0; j < R; ++j) {
+                for (int j = j_lo; j < j_hi; ++j) {
                     row_ready(j);
                     float z[NC];
 #pragma unroll
@@ -277,7 +282,7 @@ __global__ void __launch_bounds__(384, 1) conv_row_kernel(const __grid_constant_
                 }
             } else if (EPI == EPI_STORE) {
 #pragma unroll 1
-                for (int j = 0; j < R; ++j, ++chunk_it) {
+                for (int j = j_lo; j < j_hi; ++j, ++chunk_it) {
                     // a warp owns its 32 pixels of the row: its own 4 KB slab of the slot, its own TMA stores
                     const uint32_t slot = chunk_it - fdiv(chunk_it, p.fd_nout) * p.fd_nout.d;
                     const uint32_t slab = sOut + (eg * p.n_out + slot) * kOutStage + q * 4096;
@@ -320,7 +325,7 @@ __global__ void __launch_bounds__(384, 1) conv_row_kernel(const __grid_constant_
                 // register max of the two rows + one shuffle with the x neighbour; bf16 rounding is monotone, so
                 // max of rounded == rounded max.  Slots 0 / 1 of the group take the two rows.
 #pragma unroll 1
-                for (int jp = 0; jp < R / 2; ++jp) {
+                for (int jp = j_lo / 2; jp < j_hi / 2; ++jp) {
                     const uint32_t slab_a = sOut + (eg * 2 + 0) * kOutStage + q * 4096;
                     const uint32_t slab_b = sOut + (eg * 2 + 1) * kOutStage + q * 4096;
                     const uint32_t pslab = sPool + eg * 8192 + q * 2048;

@@ -134,7 +134,7 @@ int unetb200_enhance_run(const unetb200_enh_crop* table_host, const void* table_
     ub::enh_lut_kernel<<<static_cast<unsigned>(n) * ub::kEnhTiles * ub::kEnhTiles, ub::kEnhThreads, 0, s>>>(tab, ws);
     ub::enh_clahe_kernel<<<nb, ub::kEnhThreads, 0, s>>>(tab, n, ws, out_dev);
     if (any_otsu) {
-        ub::enh_otsu_kernel<<<static_cast<unsigned>(n), 32, 0, s>>>(tab, ws);
+        ub::enh_otsu_kernel<<<static_cast<unsigned>(n), ub::kEnhThreads, 0, s>>>(tab, ws);
         const unsigned spans = static_cast<unsigned>((out_bytes + ub::kEnhBinSpan - 1) / ub::kEnhBinSpan);
         ub::enh_binarize_kernel<<<spans, ub::kEnhThreads, 0, s>>>(tab, n, ws, out_dev, out_bytes);
     }

@@ -785,7 +785,9 @@ struct unetb200_handle_s {
     int pair = 2;               // CTA pairs (cta_group::2): 0 = never, 1 = wherever instantiated, 2 = where measured faster
     int pdl = 1;                // programmatic dependent launch between the layers of one forward
     int fill_sms = 1;           // narrow the column block of launches whose tiles do not cover the SMs (small batches)
-    int row64 = 0;              // 64-output-channel 3x3 convs on the row-stacked kernel (conv_row.cuh)
+    int row64 = 2;              // 64-output-channel 3x3 convs on the row-stacked kernel (conv_row.cuh): bit 0 = the
+                                // one-slice layers (down1.net.3, conv1.net.3: measured equal / 5 % slower, off),
+                                // bit 1 = conv1.net.0 (measured 3-5 % faster, on)
     int profile = 0;
     int* dbg = nullptr;         // pinned, device-visible watchdog record
     std::map<PlanKey, Plan> plans;
