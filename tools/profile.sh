@@ -3,7 +3,7 @@
 # usage: tools/profile.sh <tag>
 # Brings back only small artefacts (gpurun_out is capped at 64 MiB): CSV exports of the
 # reports plus one source-level .ncu-rep of two kernels.
-tag=${1:-r01}
+tag=${1:-r02}
 out=gpurun_out
 mkdir -p $out /tmp/ncu
 CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extras"
@@ -19,9 +19,9 @@ ncu -i /tmp/ncu/all.ncu-rep --page raw --csv > $out/prof_${tag}_raw.csv 2> /dev/
 ncu -i /tmp/ncu/all.ncu-rep --page details --csv > $out/prof_${tag}_details.csv 2> /dev/null
 # source-level capture of two tensor-core kernels: conv launches #19 (conv1.net.0, Cout=64,
 # weight-stationary) and #13 (conv3.net.0, Cout=256) of the 4th forward
-ncu --set full --clock-control none --import-source on -k regex:conv_tc -s 80 -c 1 \
+ncu --set full --clock-control none --import-source on -k regex:conv_ -s 80 -c 1 \
     -o $out/prof_${tag}_conv3_0 -f $CMD > $out/ncu_src1_$tag.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:conv_tc -s 86 -c 1 \
+ncu --set full --clock-control none --import-source on -k regex:conv_ -s 86 -c 1 \
     -o $out/prof_${tag}_conv1_0 -f $CMD > $out/ncu_src2_$tag.log 2>&1
 echo "source rc=$?"
 ls -la $out/ | tail -n 20

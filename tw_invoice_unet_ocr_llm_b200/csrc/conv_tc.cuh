@@ -170,8 +170,8 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
     static_assert(AMODE != A_STEMP || (TAPS == 9 && BN == 64 && CIN >= 1 && CIN <= 4 && EPI == EPI_STORE),
                   "patch stem: <= 4 input channels, 64 output channels");
     static_assert(TAPS == 9 || TAPS == 1, "3x3 conv or per-tap GEMM");
-    static_assert(AMODE != A_STEM || (TAPS == 1 && BN == 64 && CIN >= 1 && 9 * CIN <= 32),
-                  "stem: im2col rows of <= 32 taps, 64 output channels");
+    static_assert(AMODE != A_STEM || (TAPS == 1 && BN == 64 && CIN >= 1 && 9 * CIN < 32),
+                  "stem: im2col rows of < 32 taps (one K slot carries the bias), 64 output channels");
     static_assert(EPI != EPI_HEAD || BN == 64, "fused head needs all 64 channels in one tile");
     using Cfg = ConvCfg<BN, TAPS, AMODE, PAIR>;
     constexpr int TPA = Cfg::TPA;
@@ -425,7 +425,9 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
                         const int tap = k / CI, ci = k - tap * CI;
                         v[j] = pt[ci * 180 + (hh + tap / 3) * 10 + (ww + tap % 3)];
                     } else {
-                        v[j] = 0.f;
+                        // first pad slot = constant 1.0: its weight row holds the folded bias (pack.cuh), so the
+                        // GEMM adds it and the stem's (issue-bound) epilogue does not
+                        v[j] = k == KS ? 1.0f : 0.f;
                     }
                 }
                 hi[k2] = pack_bf16x2(v[0], v[1]);
@@ -830,7 +832,9 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
 #pragma unroll
                     for (int i = 0; i < 32; i += 4) {
                         float4 b4;
-                        if (kBiasRegs) {
+                        if (AMODE == A_STEM) {
+                            b4 = make_float4(0.f, 0.f, 0.f, 0.f);    // bias already added by the GEMM (constant-one K slot)
+                        } else if (kBiasRegs) {
                             constexpr int o = kBiasRegs ? 1 : 0;     // (keeps the indices in range otherwise)
                             b4 = make_float4(bias_r[o * (half * 32 + i)], bias_r[o * (half * 32 + i + 1)],
                                              bias_r[o * (half * 32 + i + 2)], bias_r[o * (half * 32 + i + 3)]);

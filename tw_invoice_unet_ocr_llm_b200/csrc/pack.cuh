@@ -66,17 +66,27 @@ __global__ void pack_stem_kernel(const float* __restrict__ w, const float* __res
 // First conv for the tensor-core stem (conv_tc.cuh, A_STEM): [64][Cin][3][3] ->
 // bf16 [co = 64][k = 128]:  k in [0,32) w_hi, [32,64) w_hi again, [64,96) w_lo, rest 0,
 // where w = w_hi + w_lo to 16 significand bits and tap index k = (ky*3+kx)*Cin + ci (< 9*Cin).
-__global__ void pack_stem_tc_kernel(const float* __restrict__ w, const float* __restrict__ gamma,
-                                    const float* __restrict__ var, float eps, int cout, int cin,
-                                    uint16_t* __restrict__ dst_w) {
+// Slot k = 9*Cin meets the constant 1.0 the im2col producer writes there: it holds the folded BatchNorm bias
+// (hi in part 0, lo in part 2; part 1 meets the zero of x_lo's slot), so the stem's epilogue adds no bias.
+__global__ void pack_stem_tc_kernel(const float* __restrict__ w, const float* __restrict__ b,
+                                    const float* __restrict__ gamma, const float* __restrict__ beta,
+                                    const float* __restrict__ mean, const float* __restrict__ var, float eps,
+                                    int cout, int cin, uint16_t* __restrict__ dst_w) {
     const int total = cout * 128;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int co = i / 128, kk = i % 128;
         const int k = kk & 31, part = kk >> 5;            // part 0,1: hi   2: lo   3: zero
         uint16_t out = 0;
-        if (k < 9 * cin && part < 3) {
-            const int ci = k % cin, tap = k / cin;
-            const float f = w[(static_cast<size_t>(co) * cin + ci) * 9 + tap] * bn_scale(gamma, var, eps, co);
+        if (part < 3 && (k < 9 * cin || (k == 9 * cin && part != 1))) {
+            const float s = bn_scale(gamma, var, eps, co);
+            float f;
+            if (k < 9 * cin) {
+                const int ci = k % cin, tap = k / cin;
+                f = w[(static_cast<size_t>(co) * cin + ci) * 9 + tap] * s;
+            } else {
+                const float b0 = b ? b[co] : 0.f;
+                f = gamma ? (b0 - mean[co]) * s + beta[co] : b0;
+            }
             const uint16_t hi = f32_to_bf16_bits(f);
             out = part < 2 ? hi : f32_to_bf16_bits(f - __uint_as_float(static_cast<uint32_t>(hi) << 16));
         }

@@ -983,7 +983,7 @@ int unetb200_pack_layer(const unetb200_arch_t* arch, int index, const float* wei
                 weight, bias, bn_gamma, bn_beta, bn_mean, bn_var, bn_eps, l.cout, l.cin,
                 reinterpret_cast<float*>(blob + l.w_off), db);
             ub::pack_stem_tc_kernel<<<(l.cout * 128 + threads - 1) / threads, threads, 0, s>>>(
-                weight, bn_gamma, bn_var, bn_eps, l.cout, l.cin,
+                weight, bias, bn_gamma, bn_beta, bn_mean, bn_var, bn_eps, l.cout, l.cin,
                 reinterpret_cast<uint16_t*>(blob + l.w_off + stem_tc_offset(l.cin, l.cout)));
             ub::pack_stem_patch_kernel<<<(9 * 32 * l.cout + threads - 1) / threads, threads, 0, s>>>(   // 9 x 2 x cout x 16
                 weight, bn_gamma, bn_var, bn_eps, l.cout, l.cin,
