@@ -214,7 +214,7 @@ def test_stem(cuda_dev, fmt):
 
 @pytest.mark.parametrize("variant", ["im2col", "patch"])
 @pytest.mark.parametrize("fmt", ["f32", "u8"])
-@pytest.mark.parametrize("n,h,w", [(2, 40, 48), (1, 16, 16), (3, 4, 6)])
+@pytest.mark.parametrize("n,h,w", [(2, 40, 48), (1, 16, 16), (3, 4, 16), (1, 20, 144)])
 def test_stem_tensor_core(cuda_dev, fmt, n, h, w, variant):
     """First conv on the tensor cores: in-kernel im2col, bf16 hi/lo split GEMM.  Must be as
     accurate as the fp32 CUDA-core stem (error dominated by the single bf16 output rounding),

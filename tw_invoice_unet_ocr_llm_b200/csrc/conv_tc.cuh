@@ -127,7 +127,7 @@ struct ConvParams {
     int n_epi;               // active epilogue groups: 2 = alternate tiles, 1 = group 0 takes every tile
     int pf_items;            // activation items prefetched into L2 ahead of the smem ring (0 = off)
     int off_b, off_out, off_pool, off_bar;   // smem carve-up, bytes from the 1024-aligned base
-    int off_patch;           // A_STEM: 2 x [Cin][18][10] fp32 input halo patches
+    int off_patch;           // A_STEM: ring of TMA-loaded input halo patches + the /255 table (kStemPatchBytes)
     const void* stem_x;      // A_STEM / A_STEMP: network input (format stem_fmt), see stem.cuh
     int stem_fmt;
     const void* stem_w;      // A_STEMP: weights already in the smem tile layout (pack.cuh), 9 x 4096 B
@@ -154,6 +154,9 @@ struct ConvCfg {
     static constexpr int NACC = BN == 256 ? 2 : 4;             // accumulator stages in TMEM
     static constexpr int TMEM_COLS = NACC * BN;                // 256 / 512 / 512 columns
 };
+constexpr int kStemSlots = 8;         // A_STEM: input-patch ring (TMA), slots of kStemSlotBytes
+constexpr int kStemSlotBytes = 3584;  //   fp32: [Cin <= 3][18][16] floats = 3456 B; uint8: [18][48] bytes
+constexpr int kStemPatchBytes = kStemSlots * kStemSlotBytes + 1024 + 2 * 2 * 3 * 180 * 4;   // ring + /255 table + split patches
 constexpr int kOutStage = 16384;      // 128 pixels x 64 channels bf16
 constexpr int kPoolStage = 4096;      // 32 pixels x 64 channels bf16
 constexpr int kMaxRing = 8;           // upper bound on na and (non-stationary) nb
@@ -191,6 +194,8 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
     const uint32_t bar_t_full = bar_b_empty + 8 * kMaxRing;
     const uint32_t bar_t_empty = bar_t_full + 32;
     const uint32_t s_tmem_ptr = bar_t_empty + 32;
+    const uint32_t bar_p_full = sBar + 512;            // A_STEM: input-patch ring
+    const uint32_t bar_p_empty = bar_p_full + 8 * kStemSlots;
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));   // generic view of smem_base
 
     __shared__ __align__(16) float s_bias[1024];
@@ -216,6 +221,12 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
         for (int i = 0; i < Cfg::NACC; ++i) {
             mbar_init(bar_t_full + 8 * i, 1);
             mbar_init(bar_t_empty + 8 * i, PAIR ? 8 : 4);   // one arrive per epilogue warp (of both CTAs)
+        }
+        if (AMODE == A_STEM) {
+            for (int i = 0; i < kStemSlots; ++i) {
+                mbar_init(bar_p_full + 8 * i, 1);           // the TMA load of the patch
+                mbar_init(bar_p_empty + 8 * i, 4);          // one arrive per warp of the group that read it
+            }
         }
         mbar_fence_init();
     }
@@ -333,113 +344,91 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
     } else if (AMODE == A_STEM && warp >= 12) {
         // ================== im2col producer (first conv only) =================
         // thread r builds A row r = output pixel (y0 + r/8, x0 + r%8) of the tile, one ring item:
-        //   k in [0,32) = bf16 hi of the 9*CIN taps, k in [32,64) = bf16 lo.
+        //   k in [0,32) = bf16 hi of the 9*CIN taps (+ the constant 1.0 that meets the bias row), k in [32,64) = bf16 lo.
         // The MMA warp multiplies the whole row by [w_hi | w_hi] and the hi half again by w_lo.
+        // The tile's 18 x 10 input halo patch arrives by TMA (warp 0, kStemSlots tiles ahead; out-of-image
+        // elements zero-filled = the conv padding): fp32 NCHW input as [Cin][18][16] floats, uint8 NHWC input as
+        // [18][48] bytes (pixel-interleaved; converted through the k / 255.0f table).  A TMA tile load FAULTS
+        // (illegal instruction, measured: tools/scratch/tma_probe.cu) unless the byte offset of its innermost
+        // start coordinate is a multiple of 16, so the boxes start at the 16-byte boundary below the patch's first
+        // element (floats: 3 columns early; bytes: `sh` bytes early, 5 or 13 by tile parity) and are wider than
+        // the 10 columns used.  Earlier versions fetched the
+        // patch with per-element __ldg into registers and exchanged it through shared memory: ~95 of ~270
+        // instructions per thread and tile in a kernel that is issue-bound, and the loads' latency under the
+        // layer's 3 TB/s of stores showed up as the top stall of the producer warps.
         constexpr int CI = CIN > 0 ? CIN : 1;                    // (CIN == 0 only in dead instantiations)
         constexpr int KS = 9 * CI;
-        constexpr int PE = CI * 180;                             // patch elements: [CIN][18][10]
-        constexpr int NL = (PE + 127) / 128;
+        constexpr int FW = 16;                                   // floats per fp32 patch row (columns 3..12 used)
+        constexpr int UW = CI == 1 ? 32 : 48;                    // bytes per uint8 patch row (10 * CI used, from `sh`)
         const int grp = (threadIdx.x - 384) >> 7;                // producer group: takes tiles it % 2 == grp
         const int r = (threadIdx.x - 384) & 127;
-        float* s_patch = reinterpret_cast<float*>(smem_gen + p.off_patch) + grp * 2 * PE;
-        // uint8 ingest: k / 255.0f (inference.py:36, IEEE division) for all 256 byte values, once per CTA and
-        // producer group -- a table look-up per pixel byte instead of a division (the kernel is issue-bound:
-        // the division made the uint8 path 0.4 ms per batch-64 step slower than the float path)
-        float* s_lut = reinterpret_cast<float*>(smem_gen + p.off_patch) + 4 * PE + grp * 256;
+        constexpr int PE = CI * 180;                             // patch elements: [CIN][18][10]
+        constexpr int NL = (PE + 127) / 128;
+        const uint8_t* s_ring = smem_gen + p.off_patch;
+        float* s_lut = reinterpret_cast<float*>(smem_gen + p.off_patch + kStemSlots * kStemSlotBytes);
+        // per group: two buffers of split (hi | lo) patch words
+        uint32_t* s_split = reinterpret_cast<uint32_t*>(smem_gen + p.off_patch + kStemSlots * kStemSlotBytes + 1024) +
+                            grp * 2 * PE;
         if (p.stem_fmt != 0) {
-            s_lut[r] = __fdiv_rn(static_cast<float>(r), 255.0f);
-            s_lut[r + 128] = __fdiv_rn(static_cast<float>(r + 128), 255.0f);
-            named_bar_sync(9 + grp, 128);
+            // uint8 ingest: k / 255.0f (inference.py:36, IEEE division) for all 256 byte values, once per CTA
+            s_lut[threadIdx.x - 384] = __fdiv_rn(static_cast<float>(threadIdx.x - 384), 255.0f);
+            named_bar_sync(11, 256);
         }
         const int hh = r >> 3, ww = r & 7;
-        // patch elements this thread fetches, fixed for the whole kernel: (ci, dy, dx) packed
-        int ecode[NL];
-#pragma unroll
-        for (int i = 0; i < NL; ++i) {
-            const int e = r + i * 128;
-            const int ci = e / 180, rem = e - ci * 180;
-            ecode[i] = e < PE ? ((ci << 16) | ((rem / 10) << 8) | (rem % 10)) : -1;
-        }
-        // fetch keeps the RAW loaded words (float bits, or the pixel byte) in registers: nothing may depend on a
-        // load before publish(), one tile of work later, or the global-load latency lands in the producer's
-        // critical path (converting the bytes inside fetch made the uint8 ingest 0.4 ms per step slower)
-        auto fetch = [&](int t, uint32_t (&regs)[NL]) {
-            int n, rr, ty_, tx_;
-            fdivmod(static_cast<uint32_t>(t), p.fd_tpi, n, rr);
-            fdivmod(static_cast<uint32_t>(rr), p.fd_tx, ty_, tx_);
-            const int y0 = ty_ * 16 - 1, x0 = tx_ * 8 - 1;
-#pragma unroll
-            for (int i = 0; i < NL; ++i) {
-                uint32_t v = 0u;                                 // zero padding: 0.0f, or byte 0 -> 0 / 255
-                if (ecode[i] >= 0) {
-                    const int ci = ecode[i] >> 16;
-                    const int y = y0 + ((ecode[i] >> 8) & 0xff), x = x0 + (ecode[i] & 0xff);
-                    if (y >= 0 && y < p.H && x >= 0 && x < p.W) {
-                        if (p.stem_fmt == 0) {
-                            v = __float_as_uint(__ldg(static_cast<const float*>(p.stem_x) +
-                                                      ((static_cast<size_t>(n) * CI + ci) * p.H + y) * p.W + x));
-                        } else {
-                            v = __ldg(static_cast<const uint8_t*>(p.stem_x) +
-                                      ((static_cast<size_t>(n) * p.H + y) * p.W + x) * CI + ci);
-                        }
-                    }
-                }
-                regs[i] = v;
+        uint32_t it = grp;                                       // CTA-local tile counter
+        for (int t = static_cast<int>(blockIdx.x) + grp * static_cast<int>(gridDim.x); t < p.total_tiles;
+             t += 2 * static_cast<int>(gridDim.x), it += 2) {
+            const uint32_t slot = it % kStemSlots, ph = (it / kStemSlots) & 1;
+            int sh = 3;                                          // first used column of the patch rows (floats)
+            if (p.stem_fmt != 0) {                               // bytes: (x0 - 1) * CI minus its 16-byte floor
+                int n_, rr_, ty_, tx_;
+                fdivmod(static_cast<uint32_t>(t), p.fd_tpi, n_, rr_);
+                fdivmod(static_cast<uint32_t>(rr_), p.fd_tx, ty_, tx_);
+                sh = ((tx_ * 8 - 1) * CI) & 15;
             }
-        };
-        auto publish = [&](int buf, const uint32_t (&regs)[NL]) {
+            mbar_wait(bar_p_full + 8 * slot, ph, 2, p.dbg);
+            const uint8_t* pb = s_ring + slot * kStemSlotBytes + (p.stem_fmt != 0 ? sh : 0);
+            const float* pf = reinterpret_cast<const float*>(s_ring + slot * kStemSlotBytes) + 3;
+            // pass 1: every patch element is converted and split into bf16 hi | lo ONCE (not once per tap that
+            // uses it: 540 splits per tile instead of 3 456) and parked as one packed word, [ci][18][10]
+            uint32_t* p2 = s_split + (it & 2 ? PE : 0);          // (it advances by 2: alternate buffers)
 #pragma unroll
             for (int i = 0; i < NL; ++i) {
                 const int e = r + i * 128;
-                if (e < PE)                                      // byte -> s_lut[byte] == byte / 255.0f (inference.py:36)
-                    s_patch[buf * PE + e] = p.stem_fmt == 0 ? __uint_as_float(regs[i]) : s_lut[regs[i]];
+                if (e < PE) {
+                    const int ci = e / 180, rem = e - ci * 180, py = rem / 10, px = rem - py * 10;
+                    const float v = p.stem_fmt == 0 ? pf[(ci * 18 + py) * FW + px] : s_lut[pb[py * UW + px * CI + ci]];
+                    const uint32_t h2 = pack_bf16x2(v, 0.f);                           // hi in the low half
+                    const uint32_t l2 = pack_bf16x2(v - __uint_as_float(h2 << 16), 0.f);
+                    p2[e] = __byte_perm(h2, l2, 0x5410);                                // hi | lo << 16
+                }
             }
-        };
-        // Two register sets: the loads of tile t + 2 are issued before tile t is built and are first touched when
-        // tile t + 1 has been built, so a global load has two tiles of work (not one) to come back.
-        uint32_t regs_a[NL], regs_b[NL];
-        pdl_wait();
-        const int stride = 2 * static_cast<int>(gridDim.x);
-        int it = 0;                                              // this group's tile counter
-        int t = static_cast<int>(blockIdx.x) + grp * static_cast<int>(gridDim.x);
-        if (t < p.total_tiles) {
-            fetch(t, regs_a);
-            publish(0, regs_a);
-        }
-        if (t + stride < p.total_tiles) fetch(t + stride, regs_b);
-        named_bar_sync(9 + grp, 128);
-        // one tile: prefetch tile t + 2 into `rf` (free: its tile is in the patch already), build the A rows of
-        // tile t from patch buffer it & 1, publish tile t + 1 (loaded one iteration ago, in `rp`) into the other
-        auto tile_step = [&](uint32_t (&rf)[NL], const uint32_t (&rp)[NL]) {
-            const int tn = t + stride;
-            if (tn + stride < p.total_tiles) fetch(tn + stride, rf);
-            const float* pt = s_patch + (it & 1) * PE;
-            uint32_t hi[16], lo[16];                             // 32 bf16 each, zero padded past KS
+            named_bar_sync(9 + grp, 128);
+            if (lane == 0) mbar_arrive(bar_p_empty + 8 * slot);  // (after the barrier: every warp is done with the patch)
+            // pass 2: this pixel's K row: 27 packed words -> hi pairs and lo pairs by byte permutes
+            uint32_t hi[16], lo[16];                             // 32 bf16 each, zero padded past KS + 1
 #pragma unroll
             for (int k2 = 0; k2 < 16; ++k2) {
-                float v[2], h[2];
+                uint32_t w2[2];
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
                     const int k = 2 * k2 + j;
                     if (k < KS) {
                         const int tap = k / CI, ci = k - tap * CI;
-                        v[j] = pt[ci * 180 + (hh + tap / 3) * 10 + (ww + tap % 3)];
+                        w2[j] = p2[ci * 180 + (hh + tap / 3) * 10 + (ww + tap % 3)];
                     } else {
-                        // first pad slot = constant 1.0: its weight row holds the folded bias (pack.cuh), so the
-                        // GEMM adds it and the stem's (issue-bound) epilogue does not
-                        v[j] = k == KS ? 1.0f : 0.f;
+                        // first pad slot = constant 1.0 (hi = 0x3F80, lo = 0): its weight row holds the folded bias
+                        // (pack.cuh), so the GEMM adds it and the stem's (issue-bound) epilogue does not
+                        w2[j] = k == KS ? 0x00003F80u : 0u;
                     }
                 }
-                hi[k2] = pack_bf16x2(v[0], v[1]);
-                h[0] = __uint_as_float(hi[k2] << 16);
-                h[1] = __uint_as_float(hi[k2] & 0xffff0000u);
-                lo[k2] = pack_bf16x2(v[0] - h[0], v[1] - h[1]);
+                hi[k2] = __byte_perm(w2[0], w2[1], 0x5410);
+                lo[k2] = __byte_perm(w2[0], w2[1], 0x7632);
             }
-            // ring item of this CTA-local tile (2 * it + grp)
+            // ring item of this CTA-local tile
             {
-                const uint32_t item = 2u * static_cast<uint32_t>(it) + grp;
-                const uint32_t qa = fdiv(item, p.fd_na);
-                const uint32_t sa = item - qa * p.fd_na.d, pa = qa & 1;
+                const uint32_t qa = fdiv(it, p.fd_na);
+                const uint32_t sa = it - qa * p.fd_na.d, pa = qa & 1;
                 mbar_wait(bar_a_empty + 8 * sa, pa ^ 1, 1, p.dbg);
                 const uint32_t row = sA + sa * Cfg::A_STAGE + r * 128;
 #pragma unroll
@@ -450,14 +439,31 @@ conv_tc_kernel(const __grid_constant__ ConvParams p) {
                 fence_proxy_async_smem();
                 mbar_arrive(bar_a_full + 8 * sa);
             }
-            if (tn < p.total_tiles) publish((it + 1) & 1, rp);
-            named_bar_sync(9 + grp, 128);
-            t = tn;
-            ++it;
-        };
-        while (t < p.total_tiles) {
-            tile_step(regs_a, regs_b);
-            if (t < p.total_tiles) tile_step(regs_b, regs_a);
+        }
+    } else if (warp == 0 && AMODE == A_STEM) {
+        // ============ TMA producer: input halo patches of the first conv ============
+        if (lane == 0) {
+            constexpr int CI = CIN > 0 ? CIN : 1;
+            constexpr uint32_t kBytes32 = CI * 18 * 16 * 4, kBytes8 = 18 * (CI == 1 ? 32 : 48);
+            pdl_wait();
+            uint32_t it = 0;
+            for (int t = static_cast<int>(blockIdx.x); t < p.total_tiles; t += static_cast<int>(gridDim.x), ++it) {
+                const uint32_t slot = it % kStemSlots, ph = (it / kStemSlots) & 1;
+                int n, rr, ty_, tx_;
+                fdivmod(static_cast<uint32_t>(t), p.fd_tpi, n, rr);
+                fdivmod(static_cast<uint32_t>(rr), p.fd_tx, ty_, tx_);
+                const int y0 = ty_ * 16 - 1, x0 = tx_ * 8 - 1;
+                mbar_wait(bar_p_empty + 8 * slot, ph ^ 1, 1, p.dbg);
+                const uint32_t dst = smem_base + p.off_patch + slot * kStemSlotBytes;
+                // (the innermost start coordinate must sit on a 16-byte boundary, see the im2col producer)
+                if (p.stem_fmt == 0) {                           // fp32 [N][C][H][W]: box 16 x 18 x Cin from x0 - 3
+                    mbar_expect_tx(bar_p_full + 8 * slot, kBytes32);
+                    tma_load_4d(dst, &p.tmA0, bar_p_full + 8 * slot, x0 - 3, y0, 0, n);
+                } else {                                         // uint8 [N][H][W * Cin]: box 48 (32) bytes x 18
+                    mbar_expect_tx(bar_p_full + 8 * slot, kBytes8);
+                    tma_load_3d(dst, &p.tmA0, bar_p_full + 8 * slot, (x0 * CI) & ~15, y0, n);
+                }
+            }
         }
     } else if (warp == 0) {
         // ===================== TMA producer: activations ======================

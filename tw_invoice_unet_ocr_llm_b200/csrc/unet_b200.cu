@@ -109,6 +109,41 @@ int make_w_map(CUtensorMap* m, const void* base, int cin, int rows, int taps, in
     return 0;
 }
 
+// network input of the first conv (conv_tc.cuh, A_STEM): the 18 x 10 halo patch of a tile as one TMA box.
+//   fp32 [N][C][H][W]      -> 4-D map (W, H, C, N), box (16, 18, C, 1)
+//   uint8 [N][H][W][C]     -> 3-D map (W * C, H, N), box (48 | 32 bytes, 18, 1)
+// The boxes are wider than the 10 columns used because a TMA tile load faults unless its innermost start
+// coordinate sits on a 16-byte boundary (conv_tc.cuh).  Out-of-image elements are zero-filled, which is the conv
+// padding (byte 0 -> 0 / 255).
+int make_input_map(CUtensorMap* m, const void* x, int x_fmt, int cin, int W, int H, int N) {
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) return fail(UNETB200_ECUDA, "cuTensorMapEncodeTiled entry point unavailable");
+    if (reinterpret_cast<uintptr_t>(x) & 15) return fail(UNETB200_EINVAL, "stem: the input tensor must be 16-byte aligned");
+    CUresult r;
+    if (x_fmt == UNETB200_X_F32_NCHW) {
+        if (W % 4) return fail(UNETB200_EINVAL, "stem: float input needs a width that is a multiple of 4");
+        cuuint64_t dims[4] = {uint64_t(W), uint64_t(H), uint64_t(cin), uint64_t(N)};
+        cuuint64_t strides[3] = {uint64_t(W) * 4, uint64_t(H) * W * 4, uint64_t(cin) * H * W * 4};
+        cuuint32_t box[4] = {16, 18, uint32_t(cin), 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(x), dims, strides, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {
+        if ((W * cin) % 16) return fail(UNETB200_EINVAL, "stem: uint8 input needs W * channels to be a multiple of 16");
+        cuuint64_t dims[3] = {uint64_t(W) * cin, uint64_t(H), uint64_t(N)};
+        cuuint64_t strides[2] = {uint64_t(W) * cin, uint64_t(H) * W * cin};
+        cuuint32_t box[3] = {cin == 1 ? 32u : 48u, 18, 1};
+        cuuint32_t estr[3] = {1, 1, 1};
+        r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(x), dims, strides, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    if (r != CUDA_SUCCESS)
+        return fail(UNETB200_ECUDA, "cuTensorMapEncodeTiled(network input) failed: " + std::to_string(int(r)));
+    return 0;
+}
+
 // ------------------------------------------------------------------ layer table
 struct LayerSpec {
     const char* name;
@@ -564,8 +599,12 @@ int build_conv_step(const ConvDesc& d, int num_sms, Step* st) {
         p.stem_x = d.stem_x;
         p.stem_fmt = d.stem_fmt;
         p.stem_w = d.w;
-        // tmA0/tmA1 are never used by the stem (its A rows are built in-kernel); keep them valid
-        if ((rc = make_act_map(&p.tmA0, d.out, d.cout, d.wd, d.h, d.n, 8, 16))) return rc;
+        if (stemp) {
+            // tmA0/tmA1 are never used by the patch stem (it reads the input itself); keep them valid
+            if ((rc = make_act_map(&p.tmA0, d.out, d.cout, d.wd, d.h, d.n, 8, 16))) return rc;
+        } else if ((rc = make_input_map(&p.tmA0, d.stem_x, d.stem_fmt, d.stem_cin, d.wd, d.h, d.n))) {
+            return rc;                  // im2col stem: the tile's input halo patch is one TMA box
+        }
         p.tmA1 = p.tmA0;
     } else if ((rc = make_act_map(&p.tmA0, d.src0, d.c0, d.wd, d.h, d.n, boxW, boxH))) {
         return rc;
@@ -636,7 +675,7 @@ int build_conv_step(const ConvDesc& d, int num_sms, Step* st) {
     p.pf_items = d.pf_items;
     if ((rc = plan_smem(&st->conv, &p, d.taps == 9 ? 9 : 1, cin / 64, p.n_blocks, bn,
                         d.epi == ub::EPI_STORE_POOL, d.epi != ub::EPI_HEAD, stem ? 1 : d.wstat,
-                        (stem && !stemp) ? 4 * d.stem_cin * 180 * 4 + 2 * 1024 /* patches + /255 tables */ : 0, d.epi2, d.min_na)))
+                        (stem && !stemp) ? ub::kStemPatchBytes : 0, d.epi2, d.min_na)))
         return rc;
     p.fd_tpi = ub::make_fastdiv(static_cast<uint32_t>(p.tiles_x * p.tiles_y));
     p.fd_tx = ub::make_fastdiv(static_cast<uint32_t>(p.tiles_x));

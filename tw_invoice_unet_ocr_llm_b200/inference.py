@@ -172,15 +172,27 @@ def boxes_to_crops(pil_img: Image.Image, boxes: np.ndarray, frame_dev=None, rect
     sums = prepost.box_sums(frame_dev, live, channels=3).cpu().tolist() if live else []
     crops: Dict[str, Optional[Image.Image]] = {}
     channels = 3                    # R, G, B count (an RGBX frame's padding byte does not)
+    keep = []
     for key, r in zip(FIELDS, rects):
+        crops[key] = None
         if r is None:
-            crops[key] = None
             continue
         total = sums.pop(0)
-        nbytes = (r[2] - r[0]) * (r[3] - r[1]) * channels
-        crops[key] = None if total < 3 * nbytes else pil_img.crop(r)
-        if rects_out is not None and crops[key] is not None:
-            rects_out[key] = r
+        if total >= 3 * (r[2] - r[0]) * (r[3] - r[1]) * channels:
+            keep.append((key, r))
+            if rects_out is not None:
+                rects_out[key] = r
+    # Large crops (a field mask that spans most of a 1080p frame is 8 MB of pixels) are cut side by side on the
+    # host threads: PIL.Image.crop copies under the GIL, _crop_fast copies without it.
+    big = [kr for kr in keep if (kr[1][2] - kr[1][0]) * (kr[1][3] - kr[1][1]) >= (1 << 18)]
+    if len(big) >= 2 and pil_img.mode == "RGB":
+        view = _rgb_host_view(pil_img)
+        futs = {key: _worker_pool().submit(_crop_fast, pil_img, view, r, False) for key, r in big}
+        for key, r in keep:
+            crops[key] = futs[key].result() if key in futs else pil_img.crop(r)
+    else:
+        for key, r in keep:
+            crops[key] = pil_img.crop(r)
     return crops
 
 
