@@ -203,6 +203,50 @@ def test_row_kernel_forward_identical(model, cuda_dev):
         eng.set_option("row64", keep)
 
 
+def test_graph_replay_identical(model, cuda_dev):
+    """From its second use on a plan is replayed as one CUDA graph: same logits and masks as direct launches, also
+    after the thresholds (kernel parameters baked into the graph) change, and under a caller's own stream capture."""
+    from tw_invoice_unet_ocr_llm_b200.synthetic import synthetic_invoices
+    eng = model.engine(cuda_dev)
+    keep = eng.get_option("graph")
+    x = synthetic_invoices(2, 64, 96, seed=58).to(cuda_dev)
+    z = torch.empty((2, 3, 64, 96), dtype=torch.float32, device=cuda_dev)
+    m = torch.empty((2, 3, 64, 96), dtype=torch.uint8, device=cuda_dev)
+    try:
+        eng.set_option("graph", 0)
+        eng.run(x, thresholds=[0.25, 0.40, 0.30], logits_out=z, mask_out=m)
+        torch.cuda.synchronize()
+        z0, m0 = z.clone(), m.clone()
+        eng.run(x, thresholds=[0.6, 0.5, 0.7], logits_out=z, mask_out=m)
+        torch.cuda.synchronize()
+        m1 = m.clone()
+        assert not torch.equal(m0, m1)
+        eng.set_option("graph", 1)
+        for rep in range(4):                      # direct, then captured + replayed
+            z.zero_(); m.zero_()
+            eng.run(x, thresholds=[0.25, 0.40, 0.30], logits_out=z, mask_out=m)
+            torch.cuda.synchronize()
+            assert torch.equal(z, z0) and torch.equal(m, m0), rep
+        for rep in range(2):                      # other thresholds: the graph is rebuilt
+            m.zero_()
+            eng.run(x, thresholds=[0.6, 0.5, 0.7], logits_out=z, mask_out=m)
+            torch.cuda.synchronize()
+            assert torch.equal(m, m1), rep
+        g = torch.cuda.CUDAGraph()                # the caller captures: launches go into ITS graph
+        side = torch.cuda.Stream(cuda_dev)
+        with torch.cuda.stream(side):
+            eng.run(x, thresholds=[0.25, 0.40, 0.30], logits_out=z, mask_out=m)
+            torch.cuda.synchronize()
+            with torch.cuda.graph(g, stream=side):
+                eng.run(x, thresholds=[0.25, 0.40, 0.30], logits_out=z, mask_out=m)
+        z.zero_(); m.zero_()
+        g.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(z, z0) and torch.equal(m, m0)
+    finally:
+        eng.set_option("graph", keep)
+
+
 def test_fill_sms_policy_identical(model, cuda_dev):
     """Small batches narrow the column block of the deep layers so their tiles cover the SMs (batch-1
     latency); every output element still accumulates over K in the same order: bit-identical logits, and

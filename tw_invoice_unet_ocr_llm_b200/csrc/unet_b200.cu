@@ -802,7 +802,20 @@ typedef std::tuple<const void*, int, int, int, int, void*, float*, uint8_t*, int
 
 struct Plan {
     std::vector<Step> steps;
+    // The plan's launches as ONE instantiated CUDA graph (built on the second use of a plan): a small-batch forward
+    // is 22 launches of ~10-20 us each, so a host that needs more than that per cudaLaunchKernelEx starves the GPU
+    // (batch-1 latency measured between 0.41 and 0.55 ms eager, depending on the host, against 0.39 ms replayed).
+    cudaGraphExec_t exec = nullptr;
+    float exec_thr[ub::kMaxClasses] = {};   // thresholds baked into the graph's last kernel node
+    int uses = 0;
+    bool graph_failed = false;
 };
+
+void destroy_plans(std::map<PlanKey, Plan>& plans) {
+    for (auto& kv : plans)
+        if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    plans.clear();
+}
 
 }  // namespace
 
@@ -827,6 +840,8 @@ struct unetb200_handle_s {
     int row64 = 2;              // 64-output-channel 3x3 convs on the row-stacked kernel (conv_row.cuh): bit 0 = the
                                 // one-slice layers (down1.net.3, conv1.net.3: measured equal / 5 % slower, off),
                                 // bit 1 = conv1.net.0 (measured 3-5 % faster, on)
+    int graph = 1;              // replay a plan's launches as one CUDA graph from its second use on
+    cudaStream_t cap_stream = nullptr;   // capture stream of those graphs (the caller's may be the legacy stream)
     int profile = 0;
     int* dbg = nullptr;         // pinned, device-visible watchdog record
     std::map<PlanKey, Plan> plans;
@@ -1103,6 +1118,8 @@ int unetb200_create(const unetb200_arch_t* arch, const void* blob_dev, uint64_t 
 int unetb200_destroy(unetb200_handle_t h) {
     if (!h) return 0;
     for (cudaEvent_t e : h->events) cudaEventDestroy(e);
+    destroy_plans(h->plans);
+    if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
     if (h->dbg) cudaFreeHost(h->dbg);
     delete h;
     return 0;
@@ -1143,12 +1160,14 @@ int unetb200_set_option(unetb200_handle_t h, const char* key, int value) {
     } else if (k == "row64") {
         if (value < 0 || value > 3) return fail(UNETB200_EINVAL, "row64 must be 0..3 (bit 0: Cin = 64 layers, bit 1: conv1.net.0)");
         h->row64 = value;
+    } else if (k == "graph") {
+        h->graph = value ? 1 : 0;
     } else if (k == "profile") {
         h->profile = value ? 1 : 0;
     } else {
         return fail(UNETB200_EINVAL, "unknown option " + k);
     }
-    h->plans.clear();
+    destroy_plans(h->plans);
     return 0;
 }
 
@@ -1166,6 +1185,7 @@ int unetb200_get_option(unetb200_handle_t h, const char* key, int* value) {
     else if (k == "pdl") *value = h->pdl;
     else if (k == "fill_sms") *value = h->fill_sms;
     else if (k == "row64") *value = h->row64;
+    else if (k == "graph") *value = h->graph;
     else if (k == "profile") *value = h->profile;
     else if (k == "num_sms") *value = h->num_sms;
     else return fail(UNETB200_EINVAL, "unknown option " + k);
@@ -1222,7 +1242,7 @@ static int forward_impl(unetb200_handle_t h, const void* x, int x_fmt, int n, in
         Plan plan;
         int rc = build_plan(h, x, x_fmt, n, height, width, workspace, logits, mask, mask_bits, &plan);
         if (rc) return rc;
-        if (h->plans.size() > 64) h->plans.clear();
+        if (h->plans.size() > 64) destroy_plans(h->plans);
         it = h->plans.emplace(key, std::move(plan)).first;
     }
     Plan& plan = it->second;
@@ -1239,18 +1259,54 @@ static int forward_impl(unetb200_handle_t h, const void* x, int x_fmt, int n, in
         }
         UB_CUDA(cudaEventRecord(h->events[0], s));
     }
-    int launches = 0;
-    for (size_t i = 0; i < plan.steps.size(); ++i) {
-        // the first launch of a forward keeps normal stream order (its predecessor is foreign work)
-        plan.steps[i].pdl = (h->pdl && !prof && i > 0 && plan.steps[i].kind == 1) ? 1 : 0;
-        int rc = launch_step(plan.steps[i], s);
-        if (rc) return rc;
-        ++launches;
-        if (prof) UB_CUDA(cudaEventRecord(h->events[i + 1], s));
-    }
-    h->last_launches = launches;
+    auto launch_all = [&](cudaStream_t on) -> int {
+        for (size_t i = 0; i < plan.steps.size(); ++i) {
+            // the first launch of a forward keeps normal stream order (its predecessor is foreign work)
+            plan.steps[i].pdl = (h->pdl && !prof && i > 0 && plan.steps[i].kind == 1) ? 1 : 0;
+            int rc = launch_step(plan.steps[i], on);
+            if (rc) return rc;
+            if (prof) UB_CUDA(cudaEventRecord(h->events[i + 1], on));
+        }
+        return 0;
+    };
+    h->last_launches = static_cast<int>(plan.steps.size());
     h->timed = prof;
-    return 0;
+    ++plan.uses;
+    // graph replay: not while profiling, not inside somebody else's capture, from the second use of a plan on
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (h->graph && !prof && !plan.graph_failed && plan.uses >= 2 &&
+        cudaStreamIsCapturing(s, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone) {
+        const int ncls = h->arch.n_classes;
+        if (plan.exec && mask && memcmp(plan.exec_thr, plan.steps.back().cp.thr, sizeof(float) * ncls) != 0) {
+            cudaGraphExecDestroy(plan.exec);            // other thresholds: re-capture (they are kernel parameters)
+            plan.exec = nullptr;
+        }
+        if (!plan.exec) {
+            if (!h->cap_stream && cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking) != cudaSuccess)
+                h->cap_stream = nullptr;
+            cudaGraph_t g = nullptr;
+            bool ok = h->cap_stream &&
+                      cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+            if (ok) {
+                const int rc = launch_all(h->cap_stream);
+                ok = cudaStreamEndCapture(h->cap_stream, &g) == cudaSuccess && rc == 0 && g != nullptr;
+            }
+            if (ok) ok = cudaGraphInstantiate(&plan.exec, g, 0) == cudaSuccess;
+            if (g) cudaGraphDestroy(g);
+            if (!ok) {
+                cudaGetLastError();                     // capture problems are not sticky: fall back to direct launches
+                plan.exec = nullptr;
+                plan.graph_failed = true;
+            } else {
+                memcpy(plan.exec_thr, plan.steps.back().cp.thr, sizeof plan.exec_thr);
+            }
+        }
+        if (plan.exec) {
+            UB_CUDA(cudaGraphLaunch(plan.exec, s));
+            return 0;
+        }
+    }
+    return launch_all(s);
 }
 
 int unetb200_forward(unetb200_handle_t h, const void* x, int x_fmt, int n, int height, int width,
