@@ -438,7 +438,13 @@ def main():
     e2e_run(args.warmup)
     worker.synchronize()
     e2e_ms = timed(lambda: e2e_run(args.steps), 1) / args.steps
+    # the same device-only step again, right after the end-to-end region: the GPU is power-capped and its clocks
+    # sink during the first seconds of load, so a region timed later is slower whatever it does; this is the
+    # like-for-like partner of the end-to-end figure (tools/e2e_probe.py: with the copies removed the pipeline
+    # takes the same time -- they are hidden completely)
+    dev_after_ms = timed(step, args.steps) / args.steps
     e2e = {"value": world * B / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms,
+           "device_ms_per_step_right_after": dev_after_ms, "ratio_to_device_right_after": dev_after_ms / e2e_ms,
            "h2d_bytes_per_step": int(frames_host.numel()), "d2h_bytes_per_step": int(masks_host.numel()),
            "chunk": worker.chunk,
            "api": "tw_invoice_unet_ocr_llm_b200.launcher.GpuWorker(packed=True).segment_async + synchronize (pinned "
