@@ -379,22 +379,34 @@ def main():
     layers = eng.layers
     peaks = read_peaks()
     table, tc_flops, tc_ms, tc_bytes, n_tc = [], 0.0, 0.0, 0.0, 0
+    # an up-conv folded into the following 3x3 conv (csrc/conv_phase.cuh) has no launch of its own: its ALGORITHMIC
+    # FLOPs (the reference's ConvTranspose2d, unet_model.py:38-47) are credited to the launch that does its work; the
+    # `u` tensor it no longer writes / re-reads is dropped from the algorithmic bytes
+    folded = [l.kind == nat.CONVT2X2 and layer_ms[i] == 0.0 for i, l in enumerate(layers)]
     for i, l in enumerate(layers):
-        if l.kind == nat.HEAD:
-            continue                                  # fused into conv1.net.3
+        if l.kind == nat.HEAD or folded[i]:
+            continue                                  # fused into conv1.net.3 / into the next conv
         fl = layer_flops(l, S, S) * B
         if l.name.decode() == "conv1.net.3":
             fl += layer_flops(layers[-1], S, S) * B
+        by_fold = 0.0
+        if i > 0 and folded[i - 1]:
+            up = layers[i - 1]
+            fl += layer_flops(up, S, S) * B
+            px_lo = (S >> up.level) * (S >> up.level)
+            # reads the low-resolution tensor instead of the up-conv output: + px_lo * Clow, - 4 px_lo * C (bf16)
+            by_fold = (px_lo * up.cin * 2 - 4 * px_lo * up.cout * 2) * B + 16 * up.cin * l.cout * 2
         ms = layer_ms[i]
         tf = fl / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
         tensor = l.kind in (nat.CONV3X3, nat.CONVT2X2)
-        by = layer_bytes(l, S, S) * B + l.w_bytes
+        by = layer_bytes(l, S, S) * B + l.w_bytes + by_fold
         if tensor and ms > 0:
             tc_flops += fl
             tc_ms += ms
             tc_bytes += by
             n_tc += 1
-        table.append({"layer": l.name.decode(), "kernel": "conv_tc_kernel (tcgen05)" if tensor else
+        table.append({"layer": l.name.decode() + (" (+ " + layers[i - 1].name.decode() + ", folded)" if i > 0 and folded[i - 1] else ""),
+                      "kernel": "conv_tc_kernel (tcgen05)" if tensor else
                       ("conv_tc_kernel<A_STEM> (tcgen05, in-kernel im2col; HBM / issue bound)"
                        if eng.get_option("stem_tc") else "stem_conv_kernel (CUDA cores)"),
                       "ms": round(ms, 4), "gflop": round(fl / 1e9, 2), "tflops": round(tf, 1),

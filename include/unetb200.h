@@ -87,6 +87,20 @@ int unetb200_pack_layer(const unetb200_arch_t* arch, int index, const float* wei
                         const float* bn_mean, const float* bn_var, float bn_eps, void* blob_dev,
                         void* stream);
 
+/* Decoder level `level` = 1..4 (up{level} + conv{level}.net.0, reference unet_model.py:38-51 / :70-83) with the
+ * ConvTranspose2d folded into the 3x3 conv as a four-phase sub-pixel convolution over the low-resolution tensor
+ * (csrc/conv_phase.cuh): writes the composite weights [16][Cout][Clow] bf16 and the nine border-case biases
+ * [9][Cout] fp32 into their region of the blob (behind the per-layer regions; unetb200_packed_bytes counts them).
+ * up_weight [Clow,C,2,2] / up_bias [C] (may be NULL) are the ConvTranspose2d's tensors, conv_weight [Cout,2C,3,3] /
+ * conv_bias and the BatchNorm vectors those of conv{level}.net.0 / .net.1.  Optional: a level that was not packed
+ * (or a blob that ends after the per-layer regions) runs as two launches. */
+int unetb200_pack_fused_up(const unetb200_arch_t* arch, int level, const float* up_weight, const float* up_bias,
+                           const float* conv_weight, const float* conv_bias, const float* bn_gamma,
+                           const float* bn_beta, const float* bn_mean, const float* bn_var, float bn_eps,
+                           void* blob_dev, void* stream);
+int unetb200_fused_up_info(const unetb200_arch_t* arch, int level, uint64_t* w_off, uint64_t* w_bytes,
+                           uint64_t* b_off, uint64_t* b_bytes);
+
 /* ---- model handle ---- */
 /* Replaces the model the reference builds in inference.py:17-24.  `blob_dev` (borrowed)
  * must outlive the handle.  Fails with UNETB200_EARCH on anything but sm_100. */
@@ -152,6 +166,14 @@ int unetb200_conv3x3_head(const void* src0, int c0, const void* w_packed, const 
  * bn in {64,128,256}; bn | 0x1000 selects the CTA-pair variant. */
 int unetb200_convt2x2(const void* src, int cin, const void* w_packed, const float* bias, int n,
                       int height, int width, int cout, void* out, int bn, void* stream);
+/* ConvTranspose2d(k=2,s=2) + Conv2d(3x3, pad 1) over cat([up, skip]) (+ folded BatchNorm, ReLU) as one launch:
+ * low [N,h,w,c_low] bf16, skip [N,2h,2w,c_skip] bf16 -> out [N,2h,2w,cout] bf16.  wc_packed / bias9 = the regions
+ * unetb200_pack_fused_up writes (unetb200_fused_up_info), w3_packed = the 3x3 conv's own packed weights
+ * ([9][cout][c_up + c_skip], unetb200_pack_layer), c_up = K columns of its up half.
+ * flags: bit 0 = CTA pairs, bit 1 = one phase per work unit whatever the column block (cross-check variant). */
+int unetb200_upconv3x3(const void* low, int c_low, const void* skip, int c_skip, const void* wc_packed,
+                       const void* w3_packed, int c_up, const float* bias9, int n, int h_low, int w_low, int cout,
+                       int relu, void* out, int bn, int flags, void* stream);
 /* First conv on the tensor cores (n_channels 1 or 3): w_tc = the bf16 hi/lo [64][128] layout that
  * unetb200_pack_layer(index 0) writes at blob + w_off + unetb200_stem_tc_offset(cin). */
 int unetb200_stem_tc(const void* x, int x_fmt, int cin, const void* w_tc, const float* bias, int n,

@@ -203,6 +203,41 @@ def test_row_kernel_forward_identical(model, cuda_dev):
         eng.set_option("row64", keep)
 
 
+@pytest.mark.parametrize("n,h,w,seed", [(2, 64, 96, 71), (1, 512, 512, 72), (3, 16, 16, 73), (1, 48, 272, 74)])
+def test_folded_upconv_forward(model, fixture_state, cuda_dev, n, h, w, seed):
+    """Decoder levels with the ConvTranspose2d folded into the following 3x3 conv (csrc/conv_phase.cuh; option
+    fold_up, bit k = level k): every subset of levels meets the oracle gates, the launch count drops by one per folded
+    level, and the folded forward stays within bf16 rounding noise of the two-launch forward (it skips one bf16
+    rounding of the up-conv output, so it is NOT bit-identical to it)."""
+    from oracle.unet_oracle import oracle_forward, parity_report
+    from tw_invoice_unet_ocr_llm_b200.synthetic import synthetic_invoices
+    eng = model.engine(cuda_dev)
+    assert eng.get_option("fold_avail") == 15
+    keep, keep1 = eng.get_option("fold_up"), eng.get_option("fold_one_phase")
+    x = synthetic_invoices(n, h, w, seed=seed)
+    z_ref = oracle_forward(fixture_state, x)
+    try:
+        res = {}
+        for one_phase in (0, 1):
+            eng.set_option("fold_one_phase", one_phase)
+            for mask in (0, 1, 2, 4, 8, 14, 15):
+                if one_phase and mask in (0, 4, 8):
+                    continue                      # (256-column levels run the one-phase kernel anyway)
+                eng.set_option("fold_up", mask)
+                z = eng.run(x.to(cuda_dev))[0]
+                torch.cuda.synchronize()
+                assert eng.last_launch_count() == 22 - bin(mask).count("1")
+                rep = parity_report(z_ref, z)
+                _check(rep, 0.999 if h >= 512 else 0.997)
+                res[(one_phase, mask)] = z
+        for key, z in res.items():
+            d = (z - res[(0, 0)]).abs()
+            assert float(d.max()) <= 0.2 and float(d.mean()) <= 0.02, (key, float(d.max()), float(d.mean()))
+    finally:
+        eng.set_option("fold_up", keep)
+        eng.set_option("fold_one_phase", keep1)
+
+
 def test_graph_replay_identical(model, cuda_dev):
     """From its second use on a plan is replayed as one CUDA graph: same logits and masks as direct launches, also
     after the thresholds (kernel parameters baked into the graph) change, and under a caller's own stream capture."""

@@ -60,6 +60,9 @@ SYMBOLS = {
     "unetb200_layer_info": (_I, [C.POINTER(Arch), _I, C.POINTER(Layer)]),
     "unetb200_packed_bytes": (_U64, [C.POINTER(Arch)]),
     "unetb200_pack_layer": (_I, [C.POINTER(Arch), _I, _VP, _VP, _VP, _VP, _VP, _VP, _F, _VP, _VP]),
+    "unetb200_pack_fused_up": (_I, [C.POINTER(Arch), _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _F, _VP, _VP]),
+    "unetb200_fused_up_info": (_I, [C.POINTER(Arch), _I, C.POINTER(_U64), C.POINTER(_U64), C.POINTER(_U64),
+                                    C.POINTER(_U64)]),
     "unetb200_create": (_I, [C.POINTER(Arch), _VP, _U64, _I, C.POINTER(_VP)]),
     "unetb200_destroy": (_I, [_VP]),
     "unetb200_set_option": (_I, [_VP, C.c_char_p, _I]),
@@ -73,6 +76,7 @@ SYMBOLS = {
     "unetb200_conv3x3_head": (_I, [_VP, _I, _VP, _VP, _VP, _VP, _I, _I, _I, _I, _VP, _VP,
                                    C.POINTER(_F), _I, _I, _VP]),
     "unetb200_convt2x2": (_I, [_VP, _I, _VP, _VP, _I, _I, _I, _I, _VP, _I, _VP]),
+    "unetb200_upconv3x3": (_I, [_VP, _I, _VP, _I, _VP, _VP, _I, _VP, _I, _I, _I, _I, _I, _VP, _I, _I, _VP]),
     "unetb200_stem": (_I, [_VP, _I, _I, _VP, _VP, _I, _I, _I, _VP, _VP]),
     "unetb200_stem_tc": (_I, [_VP, _I, _I, _VP, _VP, _I, _I, _I, _VP, _VP]),
     "unetb200_stem_tc_offset": (_U64, [_I]),

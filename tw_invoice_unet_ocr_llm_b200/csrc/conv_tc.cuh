@@ -68,7 +68,7 @@
 namespace ub {
 
 enum : int { EPI_STORE = 0, EPI_STORE_POOL = 1, EPI_HEAD = 2, EPI_UPSAMPLE = 3 };
-enum : int { A_TAP = 0, A_COL3 = 1, A_HALO = 2, A_STEM = 3, A_STEMP = 4, A_ROW = 5 /* conv_row.cuh */ };
+enum : int { A_TAP = 0, A_COL3 = 1, A_HALO = 2, A_STEM = 3, A_STEMP = 4, A_ROW = 5 /* conv_row.cuh */, A_PHASE = 6 /* conv_phase.cuh */ };
 
 constexpr int kMaxClasses = 8;
 
@@ -104,6 +104,10 @@ struct ConvParams {
     CUtensorMap tmB;         // weights, dims (Cin_total, rows, taps)
     CUtensorMap tmOut[4];    // output store maps ([0] for convs, [tap] for convT)
     CUtensorMap tmPool;      // pooled output store map
+    CUtensorMap tmP[4];      // conv_phase.cuh: the four (row, column) parity planes of the skip tensor, dims (C, W/2, H/2, N)
+    CUtensorMap tmB2;        // conv_phase.cuh: the 3x3 conv's own packed weights (skip half of K), dims (Cin_total, rows, 9)
+    const float* bias9;      // conv_phase.cuh: [9 border cases][Cout] fp32 (folded bias + the up-conv bias seen through the in-range taps)
+    int kskip;               // conv_phase.cuh: first K column of the skip half in tmB2 (= channels of the up-conv output)
     const float* bias;       // [Cout] fp32 (BatchNorm-folded)
     const float* head_w;     // [ncls][64] fp32      (EPI_HEAD)
     const float* head_b;     // [ncls]               (EPI_HEAD)

@@ -134,4 +134,90 @@ __global__ void pack_convt_kernel(const float* __restrict__ w, const float* __re
     if (t < cout) dst_b[t] = b ? b[t] : 0.f;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// ConvTranspose2d(2, 2) folded into the following 3x3 conv (conv_phase.cuh; unet_model.py:70-71 and the like):
+// composite 2x2 weights over the low-resolution tensor, one set per output parity (py, px):
+//   Wc[ph = 2 py + px][t = 2 a + b][co][ci] = sum_{ky in S(py, a)} sum_{kx in S(px, b)} sum_c
+//        s[co] * W3[co][c][ky][kx] * WT[ci][c][(py + ky - 1) & 1][(px + kx - 1) & 1]
+// S(p, a) = the taps k whose high-resolution row 2I + p + k - 1 lies in low-resolution row I - (1 - p) + a:
+//   p = 0: a = 0 <- {0}, a = 1 <- {1, 2};   p = 1: a = 0 <- {0, 1}, a = 1 <- {2}.
+// fp32 accumulation, one bf16 rounding.  grid (Clow / 64, Cout / 64, 16), 256 threads, 4 x 4 outputs per thread.
+__device__ __forceinline__ bool fused_tap_in(int p, int a, int k) { return ((p + k - 1) >> 1) + (1 - p) == a; }
+
+__global__ void __launch_bounds__(256) pack_fused_up_w_kernel(
+        const float* __restrict__ wT, const float* __restrict__ w3, const float* __restrict__ gamma,
+        const float* __restrict__ var, float eps, int clow, int cmid, int cin3, int cout,
+        uint16_t* __restrict__ dst) {
+    __shared__ float s3[16][65];     // [c][co]  (scaled 3x3 weights of one tap)
+    __shared__ float sT[16][65];     // [c][ci]  (up-conv weights of one phase)
+    const int pt = blockIdx.z, ph = pt >> 2, t = pt & 3;
+    const int py = ph >> 1, px = ph & 1, a = t >> 1, b = t & 1;
+    const int co0 = blockIdx.y * 64, ci0 = blockIdx.x * 64;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    float acc[4][4] = {};
+    for (int ky = 0; ky < 3; ++ky) {
+        if (!fused_tap_in(py, a, ky)) continue;
+        for (int kx = 0; kx < 3; ++kx) {
+            if (!fused_tap_in(px, b, kx)) continue;
+            const int q = (((py + ky + 1) & 1) << 1) | ((px + kx + 1) & 1);      // up-conv phase of that high-res pixel
+            for (int c0 = 0; c0 < cmid; c0 += 16) {
+                for (int e = threadIdx.x; e < 1024; e += 256) {
+                    const int c = e & 15, r = e >> 4;
+                    const int co = co0 + r;
+                    s3[c][r] = w3[(static_cast<size_t>(co) * cin3 + c0 + c) * 9 + ky * 3 + kx] * bn_scale(gamma, var, eps, co);
+                    sT[c][r] = wT[(static_cast<size_t>(ci0 + r) * cmid + c0 + c) * 4 + q];
+                }
+                __syncthreads();
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    float x3[4], xt[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { x3[i] = s3[c][ty * 4 + i]; xt[i] = sT[c][tx * 4 + i]; }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(x3[i], xt[j], acc[i][j]);
+                }
+                __syncthreads();
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            dst[(static_cast<size_t>(pt) * cout + co0 + ty * 4 + i) * clow + ci0 + tx * 4 + j] = f32_to_bf16_bits(acc[i][j]);
+}
+
+// bias9[cy * 3 + cx][co] = folded bias of the 3x3 conv + s[co] * sum over the taps INSIDE the image of
+// sum_c W3[co][c][ky][kx] * bT[c]   (cy / cx: 0 = first row / column, 1 = interior, 2 = last).  `flag` marks the
+// level's region of the blob as packed (unetb200_create reads it).
+__global__ void pack_fused_up_b_kernel(const float* __restrict__ bT, const float* __restrict__ w3,
+                                       const float* __restrict__ b3, const float* __restrict__ gamma,
+                                       const float* __restrict__ beta, const float* __restrict__ mean,
+                                       const float* __restrict__ var, float eps, int cmid, int cin3, int cout,
+                                       float* __restrict__ dst, uint32_t* __restrict__ flag) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx == 0) *flag = 0x46555345u;   // "FUSE"
+    if (idx >= 9 * cout) return;
+    const int cs = idx / cout, co = idx - cs * cout, cy = cs / 3, cx = cs - cy * 3;
+    const float s = bn_scale(gamma, var, eps, co);
+    const float b0 = b3 ? b3[co] : 0.f;
+    const float base = gamma ? (b0 - mean[co]) * s + beta[co] : b0;
+    float sum = 0.f;
+    if (bT) {
+        for (int ky = 0; ky < 3; ++ky) {
+            if ((cy == 0 && ky == 0) || (cy == 2 && ky == 2)) continue;
+            for (int kx = 0; kx < 3; ++kx) {
+                if ((cx == 0 && kx == 0) || (cx == 2 && kx == 2)) continue;
+                const float* wr = w3 + static_cast<size_t>(co) * cin3 * 9 + ky * 3 + kx;
+                float part = 0.f;
+                for (int c = 0; c < cmid; ++c) part = fmaf(wr[static_cast<size_t>(c) * 9], bT[c], part);
+                sum += part;
+            }
+        }
+    }
+    dst[idx] = fmaf(sum, s, base);
+}
+
 }  // namespace ub

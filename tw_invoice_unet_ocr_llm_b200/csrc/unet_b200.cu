@@ -18,6 +18,8 @@
 
 #include "conv_tc.cuh"
 #include "conv_row.cuh"
+#include "conv_phase.cuh"
+#include "conv_phase_multi.cuh"
 #include "errors.h"
 #include "pack.cuh"
 #include "prepost.cuh"
@@ -214,6 +216,41 @@ std::vector<unetb200_layer_t> layer_table(const unetb200_arch_t& a) {
     return out;
 }
 
+// Decoder levels with the up-conv folded into the following 3x3 conv (conv_phase.cuh): level j = 1..4 is
+// up{j} + conv{j}.net.0.  Their composite weights ([16][Cout][Clow] bf16) and border-case biases ([9][Cout] fp32,
+// then one flag word) live behind the per-layer regions of the blob.
+struct FusedUp {
+    int clow, cmid, cout;          // channels of the low-resolution source, of the up-conv output (= skip), of the conv
+    int li_up, li_conv;            // rows of the layer table
+    uint64_t w_off, w_bytes, b_off, b_bytes, flag_off;
+};
+
+std::vector<FusedUp> fused_table(const unetb200_arch_t& a) {
+    const std::vector<unetb200_layer_t> t = layer_table(a);
+    const unetb200_layer_t& last = t.back();
+    uint64_t off = (last.b_off + last.b_bytes + 255) / 256 * 256;
+    std::vector<FusedUp> out(5);
+    for (int j = 4; j >= 1; --j) {
+        FusedUp f;
+        f.li_up = 10 + 3 * (4 - j);
+        f.li_conv = f.li_up + 1;
+        f.clow = t[f.li_up].cin;
+        f.cmid = t[f.li_up].cout;
+        f.cout = t[f.li_conv].cout;
+        f.w_off = off;
+        f.w_bytes = uint64_t(16) * f.cout * f.clow * 2;
+        off = (off + f.w_bytes + 255) / 256 * 256;
+        f.b_off = off;
+        f.b_bytes = uint64_t(9) * f.cout * 4;
+        f.flag_off = f.b_off + f.b_bytes;
+        off = (f.flag_off + 4 + 255) / 256 * 256;
+        out[j] = f;
+    }
+    out[0] = FusedUp();
+    out[0].w_off = off;            // end of the blob
+    return out;
+}
+
 int check_arch(const unetb200_arch_t* a) {
     if (!a) return fail(UNETB200_EINVAL, "arch is NULL");
     if (a->base_width != 64) return fail(UNETB200_EINVAL, "base_width must be 64");
@@ -234,6 +271,7 @@ struct ConvLaunch {
     int smem = 0;                   // dynamic shared memory of this launch (set by plan_smem)
     bool pair = false;              // launched as clusters of 2 CTAs (cta_group::2)
     bool row = false;               // conv_row_kernel (conv_row.cuh): 4 x 128 tiles, ky taps stacked along N
+    bool phase = false;             // conv_phase_kernel (conv_phase.cuh): up-conv folded into the 3x3 conv
 };
 
 template <int BN, int TAPS, int AMODE, int EPI, int X = 0, bool PAIR = false>
@@ -543,6 +581,131 @@ int build_row_step(const ConvDesc& d, int num_sms, Step* st) {
     return 0;
 }
 
+// ConvTranspose2d(2,2) + 3x3 conv over cat([up, skip]) as ONE launch (conv_phase.cuh).
+struct PhaseDesc {
+    const void* low = nullptr;      // low-resolution source [N][h][w][c_low] bf16
+    int c_low = 0;
+    const void* skip = nullptr;     // skip tensor [N][2h][2w][c_skip] bf16
+    int c_skip = 0;
+    const void* wc = nullptr;       // composite weights [16][cout][c_low] bf16 (pack_fused_up_w_kernel)
+    const void* w3 = nullptr;       // the 3x3 conv's packed weights [9][cout][c_up + c_skip] bf16
+    int c_up = 0;                   // K columns of the up half in w3
+    const float* bias9 = nullptr;   // [9][cout]
+    int n = 0, h = 0, wd = 0;       // LOW-resolution size
+    int cout = 0, relu = 1;
+    void* out = nullptr;            // [N][2h][2w][cout] bf16
+    int bn = 256, pair = 1;
+    int one_phase = 0;              // 1 = one phase per unit whatever the column block (cross-check / A-B variant)
+    int* dbg = nullptr;
+};
+
+// one phase per work unit (conv_phase.cuh)
+template <int BN>
+void phase_inst(bool pair, ConvLaunch* cl, int* box_w, int* box_h, int* nph) {
+    cl->fn = pair ? ub::conv_phase_kernel<BN, true> : ub::conv_phase_kernel<BN, false>;
+    cl->a_stage = ub::kPhAStage;
+    *box_w = ub::kPhBoxW;
+    *box_h = ub::kPhBoxH;
+    *nph = 1;
+}
+// NPY x NPX phases per work unit (conv_phase_multi.cuh)
+template <int BN, int NPY, int NPX>
+void phase_multi_inst(bool pair, ConvLaunch* cl, int* box_w, int* box_h, int* nph) {
+    cl->fn = pair ? ub::conv_phase_multi_kernel<BN, true, NPY, NPX> : ub::conv_phase_multi_kernel<BN, false, NPY, NPX>;
+    cl->a_stage = ub::PhaseMultiCfg<BN, true, NPY, NPX>::A_STAGE;
+    *box_w = ub::PhaseMultiCfg<BN, true, NPY, NPX>::BW;
+    *box_h = ub::PhaseMultiCfg<BN, true, NPY, NPX>::BH;
+    *nph = NPY * NPX;
+}
+
+int build_phase_step(const PhaseDesc& d, int num_sms, Step* st) {
+    if (d.c_low <= 0 || d.c_low % 64 || d.c_skip <= 0 || d.c_skip % 64 || d.cout % 64 || d.cout <= 0 || d.c_up % 64)
+        return fail(UNETB200_EINVAL, "fused up-conv: channel counts must be multiples of 64");
+    if (d.cout > 512) return fail(UNETB200_EINVAL, "fused up-conv: at most 512 output channels");
+    int bn = d.bn;
+    if (bn > d.cout) bn = d.cout;
+    while (d.cout % bn) bn >>= 1;
+    if (!(bn == 64 || bn == 128 || bn == 256)) return fail(UNETB200_EINVAL, "fused up-conv: bad column block");
+    const bool pair = d.pair != 0;
+    st->kind = 1;
+    ConvLaunch& cl = st->conv;
+    cl = ConvLaunch();
+    cl.phase = true;
+    cl.pair = pair;
+    // phases per work unit: 1 for 256-column blocks (conv_phase.cuh), px = 0, 1 side by side for 128, all four for 64
+    // (conv_phase_multi.cuh); one_phase forces the one-phase kernel (cross-check / A-B)
+    int box_w = 0, box_h = 0, nph = 1;
+    if (bn == 256) phase_inst<256>(pair, &cl, &box_w, &box_h, &nph);
+    else if (bn == 128 && d.one_phase) phase_inst<128>(pair, &cl, &box_w, &box_h, &nph);
+    else if (bn == 128) phase_multi_inst<128, 1, 2>(pair, &cl, &box_w, &box_h, &nph);
+    else if (d.one_phase) phase_inst<64>(pair, &cl, &box_w, &box_h, &nph);
+    else phase_multi_inst<64, 2, 2>(pair, &cl, &box_w, &box_h, &nph);
+    cl.b_tap = (pair ? bn / 2 : bn) * 128;
+    cl.b_stage = cl.b_tap;
+    ub::ConvParams& p = st->cp;
+    memset(&p, 0, sizeof p);
+    int rc;
+    const int ho = 2 * d.h, wo = 2 * d.wd;
+    if ((rc = make_act_map(&p.tmA0, d.low, d.c_low, d.wd, d.h, d.n, box_w, box_h))) return rc;
+    p.tmA1 = p.tmA0;
+    p.tmPool = p.tmA0;
+    for (int q = 0; q < 4; ++q) {
+        const int qy = q >> 1, qx = q & 1;
+        // parity plane (qy, qx) of the skip tensor / of the output: pixel (i, j) of the plane is (2i + qy, 2j + qx)
+        const char* sb = static_cast<const char*>(d.skip) + (uint64_t(qy) * wo + qx) * d.c_skip * 2;
+        if ((rc = make_map4(&p.tmP[q], sb, d.c_skip, d.wd, d.h, d.n, uint64_t(2) * d.c_skip * 2,
+                            uint64_t(2) * wo * d.c_skip * 2, uint64_t(ho) * wo * d.c_skip * 2, box_w, box_h)))
+            return rc;
+        const char* ob = static_cast<const char*>(d.out) + (uint64_t(qy) * wo + qx) * d.cout * 2;
+        if ((rc = make_map4(&p.tmOut[q], ob, d.cout, d.wd, d.h, d.n, uint64_t(2) * d.cout * 2,
+                            uint64_t(2) * wo * d.cout * 2, uint64_t(ho) * wo * d.cout * 2, 8, 4)))
+            return rc;
+    }
+    if ((rc = make_w_map(&p.tmB, d.wc, d.c_low, d.cout, 16, pair ? bn / 2 : bn, 1))) return rc;
+    if ((rc = make_w_map(&p.tmB2, d.w3, d.c_up + d.c_skip, d.cout, 9, pair ? bn / 2 : bn, 1))) return rc;
+    p.bias9 = d.bias9;
+    p.kskip = d.c_up;
+    p.dbg = d.dbg;
+    p.C0 = d.c_low; p.C1 = d.c_skip; p.H = d.h; p.W = d.wd; p.NIMG = d.n; p.Cout = d.cout;
+    p.tiles_x = (d.wd + 7) / 8;
+    p.tiles_y = (d.h + 15) / 16;
+    p.n_blocks = d.cout / bn;
+    const long long m_tiles = 1LL * p.tiles_x * p.tiles_y * d.n;
+    const long long units = (pair ? (m_tiles + 1) / 2 : m_tiles) * (4 / nph) * p.n_blocks;
+    if (units > 0x7fffffffLL) return fail(UNETB200_EINVAL, "conv: too many tiles");
+    p.total_tiles = static_cast<int>(m_tiles * 4 * p.n_blocks);
+    p.relu = d.relu;
+    // shared memory: [A ring][B ring][out staging][barriers][bias9]
+    const int bias_bytes = (9 * d.cout * 4 + 1023) / 1024 * 1024;
+    const int budget = ub::kSmemLimit - ub::kStaticSmem - 1024 /*alignment slack*/ - bias_bytes - ub::kBarBytes;
+    int nb = (bn == 256 ? 3 * 32768 : (bn == 128 ? 5 * 16384 : 8 * 8192)) / cl.b_stage;
+    if (nb > ub::kMaxRing) nb = ub::kMaxRing;
+    const int n_out = 2, n_epi = 1;
+    int na = (budget - n_epi * n_out * ub::kOutStage - nb * cl.b_stage) / cl.a_stage;
+    if (na > ub::kMaxRing) na = ub::kMaxRing;
+    if (na < 2) return fail(UNETB200_EINVAL, "fused up-conv: shared memory plan does not fit");
+    p.na = na; p.nb = nb; p.wstat = 0; p.n_out = n_out; p.n_epi = n_epi;
+    p.off_b = na * cl.a_stage;
+    p.off_out = p.off_b + nb * cl.b_stage;
+    p.off_pool = p.off_out + n_epi * n_out * ub::kOutStage;
+    p.off_bar = p.off_pool;
+    p.off_patch = p.off_bar + ub::kBarBytes;
+    cl.smem = p.off_patch + bias_bytes + 1024;
+    p.fd_tpi = ub::make_fastdiv(static_cast<uint32_t>(p.tiles_x * p.tiles_y));
+    p.fd_tx = ub::make_fastdiv(static_cast<uint32_t>(p.tiles_x));
+    p.fd_nb = ub::make_fastdiv(static_cast<uint32_t>(p.n_blocks));
+    p.fd_na = ub::make_fastdiv(static_cast<uint32_t>(na));
+    p.fd_nout = ub::make_fastdiv(static_cast<uint32_t>(n_out));
+    if (pair) {
+        const long long pairs = units < num_sms / 2 ? units : num_sms / 2;
+        st->grid = dim3(static_cast<unsigned>(2 * pairs));
+    } else {
+        st->grid = dim3(static_cast<unsigned>(units < num_sms ? units : num_sms));
+    }
+    st->block = dim3(384);
+    return 0;
+}
+
 int build_conv_step(const ConvDesc& d, int num_sms, Step* st) {
     if (d.amode == ub::A_ROW) return build_row_step(d, num_sms, st);
     const bool stemp = d.amode == ub::A_STEMP;
@@ -840,6 +1003,12 @@ struct unetb200_handle_s {
     int row64 = 2;              // 64-output-channel 3x3 convs on the row-stacked kernel (conv_row.cuh): bit 0 = the
                                 // one-slice layers (down1.net.3, conv1.net.3: measured equal / 5 % slower, off),
                                 // bit 1 = conv1.net.0 (measured 3-5 % faster, on)
+    int fold_up = 14;           // bit k: decoder level k (H >> k; bit 3 = up4 + conv4.net.0) runs as ONE launch with the
+                                // up-conv folded into the 3x3 conv (conv_phase.cuh); masked by `fold_avail`
+    int fold_one_phase = 0;     // A/B: folded levels run one phase per work unit whatever the column block
+    int fold_avail = 0;         // levels whose composite weights were packed into the blob (unetb200_pack_fused_up)
+    std::vector<FusedUp> fused;
+    std::vector<int> last_layers;   // layer-table row of every launch of the last forward
     int graph = 1;              // replay a plan's launches as one CUDA graph from its second use on
     cudaStream_t cap_stream = nullptr;   // capture stream of those graphs (the caller's may be the legacy stream)
     int profile = 0;
@@ -954,8 +1123,24 @@ int build_plan(unetb200_handle_t h, const void* x, int x_fmt, int n, int H, int 
     for (int k = 3; k >= 0; --k) {
         const int li_up = 10 + 3 * (3 - k);
         const int co = bw << k;
-        if ((rc = convt(li_up, prev, k + 1, P(L.u[k])))) return rc;
-        if ((rc = conv(li_up + 1, P(L.u[k]), co, P(L.c[k]), co, k, P(L.ca[k]), nullptr))) return rc;
+        if ((h->fold_up & h->fold_avail) >> k & 1) {
+            // up_{k+1} folded into conv_{k+1}.net.0: one launch over the low-resolution tensor and the skip tensor
+            const FusedUp& f = h->fused[k + 1];
+            PhaseDesc d;
+            d.low = prev; d.c_low = f.clow; d.skip = P(L.c[k]); d.c_skip = co;
+            d.wc = h->blob + f.w_off; d.w3 = Wp(li_up + 1); d.c_up = f.cmid;
+            d.bias9 = reinterpret_cast<const float*>(h->blob + f.b_off);
+            d.n = n; d.h = H >> (k + 1); d.wd = W >> (k + 1); d.cout = f.cout; d.relu = 1;
+            d.out = P(L.ca[k]); d.bn = h->bn_max; d.pair = h->pair >= 1; d.dbg = h->dbg;
+            d.one_phase = h->fold_one_phase;
+            Step st;
+            if ((rc = build_phase_step(d, h->num_sms, &st))) return rc;
+            st.layer = li_up + 1;
+            plan->steps.push_back(st);
+        } else {
+            if ((rc = convt(li_up, prev, k + 1, P(L.u[k])))) return rc;
+            if ((rc = conv(li_up + 1, P(L.u[k]), co, P(L.c[k]), co, k, P(L.ca[k]), nullptr))) return rc;
+        }
         if (k > 0) {
             if ((rc = conv(li_up + 2, P(L.ca[k]), co, nullptr, 0, k, P(L.cc[k]), nullptr))) return rc;
             prev = P(L.cc[k]);
@@ -1009,9 +1194,44 @@ int unetb200_layer_info(const unetb200_arch_t* arch, int index, unetb200_layer_t
 
 uint64_t unetb200_packed_bytes(const unetb200_arch_t* arch) {
     if (check_arch(arch)) return 0;
-    auto t = layer_table(*arch);
-    const unetb200_layer_t& l = t.back();
-    return (l.b_off + l.b_bytes + 255) / 256 * 256;
+    return fused_table(*arch)[0].w_off;      // per-layer regions, then the folded up-conv levels
+}
+
+int unetb200_fused_up_info(const unetb200_arch_t* arch, int level, uint64_t* w_off, uint64_t* w_bytes,
+                           uint64_t* b_off, uint64_t* b_bytes) {
+    int rc = check_arch(arch);
+    if (rc) return rc;
+    if (level < 1 || level > 4) return fail(UNETB200_EINVAL, "fused up-conv level must be 1..4");
+    const FusedUp f = fused_table(*arch)[level];
+    if (w_off) *w_off = f.w_off;
+    if (w_bytes) *w_bytes = f.w_bytes;
+    if (b_off) *b_off = f.b_off;
+    if (b_bytes) *b_bytes = f.b_bytes;
+    return 0;
+}
+
+int unetb200_pack_fused_up(const unetb200_arch_t* arch, int level, const float* up_weight, const float* up_bias,
+                           const float* conv_weight, const float* conv_bias, const float* bn_gamma,
+                           const float* bn_beta, const float* bn_mean, const float* bn_var, float bn_eps,
+                           void* blob_dev, void* stream) {
+    int rc = check_arch(arch);
+    if (rc) return rc;
+    if (level < 1 || level > 4) return fail(UNETB200_EINVAL, "fused up-conv level must be 1..4");
+    if (!up_weight || !conv_weight || !blob_dev) return fail(UNETB200_EINVAL, "weight/blob pointer is NULL");
+    if (bn_gamma && (!bn_beta || !bn_mean || !bn_var))
+        return fail(UNETB200_EINVAL, "BatchNorm needs gamma, beta, mean and var together");
+    const FusedUp f = fused_table(*arch)[level];
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    char* blob = static_cast<char*>(blob_dev);
+    const int cin3 = 2 * f.cmid;                 // conv{level}.net.0 reads cat([up, skip])
+    ub::pack_fused_up_w_kernel<<<dim3(f.clow / 64, f.cout / 64, 16), 256, 0, s>>>(
+        up_weight, conv_weight, bn_gamma, bn_var, bn_eps, f.clow, f.cmid, cin3, f.cout,
+        reinterpret_cast<uint16_t*>(blob + f.w_off));
+    ub::pack_fused_up_b_kernel<<<(9 * f.cout + 127) / 128, 128, 0, s>>>(
+        up_bias, conv_weight, conv_bias, bn_gamma, bn_beta, bn_mean, bn_var, bn_eps, f.cmid, cin3, f.cout,
+        reinterpret_cast<float*>(blob + f.b_off), reinterpret_cast<uint32_t*>(blob + f.flag_off));
+    UB_CUDA(cudaGetLastError());
+    return 0;
 }
 
 int unetb200_pack_layer(const unetb200_arch_t* arch, int index, const float* weight,
@@ -1079,7 +1299,10 @@ int unetb200_create(const unetb200_arch_t* arch, const void* blob_dev, uint64_t 
     int rc = check_arch(arch);
     if (rc) return rc;
     if (!blob_dev || !out) return fail(UNETB200_EINVAL, "blob/out pointer is NULL");
-    if (blob_bytes < unetb200_packed_bytes(arch)) return fail(UNETB200_EINVAL, "weights blob too small");
+    const std::vector<FusedUp> fused = fused_table(*arch);
+    // the folded up-conv regions are optional: a blob that ends after the per-layer regions runs the unfused plan
+    const bool has_fused = blob_bytes >= fused[0].w_off;
+    if (blob_bytes < fused[4].w_off) return fail(UNETB200_EINVAL, "weights blob too small");
     UB_CUDA(cudaSetDevice(device));
     if ((rc = check_sm100())) return rc;
     if (!encode_tiled()) return fail(UNETB200_ECUDA, "cuTensorMapEncodeTiled entry point unavailable");
@@ -1093,7 +1316,23 @@ int unetb200_create(const unetb200_arch_t* arch, const void* blob_dev, uint64_t 
     cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&h->dbg), 64, cudaHostAllocMapped);
     if (e != cudaSuccess) { delete h; return fail(UNETB200_ECUDA, "cudaHostAlloc(dbg) failed"); }
     memset(h->dbg, 0, 64);
-    const char* env = getenv("UNETB200_AMODE");
+    h->fused = fused;
+    if (has_fused) {
+        for (int j = 1; j <= 4; ++j) {
+            uint32_t flag = 0;
+            if (cudaMemcpy(&flag, h->blob + fused[j].flag_off, 4, cudaMemcpyDeviceToHost) != cudaSuccess) {
+                cudaFreeHost(h->dbg);
+                delete h;
+                return fail(UNETB200_ECUDA, "reading the blob failed");
+            }
+            if (flag == 0x46555345u) h->fold_avail |= 1 << (j - 1);
+        }
+    }
+    const char* env = getenv("UNETB200_FOLD_UP");
+    if (env) h->fold_up = atoi(env) & 15;
+    env = getenv("UNETB200_FOLD_ONE_PHASE");
+    if (env) h->fold_one_phase = atoi(env) ? 1 : 0;
+    env = getenv("UNETB200_AMODE");
     if (env) h->amode = atoi(env);
     env = getenv("UNETB200_BN_MAX");
     if (env) h->bn_max = atoi(env);
@@ -1160,6 +1399,11 @@ int unetb200_set_option(unetb200_handle_t h, const char* key, int value) {
     } else if (k == "row64") {
         if (value < 0 || value > 3) return fail(UNETB200_EINVAL, "row64 must be 0..3 (bit 0: Cin = 64 layers, bit 1: conv1.net.0)");
         h->row64 = value;
+    } else if (k == "fold_up") {
+        if (value < 0 || value > 15) return fail(UNETB200_EINVAL, "fold_up must be 0..15 (bit k: decoder level k)");
+        h->fold_up = value;
+    } else if (k == "fold_one_phase") {
+        h->fold_one_phase = value ? 1 : 0;
     } else if (k == "graph") {
         h->graph = value ? 1 : 0;
     } else if (k == "profile") {
@@ -1185,6 +1429,9 @@ int unetb200_get_option(unetb200_handle_t h, const char* key, int* value) {
     else if (k == "pdl") *value = h->pdl;
     else if (k == "fill_sms") *value = h->fill_sms;
     else if (k == "row64") *value = h->row64;
+    else if (k == "fold_up") *value = h->fold_up & h->fold_avail;
+    else if (k == "fold_avail") *value = h->fold_avail;
+    else if (k == "fold_one_phase") *value = h->fold_one_phase;
     else if (k == "graph") *value = h->graph;
     else if (k == "profile") *value = h->profile;
     else if (k == "num_sms") *value = h->num_sms;
@@ -1270,6 +1517,8 @@ static int forward_impl(unetb200_handle_t h, const void* x, int x_fmt, int n, in
         return 0;
     };
     h->last_launches = static_cast<int>(plan.steps.size());
+    h->last_layers.resize(plan.steps.size());
+    for (size_t i = 0; i < plan.steps.size(); ++i) h->last_layers[i] = plan.steps[i].layer;
     h->timed = prof;
     ++plan.uses;
     // graph replay: not while profiling, not inside somebody else's capture, from the second use of a plan on
@@ -1331,10 +1580,11 @@ int unetb200_layer_times(unetb200_handle_t h, float* ms, int count) {
     // steps follow the layer table except out_conv, which is fused into conv1.net.3
     const int nsteps = h->last_launches;
     UB_CUDA(cudaEventSynchronize(h->events[nsteps]));
-    for (int i = 0; i < nsteps && i < count && i < nl; ++i) {
+    for (int i = 0; i < nsteps; ++i) {
         float t = 0.f;
         UB_CUDA(cudaEventElapsedTime(&t, h->events[i], h->events[i + 1]));
-        ms[i] = t;
+        const int li = h->last_layers[i];       // (a folded up-conv leaves its row at 0 and adds to its conv's)
+        if (li >= 0 && li < count && li < nl) ms[li] += t;
     }
     return 0;
 }
@@ -1408,6 +1658,23 @@ int unetb200_convt2x2(const void* src, int cin, const void* w_packed, const floa
     if ((rc = device_num_sms(&sms))) return rc;
     Step st;
     if ((rc = build_conv_step(d, sms, &st))) return rc;
+    return launch_step(st, static_cast<cudaStream_t>(stream));
+}
+
+int unetb200_upconv3x3(const void* low, int c_low, const void* skip, int c_skip, const void* wc_packed,
+                       const void* w3_packed, int c_up, const float* bias9, int n, int h_low, int w_low, int cout,
+                       int relu, void* out, int bn, int flags, void* stream) {
+    int rc;
+    if ((rc = check_sm100())) return rc;
+    if (!low || !skip || !wc_packed || !w3_packed || !bias9 || !out) return fail(UNETB200_EINVAL, "NULL pointer");
+    PhaseDesc d;
+    d.low = low; d.c_low = c_low; d.skip = skip; d.c_skip = c_skip; d.wc = wc_packed; d.w3 = w3_packed;
+    d.c_up = c_up; d.bias9 = bias9; d.n = n; d.h = h_low; d.wd = w_low; d.cout = cout; d.relu = relu; d.out = out;
+    d.bn = bn; d.pair = flags & 1; d.one_phase = (flags >> 1) & 1; d.dbg = g_hook_dbg();
+    int sms = 0;
+    if ((rc = device_num_sms(&sms))) return rc;
+    Step st;
+    if ((rc = build_phase_step(d, sms, &st))) return rc;
     return launch_step(st, static_cast<cudaStream_t>(stream));
 }
 

@@ -97,6 +97,16 @@ class Engine:
             nat.check(self._lib.unetb200_pack_layer(
                 C.byref(self.arch), i, _ptr(w), _ptr(b), _ptr(g), _ptr(be), _ptr(mu), _ptr(var),
                 bn_eps, self.blob.data_ptr(), stream))
+        # decoder levels with the up-conv folded into the following 3x3 conv (csrc/conv_phase.cuh,
+        # reference unet_model.py:38-51): composite weights from the fp32 tensors of up{j} and conv{j}.net.0/.1
+        for j in (4, 3, 2, 1):
+            up, cv, bn = f"up{j}", f"conv{j}.net.0", f"conv{j}.net.1"
+            nat.check(self._lib.unetb200_pack_fused_up(
+                C.byref(self.arch), j, _ptr(dev(up + ".weight")),
+                _ptr(dev(up + ".bias")) if (up + ".bias") in state else None,
+                _ptr(dev(cv + ".weight")), _ptr(dev(cv + ".bias")) if (cv + ".bias") in state else None,
+                _ptr(dev(bn + ".weight")), _ptr(dev(bn + ".bias")), _ptr(dev(bn + ".running_mean")),
+                _ptr(dev(bn + ".running_var")), bn_eps, self.blob.data_ptr(), stream))
         torch.cuda.current_stream(self.device).synchronize()
 
     # ------------------------------------------------------------------ options
