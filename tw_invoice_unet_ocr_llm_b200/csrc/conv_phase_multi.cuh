@@ -1,122 +1,47 @@
-// Folded up-conv (see conv_phase.cuh) with SEVERAL PHASES of a tile position per work unit.
+// Folded up-conv (see conv_phase.cuh) with SEVERAL PHASES of a tile position per work unit, for the column blocks
+// of 128 and 64 output channels.
 //
-// A unit computes NPY x NPX phases side by side in TMEM (NPH * BN accumulator columns), because phases of one
-// position read the same boxes and, in the skip half, the same tap weights:
-//   BN = 128 : 1 x 2  (px = 0, 1): the smem fill per UMMA halves -- one phase per unit measured 70 % tensor pipe
-//   BN = 64  : 2 x 2
-// K walk of a unit; every box covers the tile plus the halo its phases need, BH x BW = (16 + NPY) x (8 + NPX):
-//   up half   : per 64-channel slice of x: ONE item (one box of x); per phase 4 taps = 2x2 views of the box, each
-//               against its own composite weight stage
-//   skip half : per 64-channel slice of s: two items (row parity qy), each BOTH column planes; tap (ky, kx) is one
-//               weight stage used by the two phases px = 0, 1 (on planes qx = (px + kx - 1) & 1).
+// Why.  With one phase per unit every UMMA of N <= 128 needs its own activation fill and weight stage: the
+// 128-column kernel ran at 70 % tensor-pipe activity (shared-memory fill + one barrier round trip per 4 UMMAs of 64
+// cycles).  Phases of ONE tile position read the same boxes and, in the skip half, the same tap weights, so a unit
+// computes NPY x NPX phases side by side in TMEM (NPH * BN accumulator columns, two units in flight):
+//   BN = 128 : 1 x 2  (px = 0, 1; the unit's py alternates)        BN = 64 : 2 x 2  (all four)
+// K walk of a unit.  Every box is (16 + NPY) x (8 + NPX) positions with origin (I0 - 1 + [NPY == 1] py, J0 - 1), i.e.
+// the tile plus the halo the unit's phases need; one box = one slot of the activation ring.
+//   up half   : per 64-channel slice of x ONE box; per phase ONE weight stage = its four composite taps (2x2 views
+//               of the box): 16 UMMAs per barrier round trip
+//   skip half : per 64-channel slice of s and row parity qy TWO boxes (the column planes qx = 0, 1, two ring slots);
+//               per tap row ky ONE weight stage = the taps (ky, 0..2), each used by both phases px = 0, 1 on plane
+//               qx = (px + kx - 1) & 1: 24 UMMAs per round trip.  (NPY = 2: the three ky of a row parity belong to
+//               py = (qy + ky + 1) & 1; NPY = 1: only the ky of the unit's py.)
+// The MMA warp's walk is static per (NPY, NPX, py): every view offset is an immediate and a stage's UMMAs sit in
+// one elect block (conv_phase.cuh explains why that matters).
 #pragma once
+#include <type_traits>
+
 #include "conv_phase.cuh"
 
 namespace ub {
 
 template <int BN, bool PAIR, int NPY, int NPX>
 struct PhaseMultiCfg {
+    static_assert(NPX == 2 && (NPY == 1 || NPY == 2), "1 x 2 or 2 x 2 phases per unit");
     static constexpr int BW = 8 + NPX, BH = 16 + NPY;            // box: tile + the halo of the unit's phases
     static constexpr int BOX_TX = BW * BH * 128;                 // bytes of one box
-    static constexpr int BOX_STRIDE = (BOX_TX + 1023) / 1024 * 1024;
-    static constexpr int A_STAGE = NPX * BOX_STRIDE;             // largest item: NPX planes
+    static constexpr int A_STAGE = (BOX_TX + 1023) / 1024 * 1024;   // one ring slot = one box
     static constexpr int B_TAP = (PAIR ? BN / 2 : BN) * 128;     // one tap's weight rows (a CTA pair splits them)
+    static constexpr int B_STAGE = 4 * B_TAP;                    // weight ring stage: 4 composite taps / 3 skip taps
     static constexpr int NPH = NPY * NPX;                        // phases per unit
     static constexpr int NG = 4 / NPH;                           // phase groups per tile position
-    static constexpr int NACC = 512 / (NPH * BN) >= 4 ? 4 : 512 / (NPH * BN);
+    static constexpr int NACC = 2;
     static constexpr int TMEM_COLS = NACC * NPH * BN;
-    static_assert(NPH * BN <= 256, "two units must fit in TMEM");
+    static_assert(NPH * BN == 256, "two units fill TMEM");
 };
-
-// The K walk of one unit, shared by the three roles that must agree on it.  Calls, in order:
-//   item(tm0, tm1, nbox, c)               an activation item: nbox boxes (maps tm0, tm1) of channel slice c
-//   tap(tmw, k0, wtap, nmm, pl[], view[], box[], fresh)   one weight stage (map tmw, K column k0, tap index wtap) and
-//                                         the nmm (phase-local accumulator, view offset in box rows, box) MMAs using
-//                                         it; fresh = these are the first MMAs into their accumulators
-//   item_end()
-// The unit's first phase (PYU, PXU) is a template argument and every loop below the channel-slice loops unrolls, so
-// that in the MMA warp -- ONE thread feeding the tensor pipe, ~5 cycles per dependent instruction -- views, tap
-// indices and tap counts are immediates: the first, generic form of this walk (runtime phase, loops with
-// `continue`) spent 88 instructions per tap and held the N = 256 kernel at 85 % tensor-pipe activity; written out
-// per phase it is 98 %.
-template <int NPY, int NPX, int PYU, int PXU, typename FI, typename FT, typename FE>
-__device__ __forceinline__ void phase_walk_c(const ConvParams& p, FI& item, FT& tap, FE& item_end) {
-    constexpr int BW = 8 + NPX;
-    constexpr int oyo = NPY == 1 ? PYU : 0, oxo = NPX == 1 ? PXU : 0;   // box origin = (I0 - 1 + oyo, J0 - 1 + oxo)
-    const int n_cs0 = p.C0 >> 6, n_cs1 = p.C1 >> 6;
-#pragma unroll 1
-    for (int cs = 0; cs < n_cs0; ++cs) {
-        item(&p.tmA0, &p.tmA0, 1, cs << 6);
-#pragma unroll
-        for (int pyl = 0; pyl < NPY; ++pyl)
-#pragma unroll
-            for (int pxl = 0; pxl < NPX; ++pxl)
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    const int py = PYU + pyl, px = PXU + pxl;
-                    // low-resolution offset (a - (1 - py), b - (1 - px)) of tap (a, b) = (t >> 1, t & 1)
-                    const int pl[2] = {pyl * NPX + pxl, 0};
-                    const int view[2] = {((t >> 1) + py - oyo) * BW + ((t & 1) + px - oxo), 0};
-                    const int box[2] = {0, 0};
-                    tap(&p.tmB, cs << 6, (py * 2 + px) * 4 + t, 1, pl, view, box, cs == 0 && t == 0);
-                }
-        item_end();
-    }
-#pragma unroll 1
-    for (int cs = 0; cs < n_cs1; ++cs) {
-#pragma unroll
-        for (int qy = 0; qy < 2; ++qy)
-#pragma unroll
-            for (int qxi = 0; qxi < (NPX == 1 ? 2 : 1); ++qxi) {
-                if (NPX == 1) item(&p.tmP[qy * 2 + qxi], &p.tmP[qy * 2 + qxi], 1, cs << 6);
-                else item(&p.tmP[qy * 2], &p.tmP[qy * 2 + 1], 2, cs << 6);
-#pragma unroll
-                for (int ky = 0; ky < 3; ++ky) {
-                    const int py = (qy + ky + 1) & 1;            // the output row parity whose tap ky reads plane rows qy
-                    if (py < PYU || py >= PYU + NPY) continue;
-                    const int vy = ((py + ky - 1) >> 1) + 1 - oyo;
-#pragma unroll
-                    for (int kx = 0; kx < 3; ++kx) {
-                        int pl[2] = {0, 0}, view[2] = {0, 0}, box[2] = {0, 0};
-                        int nmm = 0;
-#pragma unroll
-                        for (int pxl = 0; pxl < NPX; ++pxl) {
-                            const int px = PXU + pxl, qx = (px + kx + 1) & 1;
-                            if (NPX == 1 && qx != qxi) continue;
-                            pl[nmm] = (py - PYU) * NPX + pxl;
-                            view[nmm] = vy * BW + ((px + kx - 1) >> 1) + 1 - oxo;
-                            box[nmm] = NPX == 1 ? 0 : qx;
-                            ++nmm;
-                        }
-                        if (nmm) tap(&p.tmB2, p.kskip + (cs << 6), ky * 3 + kx, nmm, pl, view, box, false);
-                    }
-                }
-                item_end();
-            }
-    }
-}
-
-template <int NPY, int NPX, typename FI, typename FT, typename FE>
-__device__ __forceinline__ void phase_walk(const ConvParams& p, int py_u, int px_u, FI&& item, FT&& tap, FE&& item_end) {
-    if (NPY == 2) {
-        phase_walk_c<NPY, NPX, 0, 0>(p, item, tap, item_end);
-    } else if (NPX == 2) {
-        if (py_u == 0) phase_walk_c<NPY, NPX, 0, 0>(p, item, tap, item_end);
-        else phase_walk_c<NPY, NPX, (NPY == 1 ? 1 : 0), 0>(p, item, tap, item_end);
-    } else {
-        switch (py_u * 2 + px_u) {
-            case 0: phase_walk_c<NPY, NPX, 0, 0>(p, item, tap, item_end); break;
-            case 1: phase_walk_c<NPY, NPX, 0, (NPX == 1 ? 1 : 0)>(p, item, tap, item_end); break;
-            case 2: phase_walk_c<NPY, NPX, (NPY == 1 ? 1 : 0), 0>(p, item, tap, item_end); break;
-            default: phase_walk_c<NPY, NPX, (NPY == 1 ? 1 : 0), (NPX == 1 ? 1 : 0)>(p, item, tap, item_end); break;
-        }
-    }
-}
 
 template <int BN, bool PAIR, int NPY, int NPX>
 __global__ void __launch_bounds__(384, 1) conv_phase_multi_kernel(const __grid_constant__ ConvParams p) {
     using Cfg = PhaseMultiCfg<BN, PAIR, NPY, NPX>;
-    constexpr int NPH = Cfg::NPH, NG = Cfg::NG;
+    constexpr int NPH = Cfg::NPH, NG = Cfg::NG, BW = Cfg::BW;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t sA = smem_base;
@@ -169,21 +94,21 @@ __global__ void __launch_bounds__(384, 1) conv_phase_multi_kernel(const __grid_c
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (s_tmem_ptr - smem_base));
     pdl_launch_dependents();
 
+    const int n_cs0 = p.C0 >> 6;                    // 64-channel slices of the low-resolution source
+    const int n_cs1 = p.C1 >> 6;                    //                  ... of the skip tensor
     const int tiles_per_img = p.tiles_x * p.tiles_y;
     const uint32_t rank = PAIR ? cluster_ctarank() : 0;
     const int m_tiles = tiles_per_img * p.NIMG;
     const int n_units = (PAIR ? ((m_tiles + 1) >> 1) : m_tiles) * NG * p.n_blocks;
     const int first_unit = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
     const int unit_stride = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
-    // unit -> (pixel tile, first phase of the group, column block): column block fastest, then the phase groups
-    // of one tile position (they re-read the same boxes: L2 hits), then the position
-    auto decode = [&](int u, int& mt, int& py_u, int& px_u, int& nb) -> bool {
+    // unit -> (pixel tile, py of the unit [NPY == 1], column block): column block fastest, then the two py groups
+    // of one tile position (they re-read the same low-resolution boxes: L2 hits), then the position
+    auto decode = [&](int u, int& mt, int& py_u, int& nb) -> bool {
         int t;
         fdivmod(static_cast<uint32_t>(u), p.fd_nb, t, nb);
-        const int gi = t & (NG - 1);
-        const int g = NG == 4 ? t >> 2 : (NG == 2 ? t >> 1 : t);
-        py_u = NPY == 2 ? 0 : (NPX == 2 ? gi : gi >> 1);
-        px_u = NPX == 2 ? 0 : gi & 1;
+        py_u = NPY == 2 ? 0 : (t & 1);
+        const int g = NPY == 2 ? t : (t >> 1);
         mt = PAIR ? 2 * g + static_cast<int>(rank) : g;
         const bool valid = mt < m_tiles;
         if (!valid) mt = m_tiles - 1;
@@ -191,115 +116,171 @@ __global__ void __launch_bounds__(384, 1) conv_phase_multi_kernel(const __grid_c
     };
 
     if (warp == 0) {
-        // ===================== TMA producer: activations ======================
+        // ===================== TMA producer: activations (one box per ring slot) ======================
         if (lane == 0) {
             pdl_wait();
             uint32_t sa = 0, pa = 0;
             for (int u = first_unit; u < n_units; u += unit_stride) {
-                int mt, py_u, px_u, nb, n, r, by, bx;
-                decode(u, mt, py_u, px_u, nb);
+                int mt, py_u, nb, n, r, by, bx;
+                decode(u, mt, py_u, nb);
                 fdivmod(static_cast<uint32_t>(mt), p.fd_tpi, n, r);
                 fdivmod(static_cast<uint32_t>(r), p.fd_tx, by, bx);
-                const int oy = by * 16 - 1 + (NPY == 1 ? py_u : 0), ox = bx * 8 - 1 + (NPX == 1 ? px_u : 0);
-                phase_walk<NPY, NPX>(p, py_u, px_u,
-                    [&](const CUtensorMap* tm0, const CUtensorMap* tm1, int nbox, int ca) {
-                        mbar_wait(bar_a_empty + 8 * sa, pa ^ 1, 1, p.dbg);
-                        const uint32_t dst = sA + sa * Cfg::A_STAGE;
-                        if (PAIR) {
-                            const uint32_t fb = mapa_shared(bar_a_full + 8 * sa, 0);
-                            if (rank == 0) mbar_expect_tx(bar_a_full + 8 * sa, 2 * nbox * Cfg::BOX_TX); else mbar_arrive_cluster(fb);
-                            tma_load_4d_pair(dst, tm0, fb, ca, ox, oy, n);
-                            if (nbox == 2) tma_load_4d_pair(dst + Cfg::BOX_STRIDE, tm1, fb, ca, ox, oy, n);
-                        } else {
-                            mbar_expect_tx(bar_a_full + 8 * sa, nbox * Cfg::BOX_TX);
-                            tma_load_4d(dst, tm0, bar_a_full + 8 * sa, ca, ox, oy, n);
-                            if (nbox == 2) tma_load_4d(dst + Cfg::BOX_STRIDE, tm1, bar_a_full + 8 * sa, ca, ox, oy, n);
-                        }
-                        if (++sa == static_cast<uint32_t>(p.na)) { sa = 0; pa ^= 1; }
-                    },
-                    [&](const CUtensorMap*, int, int, int, const int*, const int*, const int*, bool) {},
-                    [&]() {});
+                const int oy = by * 16 - 1 + (NPY == 1 ? py_u : 0), ox = bx * 8 - 1;
+                auto issue = [&](const CUtensorMap* tm, int ca) {
+                    mbar_wait(bar_a_empty + 8 * sa, pa ^ 1, 1, p.dbg);
+                    if (PAIR) {
+                        const uint32_t fb = mapa_shared(bar_a_full + 8 * sa, 0);
+                        if (rank == 0) mbar_expect_tx(bar_a_full + 8 * sa, 2 * Cfg::BOX_TX); else mbar_arrive_cluster(fb);
+                        tma_load_4d_pair(sA + sa * Cfg::A_STAGE, tm, fb, ca, ox, oy, n);
+                    } else {
+                        mbar_expect_tx(bar_a_full + 8 * sa, Cfg::BOX_TX);
+                        tma_load_4d(sA + sa * Cfg::A_STAGE, tm, bar_a_full + 8 * sa, ca, ox, oy, n);
+                    }
+                    if (++sa == static_cast<uint32_t>(p.na)) { sa = 0; pa ^= 1; }
+                };
+                for (int cs = 0; cs < n_cs0; ++cs) issue(&p.tmA0, cs << 6);
+                for (int cs = 0; cs < n_cs1; ++cs)
+#pragma unroll 1
+                    for (int q = 0; q < 4; ++q) issue(&p.tmP[q], cs << 6);      // (qy, qx) = (0,0), (0,1), (1,0), (1,1)
             }
         }
     } else if (warp == 3) {
-        // ======================= TMA producer: weights ========================
+        // ======================= TMA producer: weights (4 composite taps / 3 skip taps per stage) ========================
         if (lane == 0) {
             const int row_off = PAIR ? static_cast<int>(rank) * (BN / 2) : 0;
             uint32_t sb = 0, pb = 0;
+            auto issue = [&](const CUtensorMap* tm, int k0, int row, int tap, uint32_t bytes) {
+                mbar_wait(bar_b_empty + 8 * sb, pb ^ 1, 3, p.dbg);
+                if (PAIR) {
+                    const uint32_t fb = mapa_shared(bar_b_full + 8 * sb, 0);
+                    if (rank == 0) mbar_expect_tx(bar_b_full + 8 * sb, 2 * bytes); else mbar_arrive_cluster(fb);
+                    tma_load_3d_pair(sB + sb * Cfg::B_STAGE, tm, fb, k0, row, tap);
+                } else {
+                    mbar_expect_tx(bar_b_full + 8 * sb, bytes);
+                    tma_load_3d(sB + sb * Cfg::B_STAGE, tm, bar_b_full + 8 * sb, k0, row, tap);
+                }
+                if (++sb == static_cast<uint32_t>(p.nb)) { sb = 0; pb ^= 1; }
+            };
             for (int u = first_unit; u < n_units; u += unit_stride) {
-                int mt, py_u, px_u, nb;
-                decode(u, mt, py_u, px_u, nb);
+                int mt, py_u, nb;
+                decode(u, mt, py_u, nb);
                 const int row = nb * BN + row_off;
-                phase_walk<NPY, NPX>(p, py_u, px_u,
-                    [&](const CUtensorMap*, const CUtensorMap*, int, int) {},
-                    [&](const CUtensorMap* tm, int k0, int wtap, int, const int*, const int*, const int*, bool) {
-                        mbar_wait(bar_b_empty + 8 * sb, pb ^ 1, 3, p.dbg);
-                        if (PAIR) {
-                            const uint32_t fb = mapa_shared(bar_b_full + 8 * sb, 0);
-                            if (rank == 0) mbar_expect_tx(bar_b_full + 8 * sb, 2 * Cfg::B_TAP); else mbar_arrive_cluster(fb);
-                            tma_load_3d_pair(sB + sb * Cfg::B_TAP, tm, fb, k0, row, wtap);
-                        } else {
-                            mbar_expect_tx(bar_b_full + 8 * sb, Cfg::B_TAP);
-                            tma_load_3d(sB + sb * Cfg::B_TAP, tm, bar_b_full + 8 * sb, k0, row, wtap);
+                for (int cs = 0; cs < n_cs0; ++cs)
+#pragma unroll 1
+                    for (int pl = 0; pl < NPH; ++pl)             // phase (py_u + pl / 2, pl % 2): taps ph * 4 .. + 3
+                        issue(&p.tmB, cs << 6, row, ((py_u + pl / NPX) * 2 + pl % NPX) * 4, 4 * Cfg::B_TAP);
+                for (int cs = 0; cs < n_cs1; ++cs)
+#pragma unroll 1
+                    for (int qy = 0; qy < 2; ++qy)
+#pragma unroll 1
+                        for (int ky = 0; ky < 3; ++ky) {
+                            if (NPY == 1 && ((qy + ky + 1) & 1) != py_u) continue;
+                            issue(&p.tmB2, p.kskip + (cs << 6), row, ky * 3, 3 * Cfg::B_TAP);
                         }
-                        if (++sb == static_cast<uint32_t>(p.nb)) { sb = 0; pb ^= 1; }
-                    },
-                    [&]() {});
             }
         }
     } else if (warp == 1) {
         // ============================ MMA issuer ==============================
         if (rank == 0) {
             constexpr uint32_t idesc = umma_idesc_bf16(BN, PAIR ? 256 : 128);
-            constexpr uint32_t a_hi = umma_desc_hi_sw128(Cfg::BW * 128);
+            constexpr uint32_t a_hi = umma_desc_hi_sw128(BW * 128);
             constexpr uint32_t b_hi = umma_desc_hi_sw128(1024);
             uint32_t sa = 0, pa = 0, sb = 0, pb = 0, tile_it = 0;
             const uint32_t b_lo0 = umma_desc_lo(sB);
+            auto mma = [&](uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t flag) {
+                if (PAIR) umma_bf16_pair(d, umma_desc(a_lo, a_hi), umma_desc(b_lo, b_hi), idesc, flag);
+                else umma_bf16(d, umma_desc(a_lo, a_hi), umma_desc(b_lo, b_hi), idesc, flag);
+            };
+            auto commit = [&](uint32_t bar) {
+                if (PAIR) umma_commit_pair(bar); else umma_commit(bar);
+            };
+            // the walk of one unit whose first phase row is PYU (a compile-time constant: all views are immediates)
+            auto unit = [&](auto pyu_c, uint32_t d_tmem) {
+                constexpr int PYU = decltype(pyu_c)::value;
+                constexpr int oyo = NPY == 1 ? PYU : 0;          // box origin row = I0 - 1 + oyo
+#pragma unroll 1
+                for (int cs = 0; cs < n_cs0; ++cs) {
+                    mbar_wait(bar_a_full + 8 * sa, pa, 5, p.dbg);
+                    const uint32_t a_lo0 = umma_desc_lo(sA + sa * Cfg::A_STAGE);
+                    const uint32_t acc0 = cs ? 1u : 0u;
+#pragma unroll
+                    for (int pl = 0; pl < NPH; ++pl) {
+                        const int py = PYU + pl / NPX, px = pl % NPX;
+                        mbar_wait(bar_b_full + 8 * sb, pb, 6, p.dbg);
+                        tc_fence_after();
+                        const uint32_t b_lo = b_lo0 + sb * (Cfg::B_STAGE >> 4);
+                        if (elect_one()) {
+#pragma unroll
+                            for (int t = 0; t < 4; ++t) {
+                                // low-resolution offset (a - (1 - py), b - (1 - px)) of tap (a, b) = (t >> 1, t & 1)
+                                const uint32_t view = static_cast<uint32_t>(((t >> 1) + py - oyo) * BW + ((t & 1) + px)) * 8;
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    mma(d_tmem + pl * BN, a_lo0 + view + 2 * k, b_lo + t * (Cfg::B_TAP >> 4) + 2 * k,
+                                        (t | k) ? 1u : acc0);
+                            }
+                            commit(bar_b_empty + 8 * sb);
+                            if (pl == NPH - 1) commit(bar_a_empty + 8 * sa);
+                        }
+                        if (++sb == static_cast<uint32_t>(p.nb)) { sb = 0; pb ^= 1; }
+                    }
+                    if (++sa == static_cast<uint32_t>(p.na)) { sa = 0; pa ^= 1; }
+                }
+#pragma unroll 1
+                for (int cs = 0; cs < n_cs1; ++cs) {
+#pragma unroll
+                    for (int qy = 0; qy < 2; ++qy) {
+                        // the two column planes of row parity qy: two consecutive ring slots
+                        const uint32_t s0 = sa;
+                        mbar_wait(bar_a_full + 8 * s0, pa, 5, p.dbg);
+                        if (++sa == static_cast<uint32_t>(p.na)) { sa = 0; pa ^= 1; }
+                        const uint32_t s1 = sa;
+                        mbar_wait(bar_a_full + 8 * s1, pa, 5, p.dbg);
+                        if (++sa == static_cast<uint32_t>(p.na)) { sa = 0; pa ^= 1; }
+                        const uint32_t a_q0 = umma_desc_lo(sA + s0 * Cfg::A_STAGE), a_q1 = umma_desc_lo(sA + s1 * Cfg::A_STAGE);
+                        const int ky_last = NPY == 2 ? 2 : (qy == PYU ? 1 : 2);
+#pragma unroll
+                        for (int ky = 0; ky < 3; ++ky) {
+                            const int py = (qy + ky + 1) & 1;    // the output row parity whose tap ky reads plane rows qy
+                            if (NPY == 1 && py != PYU) continue;
+                            const int vy = ((py + ky - 1) >> 1) + 1 - oyo;
+                            mbar_wait(bar_b_full + 8 * sb, pb, 6, p.dbg);
+                            tc_fence_after();
+                            const uint32_t b_lo = b_lo0 + sb * (Cfg::B_STAGE >> 4);
+                            if (elect_one()) {
+#pragma unroll
+                                for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+                                    for (int px = 0; px < 2; ++px) {
+                                        const int qx = (px + kx + 1) & 1;
+                                        const uint32_t view = static_cast<uint32_t>(vy * BW + ((px + kx - 1) >> 1) + 1) * 8;
+                                        const uint32_t a_lo = (qx ? a_q1 : a_q0) + view;
+#pragma unroll
+                                        for (int k = 0; k < 4; ++k)
+                                            mma(d_tmem + ((py - PYU) * NPX + px) * BN, a_lo + 2 * k,
+                                                b_lo + kx * (Cfg::B_TAP >> 4) + 2 * k, 1u);
+                                    }
+                                commit(bar_b_empty + 8 * sb);
+                                if (ky == ky_last) {
+                                    commit(bar_a_empty + 8 * s0);
+                                    commit(bar_a_empty + 8 * s1);
+                                }
+                            }
+                            if (++sb == static_cast<uint32_t>(p.nb)) { sb = 0; pb ^= 1; }
+                        }
+                    }
+                }
+            };
             for (int u = first_unit; u < n_units; u += unit_stride, ++tile_it) {
-                int mt, py_u, px_u, nb;
-                decode(u, mt, py_u, px_u, nb);
+                int mt, py_u, nb;
+                decode(u, mt, py_u, nb);
                 const uint32_t acc = tile_it % Cfg::NACC, acc_ph = (tile_it / Cfg::NACC) & 1;
                 mbar_wait(bar_t_empty + 8 * acc, acc_ph ^ 1, 4, p.dbg);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * (NPH * BN);
-                uint32_t a_lo0 = 0;
-                phase_walk<NPY, NPX>(p, py_u, px_u,
-                    [&](const CUtensorMap*, const CUtensorMap*, int, int) {
-                        mbar_wait(bar_a_full + 8 * sa, pa, 5, p.dbg);
-                        tc_fence_after();
-                        a_lo0 = umma_desc_lo(sA + sa * Cfg::A_STAGE);
-                    },
-                    [&](const CUtensorMap*, int, int, int nmm, const int* pl, const int* view, const int* box, bool fresh) {
-                        mbar_wait(bar_b_full + 8 * sb, pb, 6, p.dbg);
-                        tc_fence_after();
-                        const uint32_t b_lo = b_lo0 + sb * (Cfg::B_TAP >> 4);
-                        if (elect_one()) {
-#pragma unroll
-                            for (int m = 0; m < NPX; ++m) {
-                                if (m < nmm) {
-                                    const uint32_t a_lo = a_lo0 + static_cast<uint32_t>(box[m]) * (Cfg::BOX_STRIDE >> 4) +
-                                                          static_cast<uint32_t>(view[m]) * 8;
-                                    const uint32_t d = d_tmem + static_cast<uint32_t>(pl[m]) * BN;
-#pragma unroll
-                                    for (int k = 0; k < 4; ++k) {
-                                        if (PAIR) umma_bf16_pair(d, umma_desc(a_lo + 2 * k, a_hi), umma_desc(b_lo + 2 * k, b_hi), idesc, (k || !fresh) ? 1u : 0u);
-                                        else umma_bf16(d, umma_desc(a_lo + 2 * k, a_hi), umma_desc(b_lo + 2 * k, b_hi), idesc, (k || !fresh) ? 1u : 0u);
-                                    }
-                                }
-                            }
-                            if (PAIR) umma_commit_pair(bar_b_empty + 8 * sb); else umma_commit(bar_b_empty + 8 * sb);
-                        }
-                        if (++sb == static_cast<uint32_t>(p.nb)) { sb = 0; pb ^= 1; }
-                    },
-                    [&]() {
-                        if (elect_one()) {
-                            if (PAIR) umma_commit_pair(bar_a_empty + 8 * sa); else umma_commit(bar_a_empty + 8 * sa);
-                        }
-                        if (++sa == static_cast<uint32_t>(p.na)) { sa = 0; pa ^= 1; }
-                    });
-                if (elect_one()) {
-                    if (PAIR) umma_commit_pair(bar_t_full + 8 * acc); else umma_commit(bar_t_full + 8 * acc);
-                }
+                if (NPY == 2 || py_u == 0) unit(std::integral_constant<int, 0>{}, d_tmem);
+                else unit(std::integral_constant<int, (NPY == 1 ? 1 : 0)>{}, d_tmem);
+                if (elect_one()) commit(bar_t_full + 8 * acc);
             }
         }
     } else if (warp >= 4) {
@@ -315,8 +296,8 @@ __global__ void __launch_bounds__(384, 1) conv_phase_multi_kernel(const __grid_c
         };
         for (int u = eg < estep ? first_unit + eg * unit_stride : n_units; u < n_units;
              u += estep * unit_stride, tile_it += estep) {
-            int mt, py_u, px_u, nb;
-            const bool valid = decode(u, mt, py_u, px_u, nb);
+            int mt, py_u, nb;
+            const bool valid = decode(u, mt, py_u, nb);
             int n, r, y0, x0;
             fdivmod(static_cast<uint32_t>(mt), p.fd_tpi, n, r);
             fdivmod(static_cast<uint32_t>(r), p.fd_tx, y0, x0);
@@ -329,7 +310,7 @@ __global__ void __launch_bounds__(384, 1) conv_phase_multi_kernel(const __grid_c
             const uint32_t t_addr = tmem_base + acc * (NPH * BN) + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
             for (int pl = 0; pl < NPH; ++pl) {
-                const int py = py_u + pl / NPX, px = px_u + pl % NPX, ph = py * 2 + px;
+                const int py = py_u + pl / NPX, px = pl % NPX, ph = py * 2 + px;
                 // border case of this thread's output pixel (2I + py, 2J + px): first / interior / last row and column
                 const int cy = (py == 0 && I == 0) ? 0 : ((py == 1 && I == p.H - 1) ? 2 : 1);
                 const int cx = (px == 0 && J == 0) ? 0 : ((px == 1 && J == p.W - 1) ? 2 : 1);

@@ -641,7 +641,8 @@ int build_phase_step(const PhaseDesc& d, int num_sms, Step* st) {
     else if (d.one_phase) phase_inst<64>(pair, &cl, &box_w, &box_h, &nph);
     else phase_multi_inst<64, 2, 2>(pair, &cl, &box_w, &box_h, &nph);
     cl.b_tap = (pair ? bn / 2 : bn) * 128;
-    cl.b_stage = cl.b_tap;
+    const bool multi = nph > 1;                  // conv_phase_multi.cuh: weight stages of 4 composite / 3 skip taps
+    cl.b_stage = multi ? 4 * cl.b_tap : cl.b_tap;
     ub::ConvParams& p = st->cp;
     memset(&p, 0, sizeof p);
     int rc;
@@ -661,8 +662,8 @@ int build_phase_step(const PhaseDesc& d, int num_sms, Step* st) {
                             uint64_t(2) * wo * d.cout * 2, uint64_t(ho) * wo * d.cout * 2, 8, 4)))
             return rc;
     }
-    if ((rc = make_w_map(&p.tmB, d.wc, d.c_low, d.cout, 16, pair ? bn / 2 : bn, 1))) return rc;
-    if ((rc = make_w_map(&p.tmB2, d.w3, d.c_up + d.c_skip, d.cout, 9, pair ? bn / 2 : bn, 1))) return rc;
+    if ((rc = make_w_map(&p.tmB, d.wc, d.c_low, d.cout, 16, pair ? bn / 2 : bn, multi ? 4 : 1))) return rc;
+    if ((rc = make_w_map(&p.tmB2, d.w3, d.c_up + d.c_skip, d.cout, 9, pair ? bn / 2 : bn, multi ? 3 : 1))) return rc;
     p.bias9 = d.bias9;
     p.kskip = d.c_up;
     p.dbg = d.dbg;
@@ -677,13 +678,20 @@ int build_phase_step(const PhaseDesc& d, int num_sms, Step* st) {
     p.relu = d.relu;
     // shared memory: [A ring][B ring][out staging][barriers][bias9]
     const int bias_bytes = (9 * d.cout * 4 + 1023) / 1024 * 1024;
-    const int budget = ub::kSmemLimit - ub::kStaticSmem - 1024 /*alignment slack*/ - bias_bytes - ub::kBarBytes;
+    const int budget = ub::kSmemLimit - ub::kRowStatic - 1024 /*alignment slack*/ - bias_bytes - ub::kBarBytes;   // (no static shared memory)
     int nb = (bn == 256 ? 3 * 32768 : (bn == 128 ? 5 * 16384 : 8 * 8192)) / cl.b_stage;
+    if (multi) nb = (bn == 128 ? 98304 : 65536) / cl.b_stage;   // 96 / 64 KB of weight stages (pairs: 3 / 4 stages), the rest is activation slots (one box each)
+    if (multi && nb < 2) nb = 2;
     if (nb > ub::kMaxRing) nb = ub::kMaxRing;
-    const int n_out = 2, n_epi = 1;
+    int n_out = 2;
+    const int n_epi = 1;
     int na = (budget - n_epi * n_out * ub::kOutStage - nb * cl.b_stage) / cl.a_stage;
+    if (na < 3) {                                // (the unpaired cross-check variants: full-height weight stages)
+        n_out = 1;
+        na = (budget - n_epi * n_out * ub::kOutStage - nb * cl.b_stage) / cl.a_stage;
+    }
     if (na > ub::kMaxRing) na = ub::kMaxRing;
-    if (na < 2) return fail(UNETB200_EINVAL, "fused up-conv: shared memory plan does not fit");
+    if (na < (multi ? 3 : 2)) return fail(UNETB200_EINVAL, "fused up-conv: shared memory plan does not fit");
     p.na = na; p.nb = nb; p.wstat = 0; p.n_out = n_out; p.n_epi = n_epi;
     p.off_b = na * cl.a_stage;
     p.off_out = p.off_b + nb * cl.b_stage;
@@ -869,7 +877,7 @@ int launch_step(Step& st, cudaStream_t stream) {
             if (it == configured.end() || !(it->second & (1 << dev))) {
                 UB_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(st.conv.fn),
                                              cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             ub::kSmemLimit - (st.conv.row ? ub::kRowStatic : ub::kStaticSmem)));
+                                             ub::kSmemLimit - ((st.conv.row || st.conv.phase) ? ub::kRowStatic : ub::kStaticSmem)));
                 configured[reinterpret_cast<const void*>(st.conv.fn)] |= (1 << dev);
             }
         }
@@ -1003,7 +1011,7 @@ struct unetb200_handle_s {
     int row64 = 2;              // 64-output-channel 3x3 convs on the row-stacked kernel (conv_row.cuh): bit 0 = the
                                 // one-slice layers (down1.net.3, conv1.net.3: measured equal / 5 % slower, off),
                                 // bit 1 = conv1.net.0 (measured 3-5 % faster, on)
-    int fold_up = 14;           // bit k: decoder level k (H >> k; bit 3 = up4 + conv4.net.0) runs as ONE launch with the
+    int fold_up = 15;           // bit k: decoder level k (H >> k; bit 3 = up4 + conv4.net.0) runs as ONE launch with the
                                 // up-conv folded into the 3x3 conv (conv_phase.cuh); masked by `fold_avail`
     int fold_one_phase = 0;     // A/B: folded levels run one phase per work unit whatever the column block
     int fold_avail = 0;         // levels whose composite weights were packed into the blob (unetb200_pack_fused_up)
