@@ -79,9 +79,10 @@ def read_peaks():
                 "source": "fallback of B200_PROFILING.md (MEASURED_PEAKS.json absent)"}
 
 
-def ncu_traffic_bytes():
-    """DRAM bytes (read + write) of the 21 tensor-core launches of one step, from the newest committed
-    `ncu --set full` capture (profiles/*_ncu_raw.csv, batch 64 @ 512x512); None if absent."""
+def ncu_traffic_bytes(n_launches=None):
+    """DRAM bytes (read + write) of the tensor-core launches of one step (every launch but the first conv), from the
+    newest committed `ncu --set full` capture (profiles/*_ncu_raw.csv, batch 64 @ 512x512); None if absent or if
+    the capture describes a plan with another number of launches than `n_launches`."""
     import csv
     import glob
     files = sorted(f for f in glob.glob(os.path.join(ROOT, "profiles", "*_ncu_raw.csv")) if "enhance" not in f)
@@ -92,9 +93,10 @@ def ncu_traffic_bytes():
         h, unit, data = rows[0], rows[1], rows[2:]
         ir, iw, ik = h.index("dram__bytes_read.sum"), h.index("dram__bytes_write.sum"), h.index("Kernel Name")
         scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[unit[ir]]
-        tc = [r for r in data if "conv_tc_kernel" in r[ik] and "conv_tc_kernel<64, 1, 3," not in r[ik]
+        conv = [r for r in data if "conv_tc_kernel" in r[ik] or "conv_row_kernel" in r[ik] or "conv_phase" in r[ik]]
+        tc = [r for r in conv if "conv_tc_kernel<64, 1, 3," not in r[ik]
               and "(int)64, (int)1, (int)3" not in r[ik]]            # all launches but the stem (A_STEM)
-        if len(tc) != 21:
+        if len(tc) != len(conv) - 1 or (n_launches is not None and len(conv) != n_launches):
             return None, None
         return sum(float(r[ir]) + float(r[iw]) for r in tc) * scale, os.path.basename(files[-1])
     except Exception:
@@ -421,9 +423,7 @@ def main():
     achieved = tc_flops / (tc_ms * 1e-3) / 1e12
     executed = tc_flops_exec / (tc_ms * 1e-3) / 1e12
     n_folded = sum(folded)
-    traffic, traffic_src = ncu_traffic_bytes() if (B == 64 and S == 512) else (None, None)
-    if traffic is not None and launches_per_step != 22:
-        traffic = None          # the committed capture describes the 22-launch plan only
+    traffic, traffic_src = ncu_traffic_bytes(launches_per_step) if (B == 64 and S == 512) else (None, None)
     roofline = {
         "bound": "tensor", "kernel": f"tcgen05 implicit-GEMM conv kernels ({n_tc} launches per step: 3x3 convs"
                                      f"{', ' + str(n_folded) + ' of them with the 2x2 up-conv folded in' if n_folded else ' + 2x2 up-convs'})",

@@ -25,6 +25,9 @@ LAYERS = ["down1.net.0 (stem)", "down1.net.3", "down2.net.0", "down2.net.3", "do
           "down4.net.0", "down4.net.3", "bottleneck.net.0", "bottleneck.net.3", "up4", "conv4.net.0",
           "conv4.net.3", "up3", "conv3.net.0", "conv3.net.3", "up2", "conv2.net.0", "conv2.net.3", "up1",
           "conv1.net.0", "conv1.net.3 + out_conv"]
+# the default plan folds every up-conv into the following conv (csrc/conv_phase*.cuh): 18 launches
+LAYERS_FOLDED = [l if not l.endswith(".net.0") or not l.startswith("conv") else l + " + up" + l[4] + " (folded)"
+                 for l in LAYERS if not l.startswith("up")]
 
 
 def main():
@@ -39,10 +42,11 @@ def main():
     # stem = the A_STEM instantiation conv_tc_kernel<64, 1, 3, ...> (or the CUDA-core stem_conv_kernel)
     stem = next((i for i, n in enumerate(names)
                  if "stem" in n or "conv_tc_kernel<(int)64, (int)1, (int)3" in n or "conv_tc_kernel<64, 1, 3" in n), 0)
+    layers = LAYERS_FOLDED if any("conv_phase" in n for n in names) else LAYERS
     for i, r in enumerate(data):
         name = names[i]
         short = name.split("(")[0].replace("ub::", "").replace("void ", "")[:60]
-        layer = LAYERS[(i - stem) % len(LAYERS)]
+        layer = layers[(i - stem) % len(layers)]
         print(f"| {i} | {layer} | `{short}` | " + " | ".join(r[idx[c]] for c, _ in cols) + " |")
 
 
