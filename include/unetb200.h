@@ -44,7 +44,8 @@ enum {
 
 /* A-operand staging strategy of the tensor-core conv kernel (see csrc/conv_tc.cuh) */
 enum { UNETB200_A_TAP = 0, UNETB200_A_COL3 = 1, UNETB200_A_HALO = 2,
-       UNETB200_A_ROW = 5 /* single-kernel hooks only: the row-stacked kernel (cout == 64) */ };
+       UNETB200_A_ROW = 5 /* single-kernel hooks only: the row-stacked kernel (cout == 64) */,
+       UNETB200_A_PS64 = 7 /* single-kernel hooks only: the phase-stacked kernel (64 -> 64 channels, csrc/conv_ps64.cuh) */ };
 
 /* UNet(n_channels, n_classes) of reference unet_model.py:24; base_width is the 64 of :29. */
 typedef struct {

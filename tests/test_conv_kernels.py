@@ -172,6 +172,76 @@ def test_conv3x3_row_two_sources_and_pool(cuda_dev, n, h, w):
     assert torch.equal(out, out2)
 
 
+A_PS64 = 7     # conv_ps64.cuh: the phase-stacked kernel of the 64 -> 64 channel convs
+
+
+@pytest.mark.parametrize("pool", [0, 1])
+@pytest.mark.parametrize("n,h,w", [
+    (2, 32, 16),            # one tile per image
+    (1, 64, 48),            # 2 x 3 tiles
+    (3, 32, 16),            # odd tile count: the pair tail
+    (1, 16, 16),            # smaller than a tile in both directions
+    (2, 48, 80),            # partial tiles in both directions
+    (1, 128, 512),          # many tiles per CTA pair: accumulator / ring wrap-around
+    (2, 2, 2),              # every pixel a corner
+])
+def test_conv3x3_ps64(cuda_dev, n, h, w, pool):
+    """The phase-stacked 64 -> 64 conv (N = 128 / 64 UMMAs over the output parities that share an input view)
+    against F.conv2d; the pooled output must be exactly the max-pool of the stored output.  (Its K order per
+    output element differs from the tap-per-UMMA kernel's, so it is compared by tolerance, not bit for bit.)"""
+    nat = _nat()
+    g = torch.Generator(device="cpu").manual_seed(5 * h + w)
+    x = torch.randn((n, 64, h, w), generator=g).to(cuda_dev)
+    wt = (torch.randn((64, 64, 3, 3), generator=g) / 24.0).to(cuda_dev)
+    b = torch.randn((64,), generator=g).to(cuda_dev)
+    xb, wb = _nhwc_bf16(x), _pack3x3(wt)
+    out = torch.full((n, h, w, 64), float("nan"), dtype=torch.bfloat16, device=cuda_dev)
+    pl = torch.full((n, h // 2, w // 2, 64), float("nan"), dtype=torch.bfloat16, device=cuda_dev) if pool else None
+    nat.check(nat.lib().unetb200_conv3x3(xb.data_ptr(), 64, None, 0, wb.data_ptr(), b.data_ptr(), n, h, w, 64, 1,
+                                         out.data_ptr(), pl.data_ptr() if pool else None, 64, A_PS64, 3, None))
+    torch.cuda.synchronize()
+    ref = F.relu(F.conv2d(_to_nchw_f32(xb), wb.float().reshape(3, 3, 64, 64).permute(2, 3, 0, 1), b, padding=1))
+    got = _to_nchw_f32(out)
+    assert not torch.isnan(got).any(), "unwritten output pixels"
+    _close(got, ref, "phase-stacked conv3x3")
+    if pool:
+        assert torch.equal(_to_nchw_f32(pl), F.max_pool2d(got, 2))
+
+
+@pytest.mark.parametrize("n,h,w", [(2, 32, 32), (1, 48, 176), (3, 32, 16)])
+def test_conv3x3_ps64_head(cuda_dev, n, h, w):
+    """conv1.net.3 + out_conv + threshold on the phase-stacked kernel: logits, byte masks and bit-packed masks."""
+    nat = _nat()
+    ncls = 3
+    g = torch.Generator(device="cpu").manual_seed(3 + w)
+    x = torch.randn((n, 64, h, w), generator=g).to(cuda_dev)
+    wt = (torch.randn((64, 64, 3, 3), generator=g) / 24.0).to(cuda_dev)
+    b = torch.randn((64,), generator=g).to(cuda_dev)
+    hw = torch.randn((ncls, 64), generator=g).to(cuda_dev) / 4.0
+    hb = torch.randn((ncls,), generator=g).to(cuda_dev)
+    xb, wb = _nhwc_bf16(x), _pack3x3(wt)
+    logits = torch.full((n, ncls, h, w), float("nan"), dtype=torch.float32, device=cuda_dev)
+    mask = torch.full((n, ncls, h, w), 7, dtype=torch.uint8, device=cuda_dev)
+    thr = (C.c_float * ncls)(-0.5, 0.0, 0.7)
+    nat.check(nat.lib().unetb200_conv3x3_head(xb.data_ptr(), 64, wb.data_ptr(), b.data_ptr(), hw.data_ptr(),
+                                              hb.data_ptr(), ncls, n, h, w, logits.data_ptr(), mask.data_ptr(), thr,
+                                              A_PS64, 3, None))
+    torch.cuda.synchronize()
+    feat = F.relu(F.conv2d(_to_nchw_f32(xb), wb.float().reshape(3, 3, 64, 64).permute(2, 3, 0, 1), b, padding=1))
+    ref = F.conv2d(feat, hw.reshape(ncls, 64, 1, 1), hb)
+    assert not torch.isnan(logits).any(), "unwritten logits"
+    err = (logits - ref).abs().max().item()
+    assert err < 2e-3, f"fused head logits max err {err}"
+    thr_t = torch.tensor(list(thr), device=cuda_dev).view(1, ncls, 1, 1)
+    assert torch.equal(mask, (logits > thr_t).to(torch.uint8)), "mask != (logits > thr)"
+    bits = torch.full((n, ncls, h, w // 8), 0xAA, dtype=torch.uint8, device=cuda_dev)
+    nat.check(nat.lib().unetb200_conv3x3_head(xb.data_ptr(), 64, wb.data_ptr(), b.data_ptr(), hw.data_ptr(),
+                                              hb.data_ptr(), ncls, n, h, w, None, bits.data_ptr(), thr, A_PS64, 3 | 4, None))
+    torch.cuda.synchronize()
+    from tw_invoice_unet_ocr_llm_b200.engine import unpack_mask_bits
+    assert torch.equal(unpack_mask_bits(bits), mask), "bit-packed mask != byte mask"
+
+
 @pytest.mark.parametrize("pair", [0, 1])
 @pytest.mark.parametrize("cin,cout,bn", [(128, 64, 128), (256, 128, 64), (128, 64, 256)])
 def test_convt2x2(cuda_dev, cin, cout, bn, pair):

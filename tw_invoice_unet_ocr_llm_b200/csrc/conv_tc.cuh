@@ -68,7 +68,7 @@
 namespace ub {
 
 enum : int { EPI_STORE = 0, EPI_STORE_POOL = 1, EPI_HEAD = 2, EPI_UPSAMPLE = 3 };
-enum : int { A_TAP = 0, A_COL3 = 1, A_HALO = 2, A_STEM = 3, A_STEMP = 4, A_ROW = 5 /* conv_row.cuh */, A_PHASE = 6 /* conv_phase.cuh */ };
+enum : int { A_TAP = 0, A_COL3 = 1, A_HALO = 2, A_STEM = 3, A_STEMP = 4, A_ROW = 5 /* conv_row.cuh */, A_PHASE = 6 /* conv_phase.cuh */, A_PS64 = 7 /* conv_ps64.cuh */ };
 
 constexpr int kMaxClasses = 8;
 

@@ -20,6 +20,7 @@
 #include "conv_row.cuh"
 #include "conv_phase.cuh"
 #include "conv_phase_multi.cuh"
+#include "conv_ps64.cuh"
 #include "errors.h"
 #include "pack.cuh"
 #include "prepost.cuh"
@@ -714,8 +715,99 @@ int build_phase_step(const PhaseDesc& d, int num_sms, Step* st) {
     return 0;
 }
 
+// Phase-stacked kernel for the 64 -> 64 channel 3x3 convs (conv_ps64.cuh).
+int build_ps64_step(const ConvDesc& d, int num_sms, Step* st) {
+    if (d.taps != 9 || d.cout != 64 || d.c0 != 64 || d.c1 != 0)
+        return fail(UNETB200_EINVAL, "phase-stacked kernel: 3x3 conv, 64 -> 64 channels, one source only");
+    if (d.h % 2 || d.wd % 2) return fail(UNETB200_EINVAL, "phase-stacked kernel: even H and W only");
+    st->kind = 1;
+    ConvLaunch& cl = st->conv;
+    cl = ConvLaunch();
+    cl.phase = true;            // (no static shared memory: same dynamic limit as the folded up-conv kernels)
+    cl.pair = true;
+    switch (d.epi) {
+        case ub::EPI_STORE: cl.fn = ub::conv_ps64_kernel<ub::EPI_STORE>; break;
+        case ub::EPI_STORE_POOL: cl.fn = ub::conv_ps64_kernel<ub::EPI_STORE_POOL>; break;
+        case ub::EPI_HEAD: cl.fn = d.ncls == 3 ? ub::conv_ps64_kernel<ub::EPI_HEAD, 3> : ub::conv_ps64_kernel<ub::EPI_HEAD, 0>; break;
+        default: return fail(UNETB200_EINVAL, "phase-stacked kernel: unsupported epilogue");
+    }
+    ub::ConvParams& p = st->cp;
+    memset(&p, 0, sizeof p);
+    int rc;
+    const int hb = d.h / 2, wb = d.wd / 2;      // block positions (I, J): pixel (2I + py, 2J + px)
+    for (int q = 0; q < 4; ++q) {
+        const int qy = q >> 1, qx = q & 1;
+        const char* sb = static_cast<const char*>(d.src0) + (uint64_t(qy) * d.wd + qx) * 64 * 2;
+        if ((rc = make_map4(&p.tmP[q], sb, 64, wb, hb, d.n, uint64_t(2) * 64 * 2, uint64_t(2) * d.wd * 64 * 2,
+                            uint64_t(d.h) * d.wd * 64 * 2, ub::kPsBoxW, ub::kPsBoxH)))
+            return rc;
+        if (d.epi != ub::EPI_HEAD) {
+            const char* ob = static_cast<const char*>(d.out) + (uint64_t(qy) * d.wd + qx) * 64 * 2;
+            if ((rc = make_map4(&p.tmOut[q], ob, 64, wb, hb, d.n, uint64_t(2) * 64 * 2, uint64_t(2) * d.wd * 64 * 2,
+                                uint64_t(d.h) * d.wd * 64 * 2, 8, 4)))
+                return rc;
+        } else {
+            p.tmOut[q] = p.tmP[q];
+        }
+    }
+    p.tmA0 = p.tmP[0];
+    p.tmA1 = p.tmP[0];
+    if ((rc = make_w_map(&p.tmB, d.w, 64, 64, 9, 64, 1))) return rc;      // image 1: whole taps
+    if ((rc = make_w_map(&p.tmB2, d.w, 64, 64, 9, 32, 1))) return rc;     // image 2: half taps
+    if (d.epi == ub::EPI_STORE_POOL) {
+        if (!d.pool) return fail(UNETB200_EINVAL, "pool output missing");
+        if ((rc = make_act_map(&p.tmPool, d.pool, 64, wb, hb, d.n, 8, 4))) return rc;
+    } else {
+        p.tmPool = p.tmP[0];
+    }
+    p.bias = d.bias; p.head_w = d.head_w; p.head_b = d.head_b; p.logits = d.logits; p.mask = d.mask;
+    p.mask_bits = d.mask_bits; p.dbg = d.dbg;
+    UB_CUDA(cudaMemcpy(p.bias_c, d.bias, sizeof p.bias_c, cudaMemcpyDeviceToHost));
+    if (d.epi == ub::EPI_HEAD) {
+        if (!d.head_w || !d.head_b || d.ncls < 1 || d.ncls > ub::kMaxClasses)
+            return fail(UNETB200_EINVAL, "phase-stacked kernel: head weights missing");
+        UB_CUDA(cudaMemcpy(p.head_wc, d.head_w, sizeof(float) * 64 * d.ncls, cudaMemcpyDeviceToHost));
+        UB_CUDA(cudaMemcpy(p.head_bc, d.head_b, sizeof(float) * d.ncls, cudaMemcpyDeviceToHost));
+    }
+    p.C0 = 64; p.C1 = 0; p.H = d.h; p.W = d.wd; p.NIMG = d.n; p.Cout = 64;
+    p.tiles_x = (wb + 7) / 8;
+    p.tiles_y = (hb + 15) / 16;
+    p.n_blocks = 1;
+    const long long m_tiles = 1LL * p.tiles_x * p.tiles_y * d.n;
+    if (m_tiles > 0x3fffffffLL) return fail(UNETB200_EINVAL, "conv: too many tiles");
+    p.total_tiles = static_cast<int>(m_tiles);
+    p.relu = d.relu; p.ncls = d.ncls; p.wstat = 1;
+    // shared memory: [plane-box slots][resident weight images][staging: 3 x 16 KB per epilogue group][barriers]
+    // epilogue groups alternate units; the store epilogues stage through n_out slots of 16 KB per group
+    const int n_epi = (d.epi == ub::EPI_HEAD || d.epi2 >= 1) ? 2 : 1;
+    const int n_out = n_epi == 2 ? 2 : 3;
+    const int staging = d.epi == ub::EPI_HEAD ? 0 : n_epi * n_out * ub::kOutStage;
+    const int budget = ub::kSmemLimit - ub::kPsStatic - 1024 /*alignment slack*/ - ub::kBarBytes;
+    int na = (budget - ub::kPsWBytes - staging) / ub::kPsSlot;
+    if (na > ub::kMaxRing) na = ub::kMaxRing;
+    if (na < 2) return fail(UNETB200_EINVAL, "phase-stacked kernel: shared memory plan does not fit");
+    p.na = na; p.nb = 12; p.n_out = n_out; p.n_epi = n_epi;
+    p.off_b = na * ub::kPsSlot;
+    p.off_out = p.off_b + ub::kPsWBytes;
+    p.off_pool = p.off_out + staging;
+    p.off_bar = p.off_pool;
+    cl.smem = p.off_bar + ub::kBarBytes + 1024;
+    cl.a_stage = ub::kPsSlot; cl.b_tap = 8192; cl.b_stage = 8192;
+    p.fd_tpi = ub::make_fastdiv(static_cast<uint32_t>(p.tiles_x * p.tiles_y));
+    p.fd_tx = ub::make_fastdiv(static_cast<uint32_t>(p.tiles_x));
+    p.fd_nb = ub::make_fastdiv(1u);
+    p.fd_na = ub::make_fastdiv(static_cast<uint32_t>(na));
+    p.fd_nout = ub::make_fastdiv(static_cast<uint32_t>(n_out));
+    const long long units = (m_tiles + 1) / 2;
+    const long long pairs = units < num_sms / 2 ? units : num_sms / 2;
+    st->grid = dim3(static_cast<unsigned>(2 * pairs));
+    st->block = dim3(384);
+    return 0;
+}
+
 int build_conv_step(const ConvDesc& d, int num_sms, Step* st) {
     if (d.amode == ub::A_ROW) return build_row_step(d, num_sms, st);
+    if (d.amode == ub::A_PS64) return build_ps64_step(d, num_sms, st);
     const bool stemp = d.amode == ub::A_STEMP;
     const bool stem = d.amode == ub::A_STEM || stemp;
     if (d.c0 <= 0 || d.c0 % 64 || d.c1 % 64 || d.c1 < 0)
@@ -1013,6 +1105,8 @@ struct unetb200_handle_s {
                                 // bit 1 = conv1.net.0 (measured 3-5 % faster, on)
     int fold_up = 15;           // bit k: decoder level k (H >> k; bit 3 = up4 + conv4.net.0) runs as ONE launch with the
                                 // up-conv folded into the 3x3 conv (conv_phase.cuh); masked by `fold_avail`
+    int ps64 = 0;               // 64 -> 64 channel convs on the phase-stacked kernel (conv_ps64.cuh): bit 0 = down1.net.3,
+                                // bit 1 = conv1.net.3 + head
     int fold_one_phase = 0;     // A/B: folded levels run one phase per work unit whatever the column block
     int fold_avail = 0;         // levels whose composite weights were packed into the blob (unetb200_pack_fused_up)
     std::vector<FusedUp> fused;
@@ -1076,6 +1170,7 @@ int build_plan(unetb200_handle_t h, const void* x, int x_fmt, int n, int H, int 
         d.out = out; d.pool = pool;
         d.bn = h->bn_max; d.amode = h->amode; d.wstat = h->wstat; d.pf_items = h->pf_items; d.epi2 = h->epi2; d.min_na = h->min_na; d.dbg = h->dbg; d.fill_sms = h->fill_sms;
         if (d.cout == 64 && (h->row64 & (c1 > 0 ? 2 : 1))) d.amode = ub::A_ROW;   // bit 0: one-slice layers, bit 1: conv1.net.0
+        if (d.cout == 64 && c0 == 64 && c1 == 0 && (h->ps64 & 1)) d.amode = ub::A_PS64;
         // measured on B200 (profiles/): CTA pairs win or tie on every 3x3 conv, lose slightly on the up-convs
         d.pair = h->pair >= 1;
         Step st;
@@ -1160,7 +1255,7 @@ int build_plan(unetb200_handle_t h, const void* x, int x_fmt, int n, int H, int 
             d.n = n; d.h = H; d.wd = W; d.cout = bw; d.relu = 1; d.taps = 9; d.epi = ub::EPI_HEAD;
             d.head_w = reinterpret_cast<const float*>(Wp(22)); d.head_b = Bp(22);
             d.ncls = h->arch.n_classes; d.logits = logits; d.mask = mask; d.mask_bits = mask_bits;
-            d.bn = 64; d.amode = (h->row64 & 1) ? ub::A_ROW : h->amode; d.wstat = h->wstat; d.pf_items = h->pf_items; d.epi2 = h->epi2; d.min_na = h->min_na; d.pair = h->pair >= 1; d.dbg = h->dbg;
+            d.bn = 64; d.amode = (h->ps64 & 2) ? ub::A_PS64 : ((h->row64 & 1) ? ub::A_ROW : h->amode); d.wstat = h->wstat; d.pf_items = h->pf_items; d.epi2 = h->epi2; d.min_na = h->min_na; d.pair = h->pair >= 1; d.dbg = h->dbg;
             Step st;
             if ((rc = build_conv_step(d, h->num_sms, &st))) return rc;
             st.layer = 21;
@@ -1338,6 +1433,8 @@ int unetb200_create(const unetb200_arch_t* arch, const void* blob_dev, uint64_t 
     }
     const char* env = getenv("UNETB200_FOLD_UP");
     if (env) h->fold_up = atoi(env) & 15;
+    env = getenv("UNETB200_PS64");
+    if (env) h->ps64 = atoi(env) & 3;
     env = getenv("UNETB200_FOLD_ONE_PHASE");
     if (env) h->fold_one_phase = atoi(env) ? 1 : 0;
     env = getenv("UNETB200_AMODE");
@@ -1410,6 +1507,9 @@ int unetb200_set_option(unetb200_handle_t h, const char* key, int value) {
     } else if (k == "fold_up") {
         if (value < 0 || value > 15) return fail(UNETB200_EINVAL, "fold_up must be 0..15 (bit k: decoder level k)");
         h->fold_up = value;
+    } else if (k == "ps64") {
+        if (value < 0 || value > 3) return fail(UNETB200_EINVAL, "ps64 must be 0..3 (bit 0: down1.net.3, bit 1: conv1.net.3)");
+        h->ps64 = value;
     } else if (k == "fold_one_phase") {
         h->fold_one_phase = value ? 1 : 0;
     } else if (k == "graph") {
@@ -1440,6 +1540,7 @@ int unetb200_get_option(unetb200_handle_t h, const char* key, int* value) {
     else if (k == "fold_up") *value = h->fold_up & h->fold_avail;
     else if (k == "fold_avail") *value = h->fold_avail;
     else if (k == "fold_one_phase") *value = h->fold_one_phase;
+    else if (k == "ps64") *value = h->ps64;
     else if (k == "graph") *value = h->graph;
     else if (k == "profile") *value = h->profile;
     else if (k == "num_sms") *value = h->num_sms;
