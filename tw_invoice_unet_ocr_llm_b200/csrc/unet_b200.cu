@@ -1105,7 +1105,7 @@ struct unetb200_handle_s {
                                 // bit 1 = conv1.net.0 (measured 3-5 % faster, on)
     int fold_up = 15;           // bit k: decoder level k (H >> k; bit 3 = up4 + conv4.net.0) runs as ONE launch with the
                                 // up-conv folded into the 3x3 conv (conv_phase.cuh); masked by `fold_avail`
-    int ps64 = 0;               // 64 -> 64 channel convs on the phase-stacked kernel (conv_ps64.cuh): bit 0 = down1.net.3,
+    int ps64 = 3;               // 64 -> 64 channel convs on the phase-stacked kernel (conv_ps64.cuh): bit 0 = down1.net.3,
                                 // bit 1 = conv1.net.3 + head
     int fold_one_phase = 0;     // A/B: folded levels run one phase per work unit whatever the column block
     int fold_avail = 0;         // levels whose composite weights were packed into the blob (unetb200_pack_fused_up)
