@@ -171,7 +171,8 @@ int unetb200_convt2x2(const void* src, int cin, const void* w_packed, const floa
  * low [N,h,w,c_low] bf16, skip [N,2h,2w,c_skip] bf16 -> out [N,2h,2w,cout] bf16.  wc_packed / bias9 = the regions
  * unetb200_pack_fused_up writes (unetb200_fused_up_info), w3_packed = the 3x3 conv's own packed weights
  * ([9][cout][c_up + c_skip], unetb200_pack_layer), c_up = K columns of its up half.
- * flags: bit 0 = CTA pairs, bit 1 = one phase per work unit whatever the column block (cross-check variant). */
+ * flags: bit 0 = CTA pairs, bit 1 = one phase per work unit whatever the column block (cross-check variant),
+ * bit 2 = the phase-stacked kernel (csrc/conv_phase_stack.cuh) where it applies: cout = c_skip = 64, CTA pairs. */
 int unetb200_upconv3x3(const void* low, int c_low, const void* skip, int c_skip, const void* wc_packed,
                        const void* w3_packed, int c_up, const float* bias9, int n, int h_low, int w_low, int cout,
                        int relu, void* out, int bn, int flags, void* stream);

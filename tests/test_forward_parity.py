@@ -238,6 +238,31 @@ def test_folded_upconv_forward(model, fixture_state, cuda_dev, n, h, w, seed):
         eng.set_option("fold_one_phase", keep1)
 
 
+@pytest.mark.parametrize("n,h,w,seed", [(2, 64, 96, 91), (1, 512, 512, 92), (3, 16, 16, 93), (5, 48, 272, 94)])
+def test_phase_stacked_level1_forward(model, fixture_state, cuda_dev, n, h, w, seed):
+    """Folded level 1 (up1 + conv1.net.0) on the phase-stacked kernel (csrc/conv_phase_stack.cuh; option fold_stack):
+    meets the oracle gates; against the phase-per-UMMA kernel the logits differ only by fp32 accumulation order."""
+    from oracle.unet_oracle import oracle_forward, parity_report
+    from tw_invoice_unet_ocr_llm_b200.synthetic import synthetic_invoices
+    eng = model.engine(cuda_dev)
+    keep = eng.get_option("fold_stack")
+    x = synthetic_invoices(n, h, w, seed=seed)
+    z_ref = oracle_forward(fixture_state, x)
+    try:
+        res = {}
+        for v in (0, 1):
+            eng.set_option("fold_stack", v)
+            z = eng.run(x.to(cuda_dev))[0]
+            torch.cuda.synchronize()
+            assert eng.last_launch_count() == 18
+            _check(parity_report(z_ref, z), 0.999 if h >= 512 else 0.997)
+            res[v] = z
+        d = (res[1] - res[0]).abs()
+        assert float(d.max()) <= 0.1 and float(d.mean()) <= 0.01, (float(d.max()), float(d.mean()))
+    finally:
+        eng.set_option("fold_stack", keep)
+
+
 @pytest.mark.parametrize("n,h,w,seed", [(2, 64, 96, 81), (1, 512, 512, 82), (3, 16, 16, 83), (1, 48, 272, 84)])
 def test_phase_stacked_64ch_forward(model, fixture_state, cuda_dev, n, h, w, seed):
     """down1.net.3 (+ pool) and conv1.net.3 (+ head) on the phase-stacked kernel (csrc/conv_ps64.cuh; option ps64,

@@ -144,6 +144,27 @@ def _same_operand_ref(xlow_b, skip_b, wc, w3_skip, b9, relu=True):
     (4, 256, 1, 2, 2),       # two column blocks of 256, 16 + 8 K slices
 ])
 def test_upconv3x3(cuda_dev, level, bn, n, h, w, pair):
+    _run_upconv3x3(cuda_dev, level, bn, n, h, w, pair)
+
+
+@pytest.mark.parametrize("n,h,w", [
+    (2, 16, 8),        # one full tile per image: one work unit
+    (1, 24, 20),       # partial tiles in both directions
+    (3, 16, 8),        # odd tile count (pair tail)
+    (1, 1, 1),         # 2x2 output, every pixel a corner
+    (4, 128, 128),     # 256 work units: several per CTA pair (ring wrap-around, both accumulators)
+])
+def test_upconv3x3_phase_stacked(cuda_dev, n, h, w):
+    """Level 1 (up1 + conv1.net.0) on the phase-stacked kernel (csrc/conv_phase_stack.cuh, flags bit 2): same gates as
+    the phase-per-UMMA kernel, and within fp32 accumulation-order noise of it."""
+    got = _run_upconv3x3(cuda_dev, 1, 64, n, h, w, 5)
+    base = _run_upconv3x3(cuda_dev, 1, 64, n, h, w, 1)
+    d = (got - base).abs()
+    assert float((d - base.abs() * 2.0 ** -7).max()) <= 2e-3, float(d.max())
+    assert float((d > 0).float().mean()) < 0.2, "more than rounding-boundary differences"
+
+
+def _run_upconv3x3(cuda_dev, level, bn, n, h, w, pair):
     nat = _nat()
     p, clow, c, cout = _level_tensors(level, cuda_dev, 3 * level + h)
     blob, layer, (w_off, w_bytes, b_off, b_bytes) = _pack(level, p, cuda_dev)
@@ -175,3 +196,4 @@ def test_upconv3x3(cuda_dev, level, bn, n, h, w, pair):
     z = F.conv2d(torch.cat([up, _to_nchw_f32(skip_b)], dim=1), p["w3"], p["b3"], padding=1)
     z = F.relu((z - p["mean"][None, :, None, None]) * s[None, :, None, None] + p["beta"][None, :, None, None])
     assert float((got - z).abs().max()) <= 0.02 * float(z.abs().max()), float((got - z).abs().max())
+    return got

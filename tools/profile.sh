@@ -16,11 +16,12 @@ echo "launch list rc=$?"
 ncu --set full --clock-control none -s $((4 * L)) -c $L -o /tmp/ncu/all -f $CMD > $out/ncu_all_$tag.log 2>&1
 echo "full set rc=$?"
 ncu -i /tmp/ncu/all.ncu-rep --page raw --csv > $out/prof_${tag}_raw.csv 2> /dev/null
-# source-level capture of the two multi-phase folded kernels (conv2.net.0, conv1.net.0) of the 5th forward
-for j in 0 1; do
-  ncu --set full --clock-control none --import-source on -k regex:conv_phase_multi -s $((8 + j)) -c 1 \
-      -o /tmp/ncu/pm$j -f $CMD > $out/ncu_pm${j}_$tag.log 2>&1
-  ncu -i /tmp/ncu/pm$j.ncu-rep --page source --csv > $out/src_pm${j}_$tag.csv 2>/dev/null
+# source-level capture of the folded kernels of levels 2 and 1 (conv2.net.0: conv_phase_multi, conv1.net.0: conv_phase_stack64), 5th forward
+for spec in pm0:conv_phase_multi pm1:conv_phase_stack64; do
+  IFS=: read -r j rx <<< "$spec"
+  ncu --set full --clock-control none --import-source on -k regex:$rx -s 4 -c 1 \
+      -o /tmp/ncu/$j -f $CMD > $out/ncu_${j}_$tag.log 2>&1
+  ncu -i /tmp/ncu/$j.ncu-rep --page source --csv > $out/src_${j}_$tag.csv 2>/dev/null
 done
 echo "source rc=$?"
 ls -la $out/ | tail -n 12

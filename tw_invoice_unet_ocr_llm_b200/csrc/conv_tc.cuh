@@ -106,6 +106,8 @@ struct ConvParams {
     CUtensorMap tmPool;      // pooled output store map
     CUtensorMap tmP[4];      // conv_phase.cuh: the four (row, column) parity planes of the skip tensor, dims (C, W/2, H/2, N)
     CUtensorMap tmB2;        // conv_phase.cuh: the 3x3 conv's own packed weights (skip half of K), dims (Cin_total, rows, 9)
+    CUtensorMap tmB3, tmB4;  // conv_phase_stack.cuh: the 3x3 conv's weights as boxes of 64 / 32 rows x one tap (tmB / tmB2 there: the
+                             // composite weights as boxes of 64 / 32 rows x one tap)
     const float* bias9;      // conv_phase.cuh: [9 border cases][Cout] fp32 (folded bias + the up-conv bias seen through the in-range taps)
     int kskip;               // conv_phase.cuh: first K column of the skip half in tmB2 (= channels of the up-conv output)
     const float* bias;       // [Cout] fp32 (BatchNorm-folded)

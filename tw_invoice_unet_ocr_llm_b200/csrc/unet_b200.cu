@@ -21,6 +21,7 @@
 #include "conv_phase.cuh"
 #include "conv_phase_multi.cuh"
 #include "conv_ps64.cuh"
+#include "conv_phase_stack.cuh"
 #include "errors.h"
 #include "pack.cuh"
 #include "prepost.cuh"
@@ -597,6 +598,7 @@ struct PhaseDesc {
     void* out = nullptr;            // [N][2h][2w][cout] bf16
     int bn = 256, pair = 1;
     int one_phase = 0;              // 1 = one phase per unit whatever the column block (cross-check / A-B variant)
+    int stack = 0;                  // 1 = phase-stacked kernel (conv_phase_stack.cuh) where it applies: 64 output and 64 skip channels, CTA pairs
     int* dbg = nullptr;
 };
 
@@ -641,6 +643,13 @@ int build_phase_step(const PhaseDesc& d, int num_sms, Step* st) {
     else if (bn == 128) phase_multi_inst<128, 1, 2>(pair, &cl, &box_w, &box_h, &nph);
     else if (d.one_phase) phase_inst<64>(pair, &cl, &box_w, &box_h, &nph);
     else phase_multi_inst<64, 2, 2>(pair, &cl, &box_w, &box_h, &nph);
+    // phase-stacked form of the 2 x 2 kernel (conv_phase_stack.cuh): resident skip-half images, CTA-specific stages
+    const bool stack = d.stack && bn == 64 && pair && !d.one_phase && d.cout == 64 && d.c_skip == 64;
+    if (stack) {
+        cl.fn = ub::conv_phase_stack64_kernel;
+        cl.a_stage = ub::kPsSlot;
+        box_w = ub::kPsBoxW; box_h = ub::kPsBoxH; nph = 4;
+    }
     cl.b_tap = (pair ? bn / 2 : bn) * 128;
     const bool multi = nph > 1;                  // conv_phase_multi.cuh: weight stages of 4 composite / 3 skip taps
     cl.b_stage = multi ? 4 * cl.b_tap : cl.b_tap;
@@ -665,6 +674,15 @@ int build_phase_step(const PhaseDesc& d, int num_sms, Step* st) {
     }
     if ((rc = make_w_map(&p.tmB, d.wc, d.c_low, d.cout, 16, pair ? bn / 2 : bn, multi ? 4 : 1))) return rc;
     if ((rc = make_w_map(&p.tmB2, d.w3, d.c_up + d.c_skip, d.cout, 9, pair ? bn / 2 : bn, multi ? 3 : 1))) return rc;
+    p.tmB3 = p.tmB2; p.tmB4 = p.tmB2;
+    if (stack) {
+        if ((rc = make_w_map(&p.tmB, d.wc, d.c_low, 64, 16, 64, 1))) return rc;
+        if ((rc = make_w_map(&p.tmB2, d.wc, d.c_low, 64, 16, 32, 1))) return rc;
+        if ((rc = make_w_map(&p.tmB3, d.w3, d.c_up + d.c_skip, 64, 9, 64, 1))) return rc;
+        if ((rc = make_w_map(&p.tmB4, d.w3, d.c_up + d.c_skip, 64, 9, 32, 1))) return rc;
+        // the interior border case (row 4 of bias9) as kernel parameters: constant-bank operands of the epilogue's FADDs
+        UB_CUDA(cudaMemcpy(p.bias_c, d.bias9 + 4 * 64, sizeof p.bias_c, cudaMemcpyDeviceToHost));
+    }
     p.bias9 = d.bias9;
     p.kskip = d.c_up;
     p.dbg = d.dbg;
@@ -684,20 +702,24 @@ int build_phase_step(const PhaseDesc& d, int num_sms, Step* st) {
     if (multi) nb = (bn == 128 ? 98304 : 65536) / cl.b_stage;   // 96 / 64 KB of weight stages (pairs: 3 / 4 stages), the rest is activation slots (one box each)
     if (multi && nb < 2) nb = 2;
     if (nb > ub::kMaxRing) nb = ub::kMaxRing;
+    // stacked: [A ring][up-half stages][resident skip images 72 KB][staging]: three stages leave three box slots
+    const int resident = stack ? ub::kPsWBytes : 0;
+    if (stack) nb = 3;
     int n_out = 2;
     const int n_epi = 1;
-    int na = (budget - n_epi * n_out * ub::kOutStage - nb * cl.b_stage) / cl.a_stage;
+    int na = (budget - n_epi * n_out * ub::kOutStage - nb * cl.b_stage - resident) / cl.a_stage;
     if (na < 3) {                                // (the unpaired cross-check variants: full-height weight stages)
         n_out = 1;
-        na = (budget - n_epi * n_out * ub::kOutStage - nb * cl.b_stage) / cl.a_stage;
+        na = (budget - n_epi * n_out * ub::kOutStage - nb * cl.b_stage - resident) / cl.a_stage;
     }
     if (na > ub::kMaxRing) na = ub::kMaxRing;
     if (na < (multi ? 3 : 2)) return fail(UNETB200_EINVAL, "fused up-conv: shared memory plan does not fit");
     p.na = na; p.nb = nb; p.wstat = 0; p.n_out = n_out; p.n_epi = n_epi;
     p.off_b = na * cl.a_stage;
-    p.off_out = p.off_b + nb * cl.b_stage;
+    p.off_out = p.off_b + nb * cl.b_stage + resident;
     p.off_pool = p.off_out + n_epi * n_out * ub::kOutStage;
     p.off_bar = p.off_pool;
+    if (stack) p.off_pool = p.off_b + nb * cl.b_stage;      // (the resident images' offset in this kernel)
     p.off_patch = p.off_bar + ub::kBarBytes;
     cl.smem = p.off_patch + bias_bytes + 1024;
     p.fd_tpi = ub::make_fastdiv(static_cast<uint32_t>(p.tiles_x * p.tiles_y));
@@ -1109,6 +1131,7 @@ struct unetb200_handle_s {
                                 // up-conv folded into the 3x3 conv (conv_phase.cuh); masked by `fold_avail`
     int ps64 = 3;               // 64 -> 64 channel convs on the phase-stacked kernel (conv_ps64.cuh): bit 0 = down1.net.3,
                                 // bit 1 = conv1.net.3 + head
+    int fold_stack = 1;         // folded level 1 (up1 + conv1.net.0) on the phase-stacked kernel (conv_phase_stack.cuh)
     int fold_one_phase = 0;     // A/B: folded levels run one phase per work unit whatever the column block
     int fold_avail = 0;         // levels whose composite weights were packed into the blob (unetb200_pack_fused_up)
     std::vector<FusedUp> fused;
@@ -1237,7 +1260,7 @@ int build_plan(unetb200_handle_t h, const void* x, int x_fmt, int n, int H, int 
             d.bias9 = reinterpret_cast<const float*>(h->blob + f.b_off);
             d.n = n; d.h = H >> (k + 1); d.wd = W >> (k + 1); d.cout = f.cout; d.relu = 1;
             d.out = P(L.ca[k]); d.bn = h->bn_max; d.pair = h->pair >= 1; d.dbg = h->dbg;
-            d.one_phase = h->fold_one_phase;
+            d.one_phase = h->fold_one_phase; d.stack = h->fold_stack;
             Step st;
             if ((rc = build_phase_step(d, h->num_sms, &st))) return rc;
             st.layer = li_up + 1;
@@ -1437,6 +1460,8 @@ int unetb200_create(const unetb200_arch_t* arch, const void* blob_dev, uint64_t 
     if (env) h->fold_up = atoi(env) & 15;
     env = getenv("UNETB200_PS64");
     if (env) h->ps64 = atoi(env) & 3;
+    env = getenv("UNETB200_FOLD_STACK");
+    if (env) h->fold_stack = atoi(env) ? 1 : 0;
     env = getenv("UNETB200_FOLD_ONE_PHASE");
     if (env) h->fold_one_phase = atoi(env) ? 1 : 0;
     env = getenv("UNETB200_AMODE");
@@ -1514,6 +1539,8 @@ int unetb200_set_option(unetb200_handle_t h, const char* key, int value) {
         h->ps64 = value;
     } else if (k == "fold_one_phase") {
         h->fold_one_phase = value ? 1 : 0;
+    } else if (k == "fold_stack") {
+        h->fold_stack = value ? 1 : 0;
     } else if (k == "graph") {
         h->graph = value ? 1 : 0;
     } else if (k == "profile") {
@@ -1542,6 +1569,7 @@ int unetb200_get_option(unetb200_handle_t h, const char* key, int* value) {
     else if (k == "fold_up") *value = h->fold_up & h->fold_avail;
     else if (k == "fold_avail") *value = h->fold_avail;
     else if (k == "fold_one_phase") *value = h->fold_one_phase;
+    else if (k == "fold_stack") *value = h->fold_stack;
     else if (k == "ps64") *value = h->ps64;
     else if (k == "graph") *value = h->graph;
     else if (k == "profile") *value = h->profile;
@@ -1781,7 +1809,7 @@ int unetb200_upconv3x3(const void* low, int c_low, const void* skip, int c_skip,
     PhaseDesc d;
     d.low = low; d.c_low = c_low; d.skip = skip; d.c_skip = c_skip; d.wc = wc_packed; d.w3 = w3_packed;
     d.c_up = c_up; d.bias9 = bias9; d.n = n; d.h = h_low; d.wd = w_low; d.cout = cout; d.relu = relu; d.out = out;
-    d.bn = bn; d.pair = flags & 1; d.one_phase = (flags >> 1) & 1; d.dbg = g_hook_dbg();
+    d.bn = bn; d.pair = flags & 1; d.one_phase = (flags >> 1) & 1; d.stack = (flags >> 2) & 1; d.dbg = g_hook_dbg();
     int sms = 0;
     if ((rc = device_num_sms(&sms))) return rc;
     Step st;
