@@ -164,12 +164,14 @@ def test_weight_stationary_identical(model, cuda_dev):
 
 def test_cta_pairs_identical(model, cuda_dev):
     """cta_group::2 launches (one M = 256 UMMA over two CTAs) accumulate every output element in
-    the same order as two M = 128 UMMAs: bit-identical logits.  3 x 48 x 80 gives odd tile counts."""
+    the same order as two M = 128 UMMAs: bit-identical logits.  3 x 48 x 80 gives odd tile counts.
+    (The phase-stacked level-1 kernel exists as a pair kernel only and walks K in another order: fold_stack off.)"""
     from tw_invoice_unet_ocr_llm_b200.synthetic import synthetic_invoices
     x = synthetic_invoices(3, 48, 80, seed=50).to(cuda_dev)
     eng = model.engine(cuda_dev)
-    keep = eng.get_option("pair")
+    keep, keep_st = eng.get_option("pair"), eng.get_option("fold_stack")
     try:
+        eng.set_option("fold_stack", 0)
         eng.set_option("pair", 0)
         z0, _ = eng.run(x)
         eng.set_option("pair", 1)
@@ -177,6 +179,7 @@ def test_cta_pairs_identical(model, cuda_dev):
         torch.cuda.synchronize()
     finally:
         eng.set_option("pair", keep)
+        eng.set_option("fold_stack", keep_st)
     assert torch.equal(z0, z1)
 
 
