@@ -93,7 +93,7 @@ def ncu_traffic_bytes(n_launches=None):
         h, unit, data = rows[0], rows[1], rows[2:]
         ir, iw, ik = h.index("dram__bytes_read.sum"), h.index("dram__bytes_write.sum"), h.index("Kernel Name")
         scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[unit[ir]]
-        conv = [r for r in data if "conv_tc_kernel" in r[ik] or "conv_row_kernel" in r[ik] or "conv_phase" in r[ik]]
+        conv = [r for r in data if any(k in r[ik] for k in ("conv_tc_kernel", "conv_row_kernel", "conv_phase", "conv_ps64"))]
         tc = [r for r in conv if "conv_tc_kernel<64, 1, 3," not in r[ik]
               and "(int)64, (int)1, (int)3" not in r[ik]]            # all launches but the stem (A_STEM)
         if len(tc) != len(conv) - 1 or (n_launches is not None and len(conv) != n_launches):
