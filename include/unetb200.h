@@ -112,9 +112,12 @@ int unetb200_destroy(unetb200_handle_t h);
 /* options: "amode" (UNETB200_A_*), "bn_max" (64/128/256), "wstat" (0/1), "stem_tc" (first conv: 0 CUDA cores / 1 tensor cores + im2col / 2 tensor cores, implicit GEMM), "pair" (0 never / 1 everywhere / 2 auto),
  * "pdl" (0/1 programmatic dependent launch), "epi2" (two epilogue groups: 0 never / 1 weight-stationary launches / 2 always), "pf_items" (0..64), "profile" (0/1),
  * "row64" (64-output-channel 3x3 convs on the row-stacked kernel csrc/conv_row.cuh: bit 0 = down1.net.3 and conv1.net.3, bit 1 = conv1.net.0; default 2; results are bit-identical either way),
+ * "fold_up" (bit k = decoder level k: ConvTranspose2d folded into the following 3x3 conv, csrc/conv_phase*.cuh; default 15 = every level, one launch each),
+ * "fold_one_phase" (0/1 cross-check: folded levels run one phase per work unit), "fold_stack" (0/1, default 1: folded level 1 on the phase-stacked kernel csrc/conv_phase_stack.cuh),
+ * "ps64" (bit 0 = down1.net.3, bit 1 = conv1.net.3 on the phase-stacked kernel csrc/conv_ps64.cuh; default 3; results differ from the tap-per-UMMA kernels by fp32 accumulation order only),
  * "fill_sms" (0/1/2 small-batch column-block policy), "min_na" (2..8),
  * "graph" (0/1, default 1: from its second use on, a forward of the same shape / buffers is replayed as one CUDA graph --
- *  one cudaGraphLaunch instead of 22 kernel launches; skipped while profiling or inside a caller's stream capture) */
+ *  one cudaGraphLaunch instead of 18 kernel launches; skipped while profiling or inside a caller's stream capture) */
 int unetb200_set_option(unetb200_handle_t h, const char* key, int value);
 int unetb200_get_option(unetb200_handle_t h, const char* key, int* value);
 
