@@ -262,6 +262,8 @@ def main():
                     help="skip the informational sections (batch-1 latency, run_unet, crop enhancement): profiling runs")
     ap.add_argument("--layers-out", default=None, help="write the per-layer table (JSON) here")
     ap.add_argument("--graph", type=int, default=0, help="1: replay the step as a CUDA graph")
+    ap.add_argument("--settle", type=float, default=2.0,
+                    help="idle seconds before the end-to-end region's warm-up (same power state as the device-timed region's start)")
     ap.add_argument("--e2e-chunk", type=int, default=64,
                     help="images per forward inside the end-to-end call (copies of chunk i+1 overlap chunk i)")
     args = ap.parse_args()
@@ -462,6 +464,13 @@ def main():
             worker.segment_async(frames_host, masks_host if i % 2 == 0 else masks_alt)
         worker.join_current_stream()
 
+    # The GPUs of this pool are power-capped: SM clocks sink from 1.97 to ~1.4 GHz during the first second of load
+    # (profiles/r02d_bench_long_300steps.json), so a region timed later in the process is slower whatever it does.
+    # `value` above was timed W warm-up steps after an idle GPU; give this region the same start: idle, W warm-up
+    # steps, K timed steps.  (`device_ms_per_step_right_after` below remains the partner measured in the state the
+    # end-to-end region leaves behind.)
+    sync_all()
+    time.sleep(args.settle)
     e2e_run(args.warmup)
     worker.synchronize()
     e2e_ms = timed(lambda: e2e_run(args.steps), 1) / args.steps
@@ -473,7 +482,7 @@ def main():
     e2e = {"value": world * B / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms,
            "device_ms_per_step_right_after": dev_after_ms, "ratio_to_device_right_after": dev_after_ms / e2e_ms,
            "h2d_bytes_per_step": int(frames_host.numel()), "d2h_bytes_per_step": int(masks_host.numel()),
-           "chunk": worker.chunk,
+           "chunk": worker.chunk, "settle_s": args.settle,
            "api": "tw_invoice_unet_ocr_llm_b200.launcher.GpuWorker(packed=True).segment_async + synchronize (pinned "
                   "uint8 frames -> pinned bit-packed masks [B,3,H,W/8], double-buffered across steps)"}
 
