@@ -45,7 +45,7 @@ namespace ub {
 
 constexpr int kStBStage = 16384;                 // up-half weight stage: 128 rows x 128 B per CTA
 
-__global__ void __launch_bounds__(384, 1) conv_phase_stack64_kernel(const __grid_constant__ ConvParams p) {
+__global__ void __launch_bounds__(256, 1) conv_phase_stack64_kernel(const __grid_constant__ ConvParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t sA = smem_base;                       // activation ring: one 18 x 10 box per slot (kPsSlot)
@@ -289,8 +289,8 @@ __global__ void __launch_bounds__(384, 1) conv_phase_stack64_kernel(const __grid
                 }
             }
         }
-    } else if (warp >= 4 && warp < 8) {
-        // ============================= epilogue ===============================
+    } else if (warp >= 4) {
+        // ============================= epilogue (warps 4-7: the kernel runs 256 threads) ===============================
         const int q = warp & 3;                 // TMEM lane quarter
         const int row = q * 32 + lane;          // tile position: I = y0 + row / 8, J = x0 + row % 8
         uint32_t tile_it = 0, chunk_it = 0;

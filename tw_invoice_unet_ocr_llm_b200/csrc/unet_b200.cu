@@ -733,7 +733,7 @@ int build_phase_step(const PhaseDesc& d, int num_sms, Step* st) {
     } else {
         st->grid = dim3(static_cast<unsigned>(units < num_sms ? units : num_sms));
     }
-    st->block = dim3(384);
+    st->block = dim3(stack ? 256 : 384);         // (the stacked kernel has one epilogue group: 8 warps)
     return 0;
 }
 
