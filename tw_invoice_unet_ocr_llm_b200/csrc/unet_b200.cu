@@ -599,6 +599,7 @@ struct PhaseDesc {
     int bn = 256, pair = 1;
     int one_phase = 0;              // 1 = one phase per unit whatever the column block (cross-check / A-B variant)
     int stack = 0;                  // 1 = phase-stacked kernel (conv_phase_stack.cuh) where it applies: 64 output and 64 skip channels, CTA pairs
+    int fill_sms = 0;               // small batches: 128-column blocks on the one-phase kernel when 256-column units do not cover the SMs
     int* dbg = nullptr;
 };
 
@@ -630,6 +631,21 @@ int build_phase_step(const PhaseDesc& d, int num_sms, Step* st) {
     while (d.cout % bn) bn >>= 1;
     if (!(bn == 64 || bn == 128 || bn == 256)) return fail(UNETB200_EINVAL, "fused up-conv: bad column block");
     const bool pair = d.pair != 0;
+    // Batch-1 latency (BASELINE configs[4]), as in build_conv_step: the deepest folded level has 8 tile positions per
+    // image, so its 256-column units (4 phases x 2 blocks x 4 pairs = 32) leave most SMs idle; the SAME one-phase kernel
+    // with 128-column blocks has twice the units at a lower tensor-pipe rate (0.70 vs 0.985, profiles/) and the same K
+    // order per output element -> same bits.  Larger batches keep the wide blocks.
+    bool narrow = false;
+    if (d.fill_sms && bn == 256 && !d.one_phase && d.cout % 128 == 0) {
+        const long long mt = 1LL * ((d.wd + 7) / 8) * ((d.h + 15) / 16) * d.n;
+        const long long mu = pair ? (mt + 1) / 2 : mt;
+        const long long slots = pair ? num_sms / 2 : num_sms;
+        auto cost = [&](int b, double eff) {
+            const long long units = mu * 4 * (d.cout / b);
+            return static_cast<double>((units + slots - 1) / slots) * b / eff;
+        };
+        if (cost(128, 0.70) < 0.97 * cost(256, 0.985)) { bn = 128; narrow = true; }
+    }
     st->kind = 1;
     ConvLaunch& cl = st->conv;
     cl = ConvLaunch();
@@ -639,7 +655,7 @@ int build_phase_step(const PhaseDesc& d, int num_sms, Step* st) {
     // (conv_phase_multi.cuh); one_phase forces the one-phase kernel (cross-check / A-B)
     int box_w = 0, box_h = 0, nph = 1;
     if (bn == 256) phase_inst<256>(pair, &cl, &box_w, &box_h, &nph);
-    else if (bn == 128 && d.one_phase) phase_inst<128>(pair, &cl, &box_w, &box_h, &nph);
+    else if (bn == 128 && (d.one_phase || narrow)) phase_inst<128>(pair, &cl, &box_w, &box_h, &nph);
     else if (bn == 128) phase_multi_inst<128, 1, 2>(pair, &cl, &box_w, &box_h, &nph);
     else if (d.one_phase) phase_inst<64>(pair, &cl, &box_w, &box_h, &nph);
     else phase_multi_inst<64, 2, 2>(pair, &cl, &box_w, &box_h, &nph);
@@ -1260,7 +1276,7 @@ int build_plan(unetb200_handle_t h, const void* x, int x_fmt, int n, int H, int 
             d.bias9 = reinterpret_cast<const float*>(h->blob + f.b_off);
             d.n = n; d.h = H >> (k + 1); d.wd = W >> (k + 1); d.cout = f.cout; d.relu = 1;
             d.out = P(L.ca[k]); d.bn = h->bn_max; d.pair = h->pair >= 1; d.dbg = h->dbg;
-            d.one_phase = h->fold_one_phase; d.stack = h->fold_stack;
+            d.one_phase = h->fold_one_phase; d.stack = h->fold_stack; d.fill_sms = h->fill_sms;
             Step st;
             if ((rc = build_phase_step(d, h->num_sms, &st))) return rc;
             st.layer = li_up + 1;
